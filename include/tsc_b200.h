@@ -1,0 +1,239 @@
+/* tsc_b200.h -- C ABI of the B200-native batched traffic-signal-control engine.
+ *
+ * This library replaces, for B scenario replicas at once, the one native object
+ * the reference's CityFlow backend drives: `cityflow.Engine` (third-party
+ * C++/pybind11, not vendored by the reference).  Each entry point cites the
+ * reference interface it stands in for (paths relative to the reference repo).
+ *
+ *   cityflow.Engine(config_file, thread_num)   pytsc/backends/cityflow/simulator.py:71-74   -> tsc_create
+ *   engine.reset()                             simulator.py:95                              -> tsc_reset
+ *   engine.set_tl_phase(id, phase)             backends/cityflow/traffic_signal.py:31,58    -> tsc_set_phase
+ *   engine.next_step()  (x delta_time)         simulator.py:76-77,86-88                     -> tsc_step
+ *   engine.get_lane_waiting_vehicle_count()    retriever.py:95   \
+ *   engine.get_lane_vehicles()                 retriever.py:96    |
+ *   engine.get_vehicle_speed()                 retriever.py:97    |  one call, batched      -> tsc_retrieve
+ *   engine.get_vehicle_info(v)                 retriever.py:35    |
+ *   engine.get_vehicle_count()                 retriever.py:109   |
+ *   engine.get_average_travel_time()           retriever.py:110   |
+ *   engine.get_current_time()                  simulator.py:50, retriever.py:111           /
+ *   TrafficSignalNetwork.step(actions)         pytsc/__init__.py:178-182  (fused fast path) -> tsc_env_step
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types; `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream).
+ *   - every function returns 0 on success, a negative TSC_E* code otherwise;
+ *     tsc_last_error() gives the message.  No exceptions cross the ABI.
+ *   - the handle owns all simulation state on one device.  Callers own input /
+ *     output buffers; pointers documented "device" must be device memory of the
+ *     handle's device, "host" pointers are ordinary host memory.
+ *   - nothing synchronises the stream except tsc_snapshot, tsc_check and the
+ *     *_host convenience calls.  One handle must not be used from two threads
+ *     at once.
+ *   - device-side capacity overflows / ordering violations set a sticky
+ *     per-replica flag that tsc_check reports.
+ */
+#ifndef TSC_B200_H
+#define TSC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSC_ABI_VERSION 1
+
+enum {
+    TSC_OK = 0,
+    TSC_EINVAL = -1,      /* bad argument / scenario table */
+    TSC_ECUDA = -2,       /* CUDA runtime error (message has the detail) */
+    TSC_ENOMEM = -3,      /* replica state does not fit in shared memory on this device */
+    TSC_EOVERFLOW = -4,   /* a replica exceeded vehicle_capacity (sticky flag, see tsc_check) */
+    TSC_EORDER = -5       /* a vehicle left its drivable out of FIFO order (sticky flag) */
+};
+
+/* vehicle template row layout (doubles) */
+enum {
+    TSC_T_LEN = 0, TSC_T_MAX_POS_ACC, TSC_T_MAX_NEG_ACC, TSC_T_USUAL_POS_ACC, TSC_T_USUAL_NEG_ACC,
+    TSC_T_MIN_GAP, TSC_T_MAX_SPEED, TSC_T_HEADWAY, TSC_T_YIELD_DIST, TSC_T_TURN_SPEED, TSC_T_APPROACH_DIST,
+    TSC_T_STRIDE = 12
+};
+
+enum { TSC_REWARD_QUEUE = 0, TSC_REWARD_PRESSURE = 1 };
+enum { TSC_OBS_LANE_FEATURES = 0, TSC_OBS_POSITION_MATRIX = 1 };
+enum { TSC_ACT_PHASE_SELECTION = 0, TSC_ACT_PHASE_SWITCH = 1 };
+enum { TSC_CTRL_EXTERNAL = 0, TSC_CTRL_FIXED_TIME = 1 };
+
+/* A compiled scenario: flat, read-only tables built on the host by
+ * pytsc_b200.scenario.compile_scenario().  All pointers are HOST pointers,
+ * borrowed for the duration of tsc_create only (the library copies them to the
+ * device).  Drivable index d: lanes 0..n_lanes-1 (roadnet road order, lane
+ * order), lane-links n_lanes..n_lanes+n_lanelinks-1 (intersection order,
+ * road-link order, lane-link order).  Signals ("agents") are the non-virtual
+ * intersections in roadnet order -- the order of pytsc's traffic_signals dict
+ * (backends/cityflow/network_parser.py:49-78). */
+typedef struct tsc_scenario {
+    int32_t abi_version;          /* TSC_ABI_VERSION */
+    int32_t n_lanes, n_lanelinks, n_signals;
+    int32_t n_vehicles;           /* spawn list length N (vehicles the flows create within horizon_ticks) */
+    int32_t n_templates;
+    int32_t n_route_seq;          /* length of route_seq */
+    int32_t n_cross_entries;      /* length of xr_* (two per cross) */
+    int32_t horizon_ticks;        /* ticks the spawn list covers (sim_length + initial_wait_time) */
+    int32_t max_raw_phases;       /* row stride of sig_phase_mask */
+    int32_t max_phases;           /* P: row stride of the pytsc phase tables */
+    int32_t n_in_total, n_out_total, n_nbr_total;
+
+    /* --- engine tables (CityFlow semantics) --- */
+    const double  *drv_length;        /* [D] */
+    const double  *drv_max_speed;     /* [D] lane-links: 10000 */
+    const int32_t *lane_ll_off;       /* [L+1] CSR: lane -> lane-links leaving it (roadnet appearance order) */
+    const int32_t *lane_ll;           /* lane-link index 0..K-1 */
+    const int32_t *lane_spawn_off;    /* [L+1] CSR: lane -> vehicles that start on it, FIFO order */
+    const int32_t *lane_spawn_vid;    /* [N] */
+    const int32_t *ll_start_lane;     /* [K] */
+    const int32_t *ll_end_lane;       /* [K] */
+    const int32_t *ll_signal;         /* [K] signal (agent) index */
+    const int32_t *ll_roadlink;       /* [K] road-link index inside the intersection (bit of the phase mask) */
+    const int32_t *ll_type;           /* [K] 3 go_straight, 2 turn_left, 1 turn_right */
+    const int32_t *ll_cross_off;      /* [K+1] CSR: lane-link -> crosses, ascending distance along the link */
+    const double  *xr_dist;           /* distance of the cross along this lane-link */
+    const int32_t *xr_foe_ll;         /* the other lane-link of the cross */
+    const double  *xr_foe_dist;       /* distance of the cross along the other lane-link */
+    const uint32_t *sig_phase_mask;   /* [A][max_raw_phases] bit r = road-link r available */
+    const int32_t *sig_n_raw_phases;  /* [A] */
+    const int32_t *route_seq;         /* -1, d0, d1, ..., -1, d0, ... drivable sequences, -1 separated, leading -1 */
+    const int32_t *veh_tick;          /* [N] tick at which the flow creates the vehicle (creation order) */
+    const int32_t *veh_seq_start;     /* [N] index into route_seq of the vehicle's first drivable */
+    const int32_t *veh_tmpl;          /* [N] */
+    const int32_t *veh_priority;      /* [N] mt19937 draw (yield tie-break only) */
+    const double  *tmpl;              /* [T][TSC_T_STRIDE] */
+
+    /* --- pytsc tables (Retriever / TrafficSignal / reward / mask / observation) --- */
+    const double  *lane_pytsc_length; /* [L] centre-to-centre road length (network_parser.py:325-352) */
+    const double  *lane_feat;         /* [L][9] static lane features (observations.py:90-116) */
+    const int32_t *sig_in_off;        /* [A+1] CSR incoming lanes, pytsc (sorted id) order */
+    const int32_t *sig_in_lane;
+    const int32_t *sig_out_off;       /* [A+1] CSR outgoing lanes */
+    const int32_t *sig_out_lane;
+    const int32_t *sig_n_phases;      /* [A] number of pytsc phases */
+    const int32_t *sig_phase_raw;     /* [A][P] raw light-phase of pytsc phase p */
+    const uint8_t *sig_phase_green;   /* [A][P] 1 = green index */
+    const int32_t *sig_min_time;      /* [A][P] */
+    const int32_t *sig_max_time;      /* [A][P] */
+    const int32_t *nbr_off;           /* [A+1] CSR: reward neighbours in the reference's summation order */
+    const int32_t *nbr_idx;
+    const double  *nbr_weight;        /* gamma**k */
+
+    /* --- options --- */
+    int32_t reward_type, obs_type, action_space, round_robin;
+    int32_t visibility;               /* bins (signal.visibility) */
+    int32_t yellow_time;              /* == delta_time */
+    int32_t obs_dim, state_dim, n_actions;
+    int32_t reference_exact;          /* reproduce pad_list int truncation (common/utils.py:91-112) */
+    int32_t max_lanes_per_signal;     /* 16 (observations.py max_n_controlled_lanes) */
+    int32_t max_obs_phases;           /* 20 */
+    double  veh_size_min_gap;         /* 7.5 */
+    double  flickering_coef;
+    double  interval;                 /* 1.0 */
+} tsc_scenario_t;
+
+/* Output buffers of tsc_retrieve / tsc_env_step.  DEVICE pointers owned by the
+ * caller; any may be NULL to skip that output.  Shapes in comments; B-major,
+ * contiguous. */
+typedef struct tsc_outputs {
+    int32_t *lane_count;        /* [B][L]  vehicles on lane            (retriever.py:66,78) */
+    int32_t *lane_queued;       /* [B][L]  of those, speed < 0.1       (retriever.py:64,95) */
+    float   *lane_occupancy;    /* [B][L]                               (retriever.py:74-76) */
+    float   *lane_mean_speed;   /* [B][L]                               (retriever.py:67-73) */
+    double  *lane_meas64;       /* [B][L][2] occupancy, mean_speed in fp64 (compatibility view) */
+    float   *pos_in;            /* [B][n_in_total][visibility]  last `visibility` bins   (traffic_signal.py:124) */
+    float   *pos_out;           /* [B][n_out_total][visibility] first `visibility` bins  (traffic_signal.py:135) */
+    double  *sig_stats64;       /* [B][A][8] n_queued, occupancy, mean_speed, mean_delay, out_occupancy,
+                                             pressure, norm_time_on_phase, phase_index   (traffic_signal.py:101-141) */
+    float   *obs;               /* [B][A][obs_dim]    (observations.py:140-160 | 305-329) */
+    float   *state;             /* [B][A][state_dim]  (observations.py:352-374) */
+    float   *reward;            /* [B][A] local rewards (reward.py:67-88 | 115-136) */
+    float   *reward_global;     /* [B]    (reward.py:54-65 | 102-113) */
+    uint8_t *mask;              /* [B][A][n_actions]  (actions.py:119-131 | 169-188) */
+    double  *sim;               /* [B][4] n_vehicles, average_travel_time, time_step, n_finished (retriever.py:101-112) */
+    double  *metrics;           /* [B][8] n_queued, mean_speed, mean_delay, density, pressure, network_flow,
+                                          flickering_signal, norm_mean_speed  (backends/cityflow/metrics.py:221-232) */
+} tsc_outputs_t;
+
+typedef struct tsc_engine *tsc_handle;
+
+/* Library / build information. */
+int  tsc_abi_version(void);
+const char *tsc_last_error(void);
+
+/* Allocate B replicas of `scn` on `device`.  vehicle_capacity = upper bound on
+ * simultaneously running vehicles per replica (slots), 0 = library default. */
+int  tsc_create(const tsc_scenario_t *scn, int32_t n_replicas, int32_t device,
+                int32_t vehicle_capacity, tsc_handle *out);
+void tsc_destroy(tsc_handle h);
+
+/* Sizes the caller needs to allocate outputs. */
+int  tsc_get_dims(tsc_handle h, int32_t *n_replicas, int32_t *n_lanes, int32_t *n_signals,
+                  int32_t *obs_dim, int32_t *state_dim, int32_t *n_actions,
+                  int32_t *n_in_total, int32_t *n_out_total, int32_t *visibility);
+
+/* All replicas back to tick 0, empty network, light phase 0, program state cleared. */
+int  tsc_reset(tsc_handle h, void *stream);
+
+/* raw_phase: device int32 [B][A] raw CityFlow light-phase index per signal. */
+int  tsc_set_phase(tsc_handle h, const int32_t *raw_phase, void *stream);
+
+/* Initialise pytsc's per-signal program (TSProgram.set_initial_phase,
+ * common/traffic_signal.py:83-92; backends/cityflow/traffic_signal.py:26-32):
+ * current phase index = phase_index, time_on_phase = 0, and the raw phase set. */
+int  tsc_init_program(tsc_handle h, int32_t phase_index, void *stream);
+
+/* n_ticks x engine.next_step() on every replica. */
+int  tsc_step(tsc_handle h, int32_t n_ticks, void *stream);
+
+/* Retriever + per-signal stats + reward / mask / observation from the current state. */
+int  tsc_retrieve(tsc_handle h, const tsc_outputs_t *out, void *stream);
+
+/* Fused TrafficSignalNetwork.step: apply actions (device int32 [B][A]; ignored
+ * when controller != TSC_CTRL_EXTERNAL), n_ticks engine ticks, then everything
+ * tsc_retrieve does.  controller_arg = green time for TSC_CTRL_FIXED_TIME
+ * (controllers/controllers.py:26-54). */
+int  tsc_env_step(tsc_handle h, const int32_t *actions, int32_t controller, int32_t controller_arg,
+                  int32_t n_ticks, const tsc_outputs_t *out, void *stream);
+
+/* Same through HOST buffers: copies `actions_host` in, runs the fused step and
+ * copies obs / reward / mask / reward_global back (any may be NULL), then
+ * synchronises.  This is the end-to-end path bench.py times as `e2e`. */
+int  tsc_env_step_host(tsc_handle h, const int32_t *actions_host, int32_t controller, int32_t controller_arg,
+                       int32_t n_ticks, float *obs_host, float *reward_host, uint8_t *mask_host,
+                       float *reward_global_host);
+
+/* Copy the running vehicles of replica b to host arrays of capacity `cap`
+ * (drivable-major, front to back): vehicle id (creation order), drivable,
+ * distance, speed.  Returns the vehicle count (may exceed cap) or <0.  Syncs. */
+int  tsc_snapshot(tsc_handle h, int32_t replica, int32_t cap, int32_t *vid, int32_t *drivable,
+                  double *distance, double *speed, int32_t *blocker_vid, int32_t *enter_ll_time);
+
+/* Load a vehicle snapshot into replica b (test / fixture entry point): n
+ * vehicles given drivable-major front to back.  Syncs. */
+int  tsc_load_snapshot(tsc_handle h, int32_t replica, int32_t n, const int32_t *vid, const int32_t *drivable,
+                       const double *distance, const double *speed, const int32_t *route_pos);
+
+/* Synchronise and report sticky device-side error flags: returns 0 or the most
+ * severe TSC_E* code; *first_bad_replica (may be NULL) gets the replica index. */
+int  tsc_check(tsc_handle h, int32_t *first_bad_replica);
+
+/* Per-replica counters (host arrays of length B, any may be NULL).  Syncs. */
+int  tsc_counters(tsc_handle h, int32_t *tick, int32_t *n_running, int32_t *n_finished, int32_t *n_slots);
+
+/* Number of kernel launches issued through this handle since creation. */
+int64_t tsc_launch_count(tsc_handle h);
+
+/* Name, bytes of dynamic shared memory, threads per block and grid of the step kernel. */
+int  tsc_kernel_info(tsc_handle h, int32_t *smem_bytes, int32_t *threads, int32_t *grid, int32_t *regs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSC_B200_H */

@@ -1,0 +1,1424 @@
+// tsc_b200.cu -- B200 (sm_100a) batched traffic-signal-control engine.
+//
+// One thread block owns one scenario replica for a whole env-step: the
+// replica's packed state image is staged HBM -> shared memory, the phase
+// controller, `n_ticks` CityFlow-semantics ticks and the Retriever /
+// observation / reward / mask reductions all run out of shared memory, and the
+// image is written back once.  HBM therefore sees each vehicle once per
+// env-step (read + write), not once per tick.  See DESIGN.md for the layout and
+// the roofline; include/tsc_b200.h for the ABI and the reference call sites.
+//
+// Engine semantics: SURVEY.md Appendix A (CityFlow restated).  All kinematics
+// are fp64 and compiled with -fmad=false: every operation rounds once, in the
+// order written, so that results are bit-identical to the CPU oracle.
+#include "tsc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ----------------------------------------------------------------------------
+// Device-side views
+// ----------------------------------------------------------------------------
+typedef unsigned char u8;
+typedef unsigned short u16;
+typedef unsigned int u32;
+
+struct DevScn {   // device copies of tsc_scenario_t tables
+    int L, K, D, A, N, T, horizon, max_raw, P;
+    int n_in_total, n_out_total, n_spawn_lanes;
+    const double *drv_length, *drv_max_speed;
+    const int *lane_ll_off, *lane_ll, *lane_spawn_off, *lane_spawn_vid, *spawn_lane;
+    const int *ll_start_lane, *ll_end_lane, *ll_signal, *ll_roadlink, *ll_type, *ll_cross_off;
+    const double *xr_dist, *xr_foe_dist;
+    const int *xr_foe_ll;
+    const u32 *sig_phase_mask;
+    const int *route_seq, *veh_tick, *veh_seq_start, *veh_tmpl, *veh_priority;
+    const double *tmpl;
+    const int *created_cnt;          // [horizon+2] vehicles created before tick t
+    const long long *created_enter;  // [horizon+2] sum of their creation ticks
+    // pytsc tables
+    const double *lane_pytsc_length, *lane_feat;
+    const int *sig_in_off, *sig_in_lane, *sig_out_off, *sig_out_lane;
+    const int *sig_n_phases, *sig_phase_raw, *sig_min_time, *sig_max_time;
+    const u8 *sig_phase_green;
+    const int *nbr_off, *nbr_idx;
+    const double *nbr_weight;
+    int reward_type, obs_type, action_space, round_robin, visibility, yellow_time;
+    int obs_dim, state_dim, n_actions, reference_exact, max_lanes_per_signal, max_obs_phases;
+    double v_size, flick, interval;
+};
+
+struct RepHeader {   // 64 bytes, first thing in every replica image
+    int n_slots;          // slots in use (vehicles + one spare slot per spawn lane)
+    int tick;             // engine step counter
+    int n_running;
+    int n_finished;
+    long long cum_tt;     // sum over finished vehicles of (finish tick - creation tick)
+    long long fin_enter;  // sum of creation ticks of finished vehicles
+    u32 err;              // sticky error bits
+    int n_ent;            // scratch: movers this tick
+    int pad[6];
+};
+static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
+
+#define ERR_OVERFLOW 1u
+#define ERR_ORDER 2u
+#define ERR_ENT_OVERFLOW 4u
+
+struct Layout {
+    int Vcap, ent_cap;
+    // persistent part: identical byte offsets in the HBM image and in shared memory
+    int o_cnt, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
+    int o_pos, o_spd, o_rpos, o_vid, o_ellt, o_blk, o_drv, o_pj, img_bytes;
+    // shared-memory-only scratch
+    int o_vid2, o_drv2, o_ellt2, o_pj2;
+    int o_npos, o_nspd, o_nrpos, o_nblk, o_newslot, o_nflag, o_off, o_leave, o_ent, o_fresh, o_entlist,
+        o_entpos, o_entdrv, o_scan, o_lane_q, smem_bytes;
+};
+
+struct StepArgs {
+    int B;
+    int n_ticks;
+    int apply_actions;     // 0 none, 1 external actions, 2 fixed-time controller
+    int controller_arg;
+    int do_retrieve;
+    int set_raw_phase;     // 1: raw_phase input given
+    int init_program;      // >=0: TSProgram.set_initial_phase(index)
+    const int *actions;    // [B][A]
+    const int *raw_phase;  // [B][A]
+    tsc_outputs_t out;
+};
+
+// ----------------------------------------------------------------------------
+// Small device helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double min2(double x, double y) { return x < y ? x : y; }
+__device__ __forceinline__ double max2(double x, double y) { return x > y ? x : y; }
+
+// (int) of a double as the reference's x86 build performs it: out-of-range and
+// NaN give INT_MIN (cvttsd2si), in-range truncates toward zero.
+__device__ __forceinline__ int trunc_int_x86(double x) {
+    if (!(x > -2147483649.0 && x < 2147483648.0)) return INT_MIN;
+    return (int) x;
+}
+
+struct Ctx {
+    RepHeader *h;
+    u16 *cnt, *off, *wq, *leave, *ent, *newslot, *drv, *drv2, *entlist, *entdrv;
+    u8 *sraw, *scur, *schg, *pj, *pj2, *nflag, *fresh;
+    int *stop, *rpos, *vid, *vid2, *ellt, *ellt2, *nrpos, *scan;
+    short *blk, *nblk;
+    double *pos, *spd, *npos, *nspd, *entpos;
+    int tick;
+};
+
+__device__ __forceinline__ const double *tmpl_of(const DevScn &S, int vid) {
+    return S.tmpl + (S.T == 1 ? 0 : TSC_T_STRIDE * __ldg(S.veh_tmpl + vid));
+}
+
+// ---- A.4 car following -------------------------------------------------------
+__device__ double no_collision_speed(double vL, double dL, double vF, double dF, double gap, double dt, double target) {
+    double c = vF * dt / 2 + target - 0.5 * vL * vL / dL - gap;
+    double a = 0.5 / dF;
+    double b = 0.5 * dt;
+    if (b * b < 4 * a * c) return -100;
+    double v1 = 0.5 / a * (sqrt(b * b - 4 * a * c) - b);
+    double v2 = 2 * vL - dL * dt + 2 * (gap - target) / dt;
+    return min2(v1, v2);
+}
+
+__device__ double car_follow_speed(const double *T, double v, double gap, double vL, double leaderMaxNegAcc, double dt) {
+    double s = no_collision_speed(vL, leaderMaxNegAcc, v, T[TSC_T_MAX_NEG_ACC], gap, dt, 0);
+    double assumeDecel = 0;
+    if (v > vL) assumeDecel = v - vL;
+    s = min2(s, no_collision_speed(vL, assumeDecel, v, T[TSC_T_MAX_NEG_ACC], gap, dt, T[TSC_T_MIN_GAP]));
+    s = min2(s, (gap + (vL + assumeDecel / 2) * dt - v * dt / 2) / (T[TSC_T_HEADWAY] + dt / 2));
+    return s;
+}
+
+__device__ double stop_before_speed(const double *T, double v, double distance, double dt) {
+    double nxt = v + T[TSC_T_USUAL_POS_ACC] * dt;
+    double brake = (v + nxt) * dt / 2 + (nxt * nxt / T[TSC_T_USUAL_NEG_ACC] / 2);
+    if (brake < distance) return v + T[TSC_T_USUAL_POS_ACC] * dt;
+    double take = 2 * distance / (v + 1e-8) / dt;
+    if (take >= 1) return v - v / trunc_int_x86(take);
+    return v - v / take;
+}
+
+__device__ __forceinline__ bool can_yield(const double *T, double v, double dist) {
+    double minBrake = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC];
+    return (dist > 0 && minBrake < dist - T[TSC_T_YIELD_DIST]) || (dist < 0 && dist + T[TSC_T_LEN] < 0);
+}
+
+__device__ int reach_steps(const double *T, double v, double distance, bool turn, double dt) {
+    double target = turn ? T[TSC_T_TURN_SPEED] : T[TSC_T_MAX_SPEED];
+    double acc = T[TSC_T_USUAL_POS_ACC];
+    if (distance <= 0) return -1;
+    if (v > target) return trunc_int_x86(ceil(distance / v));
+    double dUntil = 0;
+    if (!(target <= v)) {
+        int s1 = trunc_int_x86(floor((target - v) / acc / dt));
+        double s1speed = v + s1 * acc / dt;
+        double s1dis = (v + s1speed) * (s1 * dt) / 2;
+        dUntil = s1dis + (s1speed < target ? ((s1speed + target) * dt / 2) : 0);
+    }
+    if (dUntil > distance) return trunc_int_x86(ceil((sqrt(v * v + 2 * acc * distance) - v) / acc / dt));
+    return trunc_int_x86(ceil((target - v) / acc / dt)) + trunc_int_x86(ceil((distance - dUntil) / target / dt));
+}
+
+__device__ __forceinline__ bool ll_available(const DevScn &S, const Ctx &c, int ll) {
+    int a = __ldg(S.ll_signal + ll);
+    u32 m = __ldg(S.sig_phase_mask + a * S.max_raw + c.sraw[a]);
+    return (m >> __ldg(S.ll_roadlink + ll)) & 1u;
+}
+
+// Which vehicle does lane-link `f` announce at its cross lying `dc` along it
+// (CityFlow notifyCross; closed form of the sequential scan)?
+// Returns the slot or -1; *d2 = its signed distance to the cross.
+__device__ int cross_claimant(const DevScn &S, const Ctx &c, int f, double dc, double *d2) {
+    int fl = S.L + f;
+    double flen = __ldg(S.drv_length + fl);
+    int el = __ldg(S.ll_end_lane + f);
+    int n = c.cnt[el];
+    if (n > 0) {   // the vehicle that has just moved onto the end lane
+        int t = c.off[el] + n - 1;
+        if (!c.pj[t] && __ldg(S.route_seq + c.rpos[t] - 1) == fl) {
+            double crossDistance = flen - dc;
+            double vehDistance = c.pos[t] - tmpl_of(S, c.vid[t])[TSC_T_LEN];
+            if (crossDistance + vehDistance < 0.0) { *d2 = -(c.pos[t] + crossDistance); return t; }
+        }
+    }
+    n = c.cnt[fl];
+    int base = c.off[fl];
+    for (int k = 0; k < n; ++k) {   // vehicles on the link, front to back
+        int v = base + k;
+        double vd = c.pos[v];
+        if (vd > dc) {
+            if (vd - dc - tmpl_of(S, c.vid[v])[TSC_T_LEN] <= 0.0) { *d2 = dc - vd; return v; }
+        } else { *d2 = dc - vd; return v; }
+    }
+    int sl = __ldg(S.ll_start_lane + f);
+    if (c.cnt[sl] > 0) {   // first vehicle of the incoming lane, heading here on green
+        int hd = c.off[sl];
+        if (__ldg(S.route_seq + c.rpos[hd] + 1) == fl && ll_available(S, c, f)) {
+            *d2 = (__ldg(S.drv_length + sl) - c.pos[hd]) + dc;
+            return hd;
+        }
+    }
+    return -1;
+}
+
+// Cross::canPass (A.5).  *foe_out = announced vehicle on the other link.
+__device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T, int ll, int x, double dts,
+                         double dt, int *foe_out) {
+    int fll = __ldg(S.xr_foe_ll + x);
+    double d2;
+    int foe = cross_claimant(S, c, fll, __ldg(S.xr_foe_dist + x), &d2);
+    *foe_out = foe;
+    if (foe < 0) return true;
+    int t1 = __ldg(S.ll_type + ll), t2 = __ldg(S.ll_type + fll);
+    double d1 = __ldg(S.xr_dist + x) - dts;
+    double v = c.spd[me];
+    if (!can_yield(T, v, d1)) return true;
+    const double *TF = tmpl_of(S, c.vid[foe]);
+    double vf = c.spd[foe];
+    int yield = 0;
+    if (!can_yield(TF, vf, d2)) yield = 1;
+    if (yield == 0) {
+        if (t1 > t2) yield = -1;
+        else if (t1 < t2) {
+            if (d2 > 0) {
+                int fs = reach_steps(TF, vf, d2, t2 != 3, dt);
+                int ms = reach_steps(T, v, d1, t1 != 3, dt);
+                if (fs > ms) yield = -1;
+            } else if (d2 + TF[TSC_T_LEN] < 0) yield = -1;
+            if (yield == 0) yield = 1;
+        } else {
+            if (d2 > 0) {
+                int fs = reach_steps(TF, vf, d2, t2 != 3, dt);
+                int ms = reach_steps(T, v, d1, t1 != 3, dt);
+                if (fs > ms) yield = -1;
+                else if (fs < ms) yield = 1;
+                else {
+                    int e1 = c.ellt[me], e2 = c.ellt[foe];
+                    if (e1 == e2) {
+                        if (d1 == d2) yield = __ldg(S.veh_priority + c.vid[me]) > __ldg(S.veh_priority + c.vid[foe]) ? -1 : 1;
+                        else yield = d1 < d2 ? -1 : 1;
+                    } else yield = e1 < e2 ? -1 : 1;
+                }
+            } else yield = d2 + TF[TSC_T_LEN] < 0 ? -1 : 1;
+        }
+    }
+    if (yield == 1) {   // deadlock: the foe's blocker chain loops back
+        int fast = foe, slow = foe;
+        while (fast >= 0 && c.blk[fast] >= 0) {
+            slow = c.blk[slow];
+            fast = c.blk[c.blk[fast]];
+            if (slow == fast) { yield = -1; break; }
+        }
+    }
+    return yield == -1;
+}
+
+// ---- block-wide exclusive scan of u16 counts into u16 offsets -------------------
+// in[i] (+ extra[i] if given) for i < n; out[n] = total.  All threads call.
+template <int NT>
+__device__ void block_scan_counts(const u16 *in, const u8 *extra_lane, int n_lane, u16 *out, int n, int *scratch) {
+    const int per = (n + NT - 1) / NT;
+    int lo = threadIdx.x * per, hi = min(lo + per, n);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += in[i] + ((extra_lane && i < n_lane) ? extra_lane[i] : 0);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) scratch[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int ws = lane < NT / 32 ? scratch[lane] : 0;
+        int wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < NT / 32) scratch[lane] = wi - ws;
+        if (lane == NT / 32 - 1) scratch[32] = wi;
+    }
+    __syncthreads();
+    int run = scratch[w] + incl - s;
+    for (int i = lo; i < hi; ++i) {
+        out[i] = (u16) run;
+        run += in[i] + ((extra_lane && i < n_lane) ? extra_lane[i] : 0);
+    }
+    if (threadIdx.x == 0) out[n] = (u16) scratch[32];
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------
+// One engine tick for the replica held in shared memory (A.2)
+// ----------------------------------------------------------------------------
+template <int NT>
+__device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *is_spawn_lane) {
+    const int tid = threadIdx.x;
+    const int tick = c.h->tick;
+    const double dt = S.interval;
+    const int L = S.L, D = S.D;
+    const int n_slots = c.h->n_slots;
+
+    // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer ----
+    for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+        int l = __ldg(S.spawn_lane + s);
+        int hd = c.wq[s];
+        int base = __ldg(S.lane_spawn_off + l);
+        u8 fr = 0;
+        if (base + hd < __ldg(S.lane_spawn_off + l + 1)) {
+            int v = __ldg(S.lane_spawn_vid + base + hd);
+            if (__ldg(S.veh_tick + v) <= tick) {
+                int n = c.cnt[l];
+                bool ok = true;
+                if (n > 0) {
+                    int t = c.off[l] + n - 1;
+                    ok = c.pos[t] > tmpl_of(S, c.vid[t])[TSC_T_LEN] + tmpl_of(S, v)[TSC_T_MIN_GAP];
+                }
+                if (ok) {
+                    int slot = c.off[l] + n;
+                    c.pos[slot] = 0.0; c.spd[slot] = 0.0;
+                    c.rpos[slot] = __ldg(S.veh_seq_start + v);
+                    c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
+                    c.drv[slot] = (u16) l; c.pj[slot] = 0;
+                    c.cnt[l] = (u16) (n + 1);
+                    c.wq[s] = (u16) (hd + 1);
+                    fr = 1;
+                    atomicAdd(&c.h->n_running, 1);
+                }
+            }
+        }
+        c.fresh[l] = fr;
+    }
+    for (int d = tid; d < D; d += NT) { c.leave[d] = 0; c.ent[d] = 0; }
+    if (tid == 0) c.h->n_ent = 0;
+    __syncthreads();
+
+    // ---- getAction: next speed / position of every running vehicle from the old state ----
+    for (int i = tid; i < n_slots; i += NT) {
+        int vid = c.vid[i];
+        if (vid < 0) { c.nflag[i] = 0; continue; }
+        const double *T = tmpl_of(S, vid);
+        const int d = c.drv[i];
+        const int rp = c.rpos[i];
+        const double x = c.pos[i], v = c.spd[i];
+        const double dlen = __ldg(S.drv_length + d);
+        // leader and gap as of the end of the previous tick (A.7): vehicles that
+        // entered from the waiting buffer this tick are not yet visible to others
+        int leader = -1;
+        double gap = 0.0;
+        if (i > c.off[d]) {
+            leader = i - 1;
+            gap = c.pos[leader] - tmpl_of(S, c.vid[leader])[TSC_T_LEN] - x;
+        } else {
+            double dist = dlen - x;
+            const double horizon = T[TSC_T_MAX_SPEED] * T[TSC_T_MAX_SPEED] / T[TSC_T_USUAL_NEG_ACC] / 2 + T[TSC_T_MAX_SPEED] * dt * 2;
+            for (int j = 1;; ++j) {
+                int nd = __ldg(S.route_seq + rp + j);
+                if (nd < 0) break;
+                if (nd >= L) {
+                    int sl = __ldg(S.ll_start_lane + nd - L);
+                    int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
+                    for (int e = e0; e < e1; ++e) {
+                        int dl = L + __ldg(S.lane_ll + e);
+                        int n = c.cnt[dl];
+                        if (n > 0) {
+                            int cand = c.off[dl] + n - 1;
+                            double cg = dist + c.pos[cand] - tmpl_of(S, c.vid[cand])[TSC_T_LEN];
+                            if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
+                        }
+                    }
+                    if (leader >= 0) break;
+                } else {
+                    int n = c.cnt[nd] - c.fresh[nd];
+                    if (n > 0) {
+                        leader = c.off[nd] + n - 1;
+                        gap = dist + c.pos[leader] - tmpl_of(S, c.vid[leader])[TSC_T_LEN];
+                        break;
+                    }
+                }
+                dist += __ldg(S.drv_length + nd);
+                if (dist > horizon) break;
+            }
+        }
+        // next speed (A.4)
+        double ns = T[TSC_T_MAX_SPEED];
+        ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
+        ns = min2(ns, __ldg(S.drv_max_speed + d));
+        double cf = T[TSC_T_MAX_SPEED];
+        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c.vid[leader])[TSC_T_MAX_NEG_ACC], dt);
+        ns = min2(ns, cf);
+        // intersection related speed (A.5)
+        int blocker = -1;
+        const bool on_ll = d >= L;
+        const int nd1 = __ldg(S.route_seq + rp + 1);
+        if (on_ll || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {
+            double vi = T[TSC_T_MAX_SPEED];
+            int ll = -1;
+            bool done = false;
+            if (!on_ll && nd1 >= L) {
+                ll = nd1 - L;
+                int el = __ldg(S.ll_end_lane + ll);
+                bool enter = true;
+                int n = c.cnt[el];
+                if (n > 0) {
+                    int t = c.off[el] + n - 1;
+                    enter = c.pos[t] > tmpl_of(S, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
+                }
+                if (!ll_available(S, c, ll) || !enter) {
+                    if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
+                        // cannot stop before the line any more
+                    } else {
+                        vi = min2(vi, stop_before_speed(T, v, dlen - x, dt));
+                        done = true;
+                    }
+                }
+                if (!done && __ldg(S.ll_type + ll) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
+            }
+            if (!done) {
+                if (ll < 0) ll = d - L;
+                double dts = on_ll ? x : -(dlen - x);
+                int x0 = __ldg(S.ll_cross_off + ll), x1 = __ldg(S.ll_cross_off + ll + 1);
+                for (int xi = x0; xi < x1; ++xi) {
+                    double dOn = __ldg(S.xr_dist + xi);
+                    if (dOn < dts) continue;
+                    int foe;
+                    if (!can_pass(S, c, i, T, ll, xi, dts, dt, &foe)) {
+                        vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST], dt));
+                        blocker = foe;
+                        break;
+                    }
+                }
+            }
+            ns = min2(ns, vi);
+        }
+        ns = max2(ns, v - T[TSC_T_MAX_NEG_ACC] * dt);
+        double delta;
+        if (ns < 0) { delta = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC]; ns = 0; }
+        else delta = (v + ns) * dt / 2;
+        // walk forward through the drivables
+        double nx = delta + x;
+        int q = rp, dd = d, hops = 0;
+        bool end = false;
+        double cl = dlen;
+        while (nx > cl) {
+            nx -= cl;
+            int nxt = __ldg(S.route_seq + q + 1);
+            if (nxt < 0) { end = true; break; }
+            ++q; dd = nxt; ++hops;
+            cl = __ldg(S.drv_length + dd);
+        }
+        c.npos[i] = nx; c.nspd[i] = ns; c.nrpos[i] = q; c.nblk[i] = (short) blocker;
+        u8 fl = 8;                       // bit3: valid vehicle
+        if (hops > 0 || end) fl |= 1;    // leaves its drivable
+        if (end) fl |= 2;
+        if (hops > 1) fl |= 4;           // skipped a whole drivable
+        c.nflag[i] = fl;
+        if (fl & 1) {
+            atomicAdd((unsigned *) &c.leave[d & ~1], (d & 1) ? 0x10000u : 1u);
+            if (!end) {
+                atomicAdd((unsigned *) &c.ent[dd & ~1], (dd & 1) ? 0x10000u : 1u);
+                int k = atomicAdd(&c.h->n_ent, 1);
+                if (k < Y.ent_cap) { c.entlist[k] = (u16) i; c.entdrv[k] = (u16) dd; c.entpos[k] = nx; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- updateLocation: new per-drivable counts, then a stable re-pack ----
+    // leave[] becomes the number of leavers, newcnt = cnt - leave + ent (kept in ent[])
+    for (int d = tid; d < D; d += NT) c.ent[d] = (u16) (c.cnt[d] - c.leave[d] + c.ent[d]);
+    __syncthreads();
+    // reuse scan scratch; new offsets go to a temporary (nrpos is busy, so use scan+64..)
+    u16 *noff = (u16 *) (c.scan + 64);
+    block_scan_counts<NT>(c.ent, is_spawn_lane, L, noff, D, c.scan);
+    const int n_ent = min(c.h->n_ent, Y.ent_cap);
+    if (tid == 0) {
+        if (c.h->n_ent > Y.ent_cap) c.h->err |= ERR_ENT_OVERFLOW;
+        if (noff[D] > Y.Vcap) c.h->err |= ERR_OVERFLOW;
+    }
+    const bool overflow = noff[D] > Y.Vcap;
+    // destination slot of every vehicle
+    for (int i = tid; i < n_slots; i += NT) {
+        u8 fl = c.nflag[i];
+        u16 ns = 0xFFFF;
+        if (fl & 8) {
+            int d = c.drv[i];
+            int rank = i - c.off[d];
+            int nl = c.leave[d];
+            if (!(fl & 1)) {
+                if (rank < nl) atomicOr(&c.h->err, ERR_ORDER);
+                ns = (u16) (noff[d] + rank - nl);
+            } else {
+                if (rank >= nl) atomicOr(&c.h->err, ERR_ORDER);
+                if (!(fl & 2)) {
+                    int dd = __ldg(S.route_seq + c.nrpos[i]);
+                    double nx = c.npos[i];
+                    int myv = c.vid[i];
+                    int ahead = 0;
+                    for (int k = 0; k < n_ent; ++k) {
+                        if (c.entdrv[k] != dd) continue;
+                        int o = c.entlist[k];
+                        if (o == i) continue;
+                        double ox = c.entpos[k];
+                        if (ox > nx || (ox == nx && c.vid[o] < myv)) ++ahead;
+                    }
+                    ns = (u16) (noff[dd] + (c.cnt[dd] - c.leave[dd]) + ahead);
+                }
+            }
+        }
+        c.newslot[i] = ns;
+    }
+    __syncthreads();
+    if (overflow) {   // keep the old state; the sticky flag reports it
+        if (tid == 0) c.h->tick = tick + 1;
+        __syncthreads();
+        return;
+    }
+    // finished vehicles: statistics (A.8)
+    for (int i = tid; i < n_slots; i += NT) {
+        if ((c.nflag[i] & 10) == 10) {
+            int vt = __ldg(S.veh_tick + c.vid[i]);
+            atomicAdd((unsigned long long *) &c.h->cum_tt, (unsigned long long) (tick - vt));
+            atomicAdd((unsigned long long *) &c.h->fin_enter, (unsigned long long) vt);
+            atomicAdd(&c.h->n_finished, 1);
+            atomicSub(&c.h->n_running, 1);
+        }
+    }
+    // scatter: kinematics come from the n* arrays; the identity fields ping-pong
+    // between two buffers, so nothing is read after it may have been overwritten
+    for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+        int l = __ldg(S.spawn_lane + s);
+        c.vid2[noff[l] + c.ent[l]] = -1;      // the lane's spare slot stays empty
+    }
+    for (int i = tid; i < n_slots; i += NT) {
+        u16 dst = c.newslot[i];
+        if (dst == 0xFFFF) continue;
+        u8 fl = c.nflag[i];
+        int q = c.nrpos[i];
+        c.pos[dst] = c.npos[i]; c.spd[dst] = c.nspd[i]; c.rpos[dst] = q;
+        int bk = c.nblk[i];
+        if (bk >= 0) { u16 nb = c.newslot[bk]; bk = (nb == 0xFFFF) ? -1 : (int) nb; }
+        c.blk[dst] = (short) bk;
+        c.vid2[dst] = c.vid[i];
+        if (fl & 1) {
+            int dd = __ldg(S.route_seq + q);
+            c.drv2[dst] = (u16) dd;
+            c.ellt2[dst] = dd >= L ? tick : INT_MAX;
+            c.pj2[dst] = (fl & 4) ? 1 : 0;
+        } else {
+            c.drv2[dst] = c.drv[i]; c.ellt2[dst] = c.ellt[i]; c.pj2[dst] = c.pj[i];
+        }
+    }
+    { int *t = c.vid; c.vid = c.vid2; c.vid2 = t; }
+    { int *t = c.ellt; c.ellt = c.ellt2; c.ellt2 = t; }
+    { u16 *t = c.drv; c.drv = c.drv2; c.drv2 = t; }
+    { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
+    for (int d = tid; d < D; d += NT) { c.cnt[d] = c.ent[d]; c.off[d] = noff[d]; }
+    if (tid == 0) { c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1; }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------
+// pytsc layer: phase program, Retriever, per-signal stats, reward, mask, obs
+// ----------------------------------------------------------------------------
+// float("%f" % x): the reference reads distance and speed through
+// get_vehicle_info strings (retriever.py:35-36,44) -- six decimals, correctly
+// rounded both ways.  x >= 0.
+__device__ double round6(double x) {
+    double p = x * 1e6;
+    double e = __fma_rn(x, 1e6, -p);       // exact product = p + e
+    double n = rint(p);
+    double dlt = p - n;
+    if (dlt == 0.5 && e > 0) n += 1.0;
+    else if (dlt == -0.5 && e < 0) n -= 1.0;
+    return n / 1e6;
+}
+
+// Python's float floor division a // b (floatobject.c float_divmod), b > 0.
+__device__ double py_floordiv(double a, double b) {
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0) != (mod < 0))) div -= 1.0;
+    if (div != 0.0) {
+        double f = floor(div);
+        if (div - f > 0.5) f += 1.0;
+        return f;
+    }
+    return 0.0;
+}
+
+// numpy's pairwise float64 sum for n <= 128 (8 interleaved accumulators).
+__device__ double np_sum(const double *a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
+template <int NT>
+__device__ void apply_controller(const DevScn &S, Ctx &c, const StepArgs &a, int b) {
+    for (int s = threadIdx.x; s < S.A; s += NT) {
+        if (a.set_raw_phase) c.sraw[s] = (u8) a.raw_phase[(size_t) b * S.A + s];
+        if (a.init_program >= 0) {
+            c.scur[s] = (u8) a.init_program; c.schg[s] = 0; c.stop[s] = 0;
+            c.sraw[s] = (u8) __ldg(S.sig_phase_raw + s * S.P + a.init_program);
+        }
+        if (a.apply_actions) {
+            int P = __ldg(S.sig_n_phases + s);
+            int cur = c.scur[s], t = c.stop[s];
+            int idx;
+            if (a.apply_actions == 2) {   // FixedTimeController.get_action (controllers.py:39-54)
+                idx = (__ldg(S.sig_phase_green + s * S.P + cur) && t < a.controller_arg) ? cur : (cur + 1) % P;
+            } else {
+                int act = a.actions[(size_t) b * S.A + s];
+                if (S.action_space == TSC_ACT_PHASE_SWITCH) idx = act == 1 ? (cur + 1) % P : cur;   // actions.py:152-158
+                else idx = act;                                                                    // actions.py:106-108
+                if (idx < 0 || idx >= P) idx = cur;
+            }
+            // BaseTSProgram.update_current_phase (common/traffic_signal.py:94-109)
+            if (idx == cur) { c.schg[s] = 0; t += S.yellow_time; }
+            else { c.schg[s] = 1; t = S.yellow_time; }
+            c.scur[s] = (u8) idx; c.stop[s] = t;
+            c.sraw[s] = (u8) __ldg(S.sig_phase_raw + s * S.P + idx);   // engine.set_tl_phase (traffic_signal.py:58)
+        }
+    }
+}
+
+__device__ __forceinline__ float ref_trunc(double x, bool exact) { return (float) (exact ? trunc(x) : x); }
+
+template <int NT>
+__device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArgs &a, int b, unsigned char *smem) {
+    const int tid = threadIdx.x;
+    const int L = S.L, A = S.A;
+    const tsc_outputs_t &O = a.out;
+    // scratch aliases (the n* arrays are free between ticks)
+    double *l_occ = c.npos;              // [L]
+    double *l_ms = c.npos + L;           // [L]
+    int *l_q = (int *) (smem + Y.o_lane_q);   // [L]
+    double *s_loc = c.nspd;              // [A] local reward term
+    double *s_prs = c.nspd + A;          // [A] pressure
+    double *s_red = c.nspd + 2 * A;      // [4*32] reduction scratch
+
+    // --- Retriever._compute_lane_measurements (retriever.py:54-85) ---
+    for (int l = tid; l < L; l += NT) {
+        int n = c.cnt[l], base = c.off[l];
+        int q = 0;
+        double tot = 0.0;
+        for (int k = 0; k < n; ++k) {
+            double v = c.spd[base + k];
+            tot += v;
+            q += v < 0.1;
+        }
+        double ms = n ? tot / n : 0.0;
+        double lane_length = __ldg(S.lane_pytsc_length + l) / S.v_size;
+        double occ = n / lane_length;
+        l_occ[l] = occ; l_ms[l] = ms; l_q[l] = q;
+        size_t o = (size_t) b * L + l;
+        if (O.lane_count) O.lane_count[o] = n;
+        if (O.lane_queued) O.lane_queued[o] = q;
+        if (O.lane_occupancy) O.lane_occupancy[o] = (float) occ;
+        if (O.lane_mean_speed) O.lane_mean_speed[o] = (float) ms;
+        if (O.lane_meas64) { O.lane_meas64[2 * o] = occ; O.lane_meas64[2 * o + 1] = ms; }
+    }
+    __syncthreads();
+
+    // --- position-matrix windows (retriever.py:20-52, traffic_signal.py:124,135) ---
+    const int vis = S.visibility;
+    const bool need_pos = O.pos_in || O.pos_out || (O.obs && S.obs_type == TSC_OBS_POSITION_MATRIX);
+    double *win_in = (double *) c.nrpos;   // [n_in_total][vis] scratch (fp64), only when needed
+    if (need_pos) {
+        const int n_in = S.n_in_total, n_out = S.n_out_total;
+        for (int e = tid; e < n_in + n_out; e += NT) {
+            bool inc = e < n_in;
+            int l = inc ? __ldg(S.sig_in_lane + e) : __ldg(S.sig_out_lane + e - n_in);
+            double plen = __ldg(S.lane_pytsc_length + l);
+            double mspeed = __ldg(S.drv_max_speed + l);
+            int bins = (int) (plen / S.v_size);
+            int n = c.cnt[l], base = c.off[l];
+            double w[16];
+            for (int k = 0; k < vis; ++k) w[k] = -1.0;
+            if (bins > 0 && n > 0) {
+                int len = bins < vis ? vis : bins;           // padded length
+                int lo = inc ? len - vis : 0;                // window start in the padded list
+                double bin_size = plen / bins;
+                for (int k = 0; k < n; ++k) {
+                    double p = round6(c.pos[base + k]);
+                    if (p < 0) p = 0; else if (p > plen) p = plen;
+                    int bi = trunc_int_x86(py_floordiv(p, bin_size));
+                    if (bi >= bins) bi = bins - 1;
+                    int wi = bi - lo;
+                    if (wi >= 0 && wi < vis) {
+                        double nsp = round6(c.spd[base + k]) / mspeed;
+                        w[wi] += 1.0;
+                        w[wi] += nsp;
+                    }
+                }
+            }
+            if (inc) {
+                if (S.obs_type == TSC_OBS_POSITION_MATRIX) for (int k = 0; k < vis; ++k) win_in[e * vis + k] = w[k];
+                if (O.pos_in) for (int k = 0; k < vis; ++k) O.pos_in[((size_t) b * n_in + e) * vis + k] = (float) w[k];
+            } else if (O.pos_out) {
+                for (int k = 0; k < vis; ++k) O.pos_out[((size_t) b * n_out + (e - n_in)) * vis + k] = (float) w[k];
+            }
+        }
+        __syncthreads();
+    }
+
+    // --- TrafficSignal.update_stats (traffic_signal.py:101-141), obs, state, mask ---
+    for (int s = tid; s < A; s += NT) {
+        int i0 = __ldg(S.sig_in_off + s), i1 = __ldg(S.sig_in_off + s + 1);
+        int o0 = __ldg(S.sig_out_off + s), o1 = __ldg(S.sig_out_off + s + 1);
+        int nq = 0;
+        double occ = 0, ms = 0, md = 0, oocc = 0;
+        for (int e = i0; e < i1; ++e) {
+            int l = __ldg(S.sig_in_lane + e);
+            nq += l_q[l];
+            occ += l_occ[l];
+            ms += l_ms[l];
+            md += 1 - l_ms[l] / __ldg(S.drv_max_speed + l);
+        }
+        int nin = i1 - i0, nout = o1 - o0;
+        occ /= nin; ms /= nin; md /= nin;
+        for (int e = o0; e < o1; ++e) oocc += l_occ[__ldg(S.sig_out_lane + e)];
+        oocc /= nout;
+        double pressure = fabs(occ - oocc);
+        int cur = c.scur[s], t = c.stop[s], P = __ldg(S.sig_n_phases + s);
+        double ntop = (double) t / (double) __ldg(S.sig_max_time + s * S.P + cur);
+        if (O.sig_stats64) {
+            double *o = O.sig_stats64 + ((size_t) b * A + s) * 8;
+            o[0] = nq; o[1] = occ; o[2] = ms; o[3] = md; o[4] = oocc; o[5] = pressure; o[6] = ntop; o[7] = cur;
+        }
+        // local reward term (reward.py:77-80 | 125-128)
+        double chg = c.schg[s] ? 1.0 : 0.0;
+        double metric = S.reward_type == TSC_REWARD_QUEUE ? (double) nq : pressure;
+        s_loc[s] = -S.flick * chg - metric - 1e-6;
+        s_prs[s] = pressure;
+
+        // observation / state vectors
+        const int per = 12, ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
+        const bool ex = S.reference_exact != 0;
+        if (O.state || (O.obs && S.obs_type == TSC_OBS_LANE_FEATURES)) {
+            bool tr = ex && nin * per < ML * per;   // pad_list only converts when it pads
+            for (int rep = 0; rep < 2; ++rep) {
+                float *dst = rep == 0 ? ((O.obs && S.obs_type == TSC_OBS_LANE_FEATURES) ? O.obs + ((size_t) b * A + s) * S.obs_dim : nullptr)
+                                      : (O.state ? O.state + ((size_t) b * A + s) * S.state_dim : nullptr);
+                if (!dst) continue;
+                int k = 0;
+                for (int e = i0; e < i1 && e - i0 < ML; ++e) {
+                    int l = __ldg(S.sig_in_lane + e);
+                    for (int f = 0; f < 9; ++f) dst[k++] = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
+                    dst[k++] = (float) l_q[l];
+                    dst[k++] = ref_trunc(l_occ[l], tr);
+                    dst[k++] = ref_trunc(l_ms[l], tr);
+                }
+                for (; k < ML * per; ++k) dst[k] = -1.0f;
+                for (int p = 0; p < MP; ++p) dst[k++] = p < P ? (p == cur ? 1.0f : 0.0f) : 0.0f;
+            }
+        }
+        if (O.obs && S.obs_type == TSC_OBS_POSITION_MATRIX) {
+            float *dst = O.obs + ((size_t) b * A + s) * S.obs_dim;
+            const int body = ML * (vis + 9);
+            // count entries first: pad_list truncates only if it pads
+            int total = 0;
+            for (int e = i0; e < i1; ++e) {
+                total += 9;
+                for (int k = 0; k < vis; ++k) total += win_in[e * vis + k] > 0;
+            }
+            bool tr = ex && total < body;
+            int k = 0;
+            for (int e = i0; e < i1; ++e) {
+                int l = __ldg(S.sig_in_lane + e);
+                for (int f = 0; f < 9 && k < body; ++f) dst[k++] = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
+                for (int j = 0; j < vis; ++j) {
+                    double val = win_in[e * vis + j];
+                    if (val > 0 && k < body) dst[k++] = ref_trunc(val > 1.0 ? 1.0 : val, tr);   // np.clip(val + 0, 0, 1)
+                }
+            }
+            for (; k < body; ++k) dst[k] = -1.0f;
+            for (int p = 0; p < MP; ++p) dst[k++] = p < P ? (p == cur ? 1.0f : 0.0f) : -1.0f;
+        }
+        // action mask (common/traffic_signal.py:329-361, 375-404; actions.py:119-131, 169-188)
+        if (O.mask) {
+            u32 allow = 0;
+            if (__ldg(S.sig_phase_green + s * S.P + cur)) {
+                int mn = __ldg(S.sig_min_time + s * S.P + cur), mx = __ldg(S.sig_max_time + s * S.P + cur);
+                int nxt = (cur + 1) % P;
+                if (t < mn) allow = 1u << cur;
+                else if (t < mx) allow = (1u << cur) | (1u << nxt);
+                else if (t == mx) allow = 1u << nxt;
+            } else if (S.round_robin) {
+                allow = 1u << ((cur + 1) % P);
+            } else {
+                for (int p = 0; p < P; ++p)
+                    if (__ldg(S.sig_phase_green + s * S.P + p) && p != cur - 1) allow |= 1u << p;
+            }
+            u8 *m = O.mask + ((size_t) b * A + s) * S.n_actions;
+            if (S.action_space == TSC_ACT_PHASE_SWITCH) {
+                m[0] = (allow >> cur) & 1; m[1] = (allow >> ((cur + 1) % P)) & 1;
+            } else {
+                for (int p = 0; p < S.n_actions; ++p) m[p] = p < P ? ((allow >> p) & 1) : 0;
+            }
+        }
+    }
+    __syncthreads();
+
+    // --- local rewards with spatially discounted neighbours (reward.py:81-88 | 129-136) ---
+    if (O.reward) {
+        for (int s = tid; s < A; s += NT) {
+            double r = s_loc[s];
+            int n0 = __ldg(S.nbr_off + s), n1 = __ldg(S.nbr_off + s + 1);
+            for (int e = n0; e < n1; ++e) r += __ldg(S.nbr_weight + e) * s_loc[__ldg(S.nbr_idx + e)];
+            O.reward[(size_t) b * A + s] = (float) r;
+        }
+    }
+
+    // --- network metrics (metrics.py) and the global reward: warp 0 ---
+    if (tid < 32) {
+        int qsum = 0, vsum = 0;
+        double wspeed = 0, occs = 0, nms = 0;
+        for (int l = tid; l < L; l += 32) {
+            int n = c.cnt[l];
+            qsum += l_q[l]; vsum += n;
+            wspeed += l_ms[l] * n;
+            occs += l_occ[l];
+            nms += l_ms[l] / __ldg(S.drv_max_speed + l);
+        }
+        int chg = 0;
+        for (int s = tid; s < A; s += 32) chg += c.schg[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+            vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            chg += __shfl_xor_sync(0xffffffffu, chg, o);
+            wspeed += __shfl_xor_sync(0xffffffffu, wspeed, o);
+            occs += __shfl_xor_sync(0xffffffffu, occs, o);
+            nms += __shfl_xor_sync(0xffffffffu, nms, o);
+        }
+        if (tid == 0) {
+            double flicker = (double) chg / (double) A;
+            double psum = A <= 128 ? np_sum(s_prs, A) : 0.0;
+            if (A > 128) for (int s = 0; s < A; ++s) psum += s_prs[s];
+            double density = occs / L, norm_ms = nms / L;
+            if (O.metrics) {
+                double *m = O.metrics + (size_t) b * 8;
+                m[0] = qsum; m[1] = vsum ? wspeed / vsum : 0.0; m[2] = 1 - norm_ms; m[3] = density;
+                m[4] = psum; m[5] = density * norm_ms; m[6] = flicker; m[7] = norm_ms;
+            }
+            if (O.reward_global) {
+                double r;
+                if (S.reward_type == TSC_REWARD_QUEUE) { r = 1e-6; r += S.flick * flicker; r += qsum; r = -1 * r; }
+                else { r = 1e-6; r -= S.flick * flicker; r -= psum; }
+                O.reward_global[b] = (float) r;
+            }
+            if (O.sim) {
+                int now = c.h->tick;
+                int tt = now < S.horizon + 1 ? now : S.horizon + 1;
+                long long created = __ldg(S.created_cnt + tt);
+                long long alive = created - c.h->n_finished;
+                double total = (double) (c.h->cum_tt + alive * now - (__ldg(S.created_enter + tt) - c.h->fin_enter)) * S.interval;
+                long long n = c.h->n_finished + alive;
+                double *o = O.sim + (size_t) b * 4;
+                o[0] = c.h->n_running; o[1] = n == 0 ? 0.0 : total / (double) n; o[2] = now * S.interval; o[3] = c.h->n_finished;
+            }
+        }
+    }
+    __syncthreads();
+    (void) s_red;
+}
+
+// ----------------------------------------------------------------------------
+// The step kernel
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, int tid, int nt) {
+    // bytes is a multiple of 16, both pointers 16-byte aligned
+    const int4 *s = (const int4 *) src;
+    int4 *d = (int4 *) dst;
+    for (int i = tid; i < bytes / 16; i += nt) d[i] = s[i];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
+                                                      const u8 *is_spawn_lane, const StepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    Ctx c;
+    c.h = (RepHeader *) smem;
+    c.cnt = (u16 *) (smem + Y.o_cnt); c.wq = (u16 *) (smem + Y.o_wq);
+    c.sraw = smem + Y.o_sraw; c.scur = smem + Y.o_scur; c.schg = smem + Y.o_schg; c.stop = (int *) (smem + Y.o_stop);
+    c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd);
+    c.rpos = (int *) (smem + Y.o_rpos); c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt);
+    c.blk = (short *) (smem + Y.o_blk); c.drv = (u16 *) (smem + Y.o_drv); c.pj = smem + Y.o_pj;
+    c.npos = (double *) (smem + Y.o_npos); c.nspd = (double *) (smem + Y.o_nspd); c.nrpos = (int *) (smem + Y.o_nrpos);
+    c.vid2 = (int *) (smem + Y.o_vid2); c.drv2 = (u16 *) (smem + Y.o_drv2); c.ellt2 = (int *) (smem + Y.o_ellt2); c.pj2 = smem + Y.o_pj2;
+    c.nblk = (short *) (smem + Y.o_nblk); c.newslot = (u16 *) (smem + Y.o_newslot); c.nflag = smem + Y.o_nflag;
+    c.off = (u16 *) (smem + Y.o_off); c.leave = (u16 *) (smem + Y.o_leave); c.ent = (u16 *) (smem + Y.o_ent);
+    c.fresh = smem + Y.o_fresh; c.entlist = (u16 *) (smem + Y.o_entlist); c.entpos = (double *) (smem + Y.o_entpos);
+    c.entdrv = (u16 *) (smem + Y.o_entdrv); c.scan = (int *) (smem + Y.o_scan);
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        unsigned char *img = images + (size_t) b * Y.img_bytes;
+        // the identity fields ping-pong between two buffers every tick: start from the primary ones
+        c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt); c.drv = (u16 *) (smem + Y.o_drv); c.pj = smem + Y.o_pj;
+        c.vid2 = (int *) (smem + Y.o_vid2); c.ellt2 = (int *) (smem + Y.o_ellt2); c.drv2 = (u16 *) (smem + Y.o_drv2); c.pj2 = smem + Y.o_pj2;
+        // ---- stage the replica image into shared memory ----
+        copy16(smem, img, Y.o_meta_end, tid, NT);
+        __syncthreads();
+        {
+            const int n = c.h->n_slots;
+            const int n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
+            copy16(smem + Y.o_pos, img + Y.o_pos, n8, tid, NT);
+            copy16(smem + Y.o_spd, img + Y.o_spd, n8, tid, NT);
+            copy16(smem + Y.o_rpos, img + Y.o_rpos, n4, tid, NT);
+            copy16(smem + Y.o_vid, img + Y.o_vid, n4, tid, NT);
+            copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
+            copy16(smem + Y.o_blk, img + Y.o_blk, n2, tid, NT);
+            copy16(smem + Y.o_drv, img + Y.o_drv, n2, tid, NT);
+            copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
+        }
+        for (int l = tid; l < S.L; l += NT) c.fresh[l] = 0;
+        __syncthreads();
+        block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
+
+        apply_controller<NT>(S, c, a, b);
+        __syncthreads();
+        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT>(S, Y, c, is_spawn_lane);
+        if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
+
+        // ---- write the image back ----
+        if (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0) {
+            copy16(img, smem, Y.o_meta_end, tid, NT);
+            const int n = c.h->n_slots;
+            const int n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
+            if (a.n_ticks > 0) {
+                copy16(img + Y.o_pos, smem + Y.o_pos, n8, tid, NT);
+                copy16(img + Y.o_spd, smem + Y.o_spd, n8, tid, NT);
+                copy16(img + Y.o_rpos, smem + Y.o_rpos, n4, tid, NT);
+                copy16(img + Y.o_vid, c.vid, n4, tid, NT);
+                copy16(img + Y.o_ellt, c.ellt, n4, tid, NT);
+                copy16(img + Y.o_blk, smem + Y.o_blk, n2, tid, NT);
+                copy16(img + Y.o_drv, c.drv, n2, tid, NT);
+                copy16(img + Y.o_pj, c.pj, n1, tid, NT);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Host side: handle, tables, C ABI
+// ----------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (x);                                                                        \
+        if (e__ != cudaSuccess) return fail(TSC_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
+    } while (0)
+
+static constexpr int NT = 256;
+
+struct tsc_engine {
+    int device = 0, B = 0;
+    DevScn S{};
+    Layout Y{};
+    std::vector<void *> dev_allocs;
+    unsigned char *images = nullptr;
+    u8 *d_is_spawn_lane = nullptr;
+    int *d_actions = nullptr;
+    float *d_obs = nullptr, *d_reward = nullptr, *d_rg = nullptr;
+    u8 *d_mask = nullptr;
+    int32_t *h_actions = nullptr;      // pinned staging for the *_host path
+    float *h_obs = nullptr, *h_reward = nullptr, *h_rg = nullptr;
+    u8 *h_mask = nullptr;
+    int grid = 0, regs = 0;
+    int64_t launches = 0;
+    std::vector<unsigned char> init_image;   // host copy of the tick-0 image
+    // host copies needed by snapshot/load
+    std::vector<int> h_route_seq, h_veh_seq_start;
+    int n_spawn_lanes = 0;
+    std::vector<int> h_spawn_lane;
+    std::vector<u8> h_is_spawn;
+};
+
+template <typename Tp>
+static int upload(tsc_engine *E, const Tp *host, size_t n, const Tp **dev) {
+    void *p = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(Tp);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    E->dev_allocs.push_back(p);
+    if (n) CUDA_TRY(cudaMemcpy(p, host, n * sizeof(Tp), cudaMemcpyHostToDevice));
+    *dev = (const Tp *) p;
+    return 0;
+}
+
+static int align16(int x) { return (x + 15) & ~15; }
+
+static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
+    Y.Vcap = Vcap;
+    Y.ent_cap = Vcap < 512 ? Vcap : 512;
+    int o = sizeof(RepHeader);
+    Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_wq = o; o = align16(o + 2 * (S.n_spawn_lanes + 1));
+    Y.o_sraw = o; o = align16(o + S.A);
+    Y.o_scur = o; o = align16(o + S.A);
+    Y.o_schg = o; o = align16(o + S.A);
+    Y.o_stop = o; o = align16(o + 4 * S.A);
+    Y.o_meta_end = o;
+    Y.o_pos = o; o = align16(o + 8 * Vcap);
+    Y.o_spd = o; o = align16(o + 8 * Vcap);
+    Y.o_rpos = o; o = align16(o + 4 * Vcap);
+    Y.o_vid = o; o = align16(o + 4 * Vcap);
+    Y.o_ellt = o; o = align16(o + 4 * Vcap);
+    Y.o_blk = o; o = align16(o + 2 * Vcap);
+    Y.o_drv = o; o = align16(o + 2 * Vcap);
+    Y.o_pj = o; o = align16(o + Vcap);
+    Y.img_bytes = o;
+    // scratch; npos/nspd/nrpos double as retrieve scratch: make sure they are large enough
+    int need_np = 2 * S.L, need_ns = 2 * S.A + 160;
+    int need_nr = (S.n_in_total * S.visibility * 8 + 3) / 4;
+    Y.o_vid2 = o; o = align16(o + 4 * Vcap);
+    Y.o_ellt2 = o; o = align16(o + 4 * Vcap);
+    Y.o_drv2 = o; o = align16(o + 2 * Vcap);
+    Y.o_pj2 = o; o = align16(o + Vcap);
+    Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
+    Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
+    Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
+    Y.o_nblk = o; o = align16(o + 2 * Vcap);
+    Y.o_newslot = o; o = align16(o + 2 * Vcap);
+    Y.o_nflag = o; o = align16(o + Vcap);
+    Y.o_off = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_leave = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_ent = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_fresh = o; o = align16(o + S.L);
+    Y.o_entlist = o; o = align16(o + 2 * Y.ent_cap);
+    Y.o_entdrv = o; o = align16(o + 2 * Y.ent_cap);
+    Y.o_entpos = o; o = align16(o + 8 * Y.ent_cap);
+    Y.o_scan = o; o = align16(o + 4 * 64 + 2 * (S.D + 2));
+    Y.o_lane_q = o; o = align16(o + 4 * S.L);
+    Y.smem_bytes = o;
+}
+
+extern "C" {
+
+int tsc_abi_version(void) { return TSC_ABI_VERSION; }
+const char *tsc_last_error(void) { return g_err.c_str(); }
+
+int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int32_t vehicle_capacity, tsc_handle *out) {
+    if (!s || !out) return fail(TSC_EINVAL, "null argument");
+    if (s->abi_version != TSC_ABI_VERSION) return fail(TSC_EINVAL, "scenario abi_version %d != %d", s->abi_version, TSC_ABI_VERSION);
+    if (n_replicas <= 0) return fail(TSC_EINVAL, "n_replicas must be positive");
+    if (s->interval != 1.0) return fail(TSC_EINVAL, "interval must be 1.0");
+    if (s->visibility > 16 || s->visibility < 1) return fail(TSC_EINVAL, "visibility must be in 1..16");
+    if (s->max_phases > 32) return fail(TSC_EINVAL, "more than 32 phases per signal");
+    if (s->n_lanes + s->n_lanelinks >= 65535) return fail(TSC_EINVAL, "too many drivables for one replica block");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(TSC_EINVAL, "device %d not available (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    auto *E = new tsc_engine();
+    E->device = device; E->B = n_replicas;
+    DevScn &S = E->S;
+    S.L = s->n_lanes; S.K = s->n_lanelinks; S.D = S.L + S.K; S.A = s->n_signals; S.N = s->n_vehicles; S.T = s->n_templates;
+    S.horizon = s->horizon_ticks; S.max_raw = s->max_raw_phases; S.P = s->max_phases;
+    S.n_in_total = s->n_in_total; S.n_out_total = s->n_out_total;
+    const int L = S.L, K = S.K, D = S.D, A = S.A, N = S.N;
+    int rc = 0;
+#define UP(field, n) if ((rc = upload(E, s->field, (size_t) (n), &S.field))) { tsc_destroy(E); return rc; }
+    UP(drv_length, D) UP(drv_max_speed, D) UP(lane_ll_off, L + 1) UP(lane_ll, s->lane_ll_off[L])
+    UP(lane_spawn_off, L + 1) UP(lane_spawn_vid, N)
+    UP(ll_start_lane, K) UP(ll_end_lane, K) UP(ll_signal, K) UP(ll_roadlink, K) UP(ll_type, K) UP(ll_cross_off, K + 1)
+    UP(xr_dist, s->n_cross_entries) UP(xr_foe_ll, s->n_cross_entries) UP(xr_foe_dist, s->n_cross_entries)
+    UP(sig_phase_mask, A * s->max_raw_phases) UP(route_seq, s->n_route_seq)
+    UP(veh_tick, N) UP(veh_seq_start, N) UP(veh_tmpl, N) UP(veh_priority, N) UP(tmpl, s->n_templates * TSC_T_STRIDE)
+    UP(lane_pytsc_length, L) UP(lane_feat, L * 9) UP(sig_in_off, A + 1) UP(sig_in_lane, s->n_in_total)
+    UP(sig_out_off, A + 1) UP(sig_out_lane, s->n_out_total) UP(sig_n_phases, A) UP(sig_phase_raw, A * s->max_phases)
+    UP(sig_phase_green, A * s->max_phases) UP(sig_min_time, A * s->max_phases) UP(sig_max_time, A * s->max_phases)
+    UP(nbr_off, A + 1) UP(nbr_idx, s->n_nbr_total) UP(nbr_weight, s->n_nbr_total)
+#undef UP
+    S.reward_type = s->reward_type; S.obs_type = s->obs_type; S.action_space = s->action_space; S.round_robin = s->round_robin;
+    S.visibility = s->visibility; S.yellow_time = s->yellow_time; S.obs_dim = s->obs_dim; S.state_dim = s->state_dim;
+    S.n_actions = s->n_actions; S.reference_exact = s->reference_exact; S.max_lanes_per_signal = s->max_lanes_per_signal;
+    S.max_obs_phases = s->max_obs_phases; S.v_size = s->veh_size_min_gap; S.flick = s->flickering_coef; S.interval = s->interval;
+    // spawn lanes and creation prefix tables
+    E->h_is_spawn.assign(L, 0);
+    for (int l = 0; l < L; ++l) if (s->lane_spawn_off[l + 1] > s->lane_spawn_off[l]) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
+    S.n_spawn_lanes = E->n_spawn_lanes = (int) E->h_spawn_lane.size();
+    if ((rc = upload(E, E->h_spawn_lane.data(), E->h_spawn_lane.size(), &S.spawn_lane))) { tsc_destroy(E); return rc; }
+    { const u8 *p; if ((rc = upload(E, E->h_is_spawn.data(), (size_t) L, &p))) { tsc_destroy(E); return rc; } E->d_is_spawn_lane = (u8 *) p; }
+    std::vector<int> ccnt(S.horizon + 2, 0);
+    std::vector<long long> cent(S.horizon + 2, 0);
+    for (int v = 0; v < N; ++v) {
+        int t = s->veh_tick[v];
+        if (t < 0 || t > S.horizon) { tsc_destroy(E); return fail(TSC_EINVAL, "veh_tick out of horizon"); }
+        ccnt[t + 1] += 1; cent[t + 1] += t;
+    }
+    for (int t = 1; t <= S.horizon + 1; ++t) { ccnt[t] += ccnt[t - 1]; cent[t] += cent[t - 1]; }
+    if ((rc = upload(E, ccnt.data(), ccnt.size(), &S.created_cnt))) { tsc_destroy(E); return rc; }
+    if ((rc = upload(E, cent.data(), cent.size(), &S.created_enter))) { tsc_destroy(E); return rc; }
+    E->h_route_seq.assign(s->route_seq, s->route_seq + s->n_route_seq);
+    E->h_veh_seq_start.assign(s->veh_seq_start, s->veh_seq_start + N);
+
+    int Vcap = vehicle_capacity > 0 ? vehicle_capacity : 1024;
+    Vcap = (Vcap + E->n_spawn_lanes + 31) & ~31;
+    if (Vcap > 65000) { tsc_destroy(E); return fail(TSC_EINVAL, "vehicle_capacity too large for one replica block"); }
+    build_layout(E->Y, S, Vcap);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) {
+        int need = E->Y.smem_bytes;
+        tsc_destroy(E);
+        return fail(TSC_ENOMEM, "replica working set %d B exceeds %zu B of shared memory per block; lower vehicle_capacity",
+                    need, (size_t) prop.sharedMemPerBlockOptin);
+    }
+    CUDA_TRY(cudaFuncSetAttribute(tsc_step_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, E->Y.smem_bytes));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsc_step_kernel<NT>, NT, E->Y.smem_bytes));
+    if (per_sm < 1) per_sm = 1;
+    E->grid = prop.multiProcessorCount * per_sm;
+    if (E->grid > n_replicas) E->grid = n_replicas;
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, tsc_step_kernel<NT>));
+    E->regs = fa.numRegs;
+
+    CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) n_replicas * E->Y.img_bytes));
+    // tick-0 image: empty network, one spare slot per spawn lane
+    E->init_image.assign(E->Y.img_bytes, 0);
+    {
+        RepHeader *h = (RepHeader *) E->init_image.data();
+        h->n_slots = E->n_spawn_lanes;
+        int *vid = (int *) (E->init_image.data() + E->Y.o_vid);
+        for (int i = 0; i < E->Y.Vcap; ++i) vid[i] = -1;
+        short *blk = (short *) (E->init_image.data() + E->Y.o_blk);
+        for (int i = 0; i < E->Y.Vcap; ++i) blk[i] = -1;
+    }
+    size_t io = (size_t) n_replicas * A;
+    CUDA_TRY(cudaMalloc((void **) &E->d_actions, io * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void **) &E->d_obs, io * S.obs_dim * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void **) &E->d_reward, io * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void **) &E->d_rg, (size_t) n_replicas * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void **) &E->d_mask, io * S.n_actions));
+    CUDA_TRY(cudaMallocHost((void **) &E->h_actions, io * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void **) &E->h_obs, io * S.obs_dim * sizeof(float)));
+    CUDA_TRY(cudaMallocHost((void **) &E->h_reward, io * sizeof(float)));
+    CUDA_TRY(cudaMallocHost((void **) &E->h_rg, (size_t) n_replicas * sizeof(float)));
+    CUDA_TRY(cudaMallocHost((void **) &E->h_mask, io * S.n_actions));
+    *out = E;
+    int r = tsc_reset(E, nullptr);
+    if (r) { tsc_destroy(E); *out = nullptr; return r; }
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+void tsc_destroy(tsc_handle E) {
+    if (!E) return;
+    cudaSetDevice(E->device);
+    for (void *p : E->dev_allocs) cudaFree(p);
+    cudaFree(E->images); cudaFree(E->d_actions); cudaFree(E->d_obs); cudaFree(E->d_reward); cudaFree(E->d_rg); cudaFree(E->d_mask);
+    cudaFreeHost(E->h_actions); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_reward); cudaFreeHost(E->h_rg); cudaFreeHost(E->h_mask);
+    delete E;
+}
+
+int tsc_get_dims(tsc_handle E, int32_t *n_replicas, int32_t *n_lanes, int32_t *n_signals, int32_t *obs_dim, int32_t *state_dim,
+                 int32_t *n_actions, int32_t *n_in_total, int32_t *n_out_total, int32_t *visibility) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    if (n_replicas) *n_replicas = E->B;
+    if (n_lanes) *n_lanes = E->S.L;
+    if (n_signals) *n_signals = E->S.A;
+    if (obs_dim) *obs_dim = E->S.obs_dim;
+    if (state_dim) *state_dim = E->S.state_dim;
+    if (n_actions) *n_actions = E->S.n_actions;
+    if (n_in_total) *n_in_total = E->S.n_in_total;
+    if (n_out_total) *n_out_total = E->S.n_out_total;
+    if (visibility) *visibility = E->S.visibility;
+    return 0;
+}
+
+int tsc_reset(tsc_handle E, void *stream) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(E->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    // the initial image is tiny compared with B of them: upload once, then replicate on the device
+    CUDA_TRY(cudaMemcpyAsync(E->images, E->init_image.data(), E->Y.img_bytes, cudaMemcpyHostToDevice, st));
+    size_t done = 1;
+    while (done < (size_t) E->B) {
+        size_t n = done < (size_t) E->B - done ? done : (size_t) E->B - done;
+        CUDA_TRY(cudaMemcpyAsync(E->images + done * E->Y.img_bytes, E->images, n * E->Y.img_bytes, cudaMemcpyDeviceToDevice, st));
+        done += n;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int launch(tsc_handle E, const StepArgs &a, void *stream) {
+    CUDA_TRY(cudaSetDevice(E->device));
+    tsc_step_kernel<NT><<<E->grid, NT, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    E->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static StepArgs blank_args(tsc_handle E) {
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = E->B; a.init_program = -1;
+    return a;
+}
+
+int tsc_set_phase(tsc_handle E, const int32_t *raw_phase, void *stream) {
+    if (!E || !raw_phase) return fail(TSC_EINVAL, "null argument");
+    StepArgs a = blank_args(E);
+    a.set_raw_phase = 1; a.raw_phase = raw_phase;
+    return launch(E, a, stream);
+}
+
+int tsc_init_program(tsc_handle E, int32_t phase_index, void *stream) {
+    if (!E || phase_index < 0) return fail(TSC_EINVAL, "bad argument");
+    StepArgs a = blank_args(E);
+    a.init_program = phase_index;
+    return launch(E, a, stream);
+}
+
+int tsc_step(tsc_handle E, int32_t n_ticks, void *stream) {
+    if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
+    StepArgs a = blank_args(E);
+    a.n_ticks = n_ticks;
+    return launch(E, a, stream);
+}
+
+int tsc_retrieve(tsc_handle E, const tsc_outputs_t *out, void *stream) {
+    if (!E || !out) return fail(TSC_EINVAL, "null argument");
+    StepArgs a = blank_args(E);
+    a.do_retrieve = 1; a.out = *out;
+    return launch(E, a, stream);
+}
+
+int tsc_env_step(tsc_handle E, const int32_t *actions, int32_t controller, int32_t controller_arg, int32_t n_ticks,
+                 const tsc_outputs_t *out, void *stream) {
+    if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
+    if (controller == TSC_CTRL_EXTERNAL && !actions) return fail(TSC_EINVAL, "actions required for TSC_CTRL_EXTERNAL");
+    StepArgs a = blank_args(E);
+    a.apply_actions = controller == TSC_CTRL_FIXED_TIME ? 2 : 1;
+    a.controller_arg = controller_arg; a.actions = actions; a.n_ticks = n_ticks;
+    if (out) { a.do_retrieve = 1; a.out = *out; }
+    return launch(E, a, stream);
+}
+
+int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t controller, int32_t controller_arg, int32_t n_ticks,
+                      float *obs_host, float *reward_host, uint8_t *mask_host, float *reward_global_host) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(E->device));
+    const size_t io = (size_t) E->B * E->S.A;
+    if (controller == TSC_CTRL_EXTERNAL) {
+        if (!actions_host) return fail(TSC_EINVAL, "actions required for TSC_CTRL_EXTERNAL");
+        memcpy(E->h_actions, actions_host, io * sizeof(int));
+        CUDA_TRY(cudaMemcpyAsync(E->d_actions, E->h_actions, io * sizeof(int), cudaMemcpyHostToDevice, 0));
+    }
+    tsc_outputs_t o;
+    memset(&o, 0, sizeof o);
+    if (obs_host) o.obs = E->d_obs;
+    if (reward_host) o.reward = E->d_reward;
+    if (mask_host) o.mask = E->d_mask;
+    if (reward_global_host) o.reward_global = E->d_rg;
+    int rc = tsc_env_step(E, E->d_actions, controller, controller_arg, n_ticks, &o, nullptr);
+    if (rc) return rc;
+    if (obs_host) CUDA_TRY(cudaMemcpyAsync(E->h_obs, E->d_obs, io * E->S.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(E->h_reward, E->d_reward, io * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (mask_host) CUDA_TRY(cudaMemcpyAsync(E->h_mask, E->d_mask, io * E->S.n_actions, cudaMemcpyDeviceToHost, 0));
+    if (reward_global_host) CUDA_TRY(cudaMemcpyAsync(E->h_rg, E->d_rg, (size_t) E->B * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    if (obs_host) memcpy(obs_host, E->h_obs, io * E->S.obs_dim * sizeof(float));
+    if (reward_host) memcpy(reward_host, E->h_reward, io * sizeof(float));
+    if (mask_host) memcpy(mask_host, E->h_mask, io * E->S.n_actions);
+    if (reward_global_host) memcpy(reward_global_host, E->h_rg, (size_t) E->B * sizeof(float));
+    return 0;
+}
+
+int tsc_snapshot(tsc_handle E, int32_t b, int32_t cap, int32_t *vid, int32_t *drivable, double *distance, double *speed,
+                 int32_t *blocker_vid, int32_t *enter_ll_time) {
+    if (!E || b < 0 || b >= E->B) return fail(TSC_EINVAL, "bad replica index");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<unsigned char> img(E->Y.img_bytes);
+    CUDA_TRY(cudaMemcpy(img.data(), E->images + (size_t) b * E->Y.img_bytes, E->Y.img_bytes, cudaMemcpyDeviceToHost));
+    const Layout &Y = E->Y;
+    const RepHeader *h = (const RepHeader *) img.data();
+    const int *v = (const int *) (img.data() + Y.o_vid);
+    const int *el = (const int *) (img.data() + Y.o_ellt);
+    const u16 *dr = (const u16 *) (img.data() + Y.o_drv);
+    const short *bl = (const short *) (img.data() + Y.o_blk);
+    const double *ps = (const double *) (img.data() + Y.o_pos), *sp = (const double *) (img.data() + Y.o_spd);
+    int n = 0;
+    for (int i = 0; i < h->n_slots; ++i) {
+        if (v[i] < 0) continue;
+        if (n < cap) {
+            if (vid) vid[n] = v[i];
+            if (drivable) drivable[n] = dr[i];
+            if (distance) distance[n] = ps[i];
+            if (speed) speed[n] = sp[i];
+            if (blocker_vid) blocker_vid[n] = bl[i] >= 0 ? v[bl[i]] : -1;
+            if (enter_ll_time) enter_ll_time[n] = el[i];
+        }
+        ++n;
+    }
+    return n;
+}
+
+int tsc_load_snapshot(tsc_handle E, int32_t b, int32_t n, const int32_t *vid, const int32_t *drivable, const double *distance,
+                      const double *speed, const int32_t *route_pos) {
+    if (!E || b < 0 || b >= E->B || n < 0) return fail(TSC_EINVAL, "bad argument");
+    if (n && (!drivable || !distance || !speed)) return fail(TSC_EINVAL, "null array");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const Layout &Y = E->Y;
+    const int D = E->S.D, L = E->S.L;
+    std::vector<unsigned char> img(Y.img_bytes);
+    CUDA_TRY(cudaMemcpy(img.data(), E->images + (size_t) b * Y.img_bytes, Y.img_bytes, cudaMemcpyDeviceToHost));
+    RepHeader *h = (RepHeader *) img.data();
+    u16 *cnt = (u16 *) (img.data() + Y.o_cnt);
+    int *v = (int *) (img.data() + Y.o_vid), *rp = (int *) (img.data() + Y.o_rpos), *el = (int *) (img.data() + Y.o_ellt);
+    u16 *dr = (u16 *) (img.data() + Y.o_drv);
+    short *bl = (short *) (img.data() + Y.o_blk);
+    u8 *pj = img.data() + Y.o_pj;
+    double *ps = (double *) (img.data() + Y.o_pos), *sp = (double *) (img.data() + Y.o_spd);
+    if (n + E->n_spawn_lanes > Y.Vcap) return fail(TSC_EOVERFLOW, "snapshot of %d vehicles exceeds vehicle_capacity", n);
+    for (int d = 0; d < D; ++d) cnt[d] = 0;
+    int prev = -1;
+    for (int i = 0; i < n; ++i) {
+        if (drivable[i] < prev || drivable[i] >= D || drivable[i] < 0) return fail(TSC_EINVAL, "snapshot must be drivable-major");
+        prev = drivable[i];
+        cnt[drivable[i]] += 1;
+    }
+    int slot = 0, k = 0;
+    for (int d = 0; d < D; ++d) {
+        for (int j = 0; j < cnt[d]; ++j, ++k, ++slot) {
+            v[slot] = vid ? vid[k] : k;
+            ps[slot] = distance[k]; sp[slot] = speed[k];
+            rp[slot] = route_pos ? route_pos[k] : 0;
+            el[slot] = d >= L ? 0 : INT_MAX; bl[slot] = -1; dr[slot] = (u16) d; pj[slot] = 0;
+        }
+        if (d < L && E->h_is_spawn[d]) { v[slot] = -1; ++slot; }
+    }
+    h->n_slots = slot; h->n_running = n;
+    CUDA_TRY(cudaMemcpy(E->images + (size_t) b * Y.img_bytes, img.data(), Y.img_bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int tsc_check(tsc_handle E, int32_t *first_bad) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<RepHeader> hs(E->B);
+    CUDA_TRY(cudaMemcpy2D(hs.data(), sizeof(RepHeader), E->images, E->Y.img_bytes, sizeof(RepHeader), E->B, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < E->B; ++b) {
+        if (hs[b].err) {
+            if (first_bad) *first_bad = b;
+            if (hs[b].err & (ERR_OVERFLOW | ERR_ENT_OVERFLOW))
+                return fail(TSC_EOVERFLOW, "replica %d exceeded vehicle_capacity (flags 0x%x)", b, hs[b].err);
+            return fail(TSC_EORDER, "replica %d: a vehicle left its drivable out of order (flags 0x%x)", b, hs[b].err);
+        }
+    }
+    return 0;
+}
+
+int tsc_counters(tsc_handle E, int32_t *tick, int32_t *n_running, int32_t *n_finished, int32_t *n_slots) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<RepHeader> hs(E->B);
+    CUDA_TRY(cudaMemcpy2D(hs.data(), sizeof(RepHeader), E->images, E->Y.img_bytes, sizeof(RepHeader), E->B, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < E->B; ++b) {
+        if (tick) tick[b] = hs[b].tick;
+        if (n_running) n_running[b] = hs[b].n_running;
+        if (n_finished) n_finished[b] = hs[b].n_finished;
+        if (n_slots) n_slots[b] = hs[b].n_slots;
+    }
+    return 0;
+}
+
+int64_t tsc_launch_count(tsc_handle E) { return E ? E->launches : 0; }
+
+int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t *grid, int32_t *regs) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    if (smem_bytes) *smem_bytes = E->Y.smem_bytes;
+    if (threads) *threads = NT;
+    if (grid) *grid = E->grid;
+    if (regs) *regs = E->regs;
+    return 0;
+}
+
+}  // extern "C"
