@@ -62,7 +62,10 @@ enum {
 enum { TSC_REWARD_QUEUE = 0, TSC_REWARD_PRESSURE = 1 };
 enum { TSC_OBS_LANE_FEATURES = 0, TSC_OBS_POSITION_MATRIX = 1 };
 enum { TSC_ACT_PHASE_SELECTION = 0, TSC_ACT_PHASE_SWITCH = 1 };
-enum { TSC_CTRL_EXTERNAL = 0, TSC_CTRL_FIXED_TIME = 1 };
+/* who picks the next phase in tsc_env_step: the caller's actions interpreted by the scenario's action
+ * space; the in-kernel fixed-time controller; or the caller's actions taken as pytsc phase indices
+ * (TSController.switch_phase, backends/cityflow/traffic_signal.py:51-59) whatever the action space. */
+enum { TSC_CTRL_EXTERNAL = 0, TSC_CTRL_FIXED_TIME = 1, TSC_CTRL_PHASE_INDEX = 2 };
 
 /* A compiled scenario: flat, read-only tables built on the host by
  * pytsc_b200.scenario.compile_scenario().  All pointers are HOST pointers,
@@ -196,7 +199,7 @@ int  tsc_step(tsc_handle h, int32_t n_ticks, void *stream);
 int  tsc_retrieve(tsc_handle h, const tsc_outputs_t *out, void *stream);
 
 /* Fused TrafficSignalNetwork.step: apply actions (device int32 [B][A]; ignored
- * when controller != TSC_CTRL_EXTERNAL), n_ticks engine ticks, then everything
+ * when controller == TSC_CTRL_FIXED_TIME), n_ticks engine ticks, then everything
  * tsc_retrieve does.  controller_arg = green time for TSC_CTRL_FIXED_TIME
  * (controllers/controllers.py:26-54). */
 int  tsc_env_step(tsc_handle h, const int32_t *actions, int32_t controller, int32_t controller_arg,

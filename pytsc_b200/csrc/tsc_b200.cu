@@ -87,7 +87,7 @@ struct Layout {
 struct StepArgs {
     int B;
     int n_ticks;
-    int apply_actions;     // 0 none, 1 external actions, 2 fixed-time controller
+    int apply_actions;     // 0 none, 1 external actions, 2 fixed-time controller, 3 external phase indices
     int controller_arg;
     int do_retrieve;
     int set_raw_phase;     // 1: raw_phase input given
@@ -638,7 +638,8 @@ __device__ void apply_controller(const DevScn &S, Ctx &c, const StepArgs &a, int
                 idx = (__ldg(S.sig_phase_green + s * S.P + cur) && t < a.controller_arg) ? cur : (cur + 1) % P;
             } else {
                 int act = a.actions[(size_t) b * S.A + s];
-                if (S.action_space == TSC_ACT_PHASE_SWITCH) idx = act == 1 ? (cur + 1) % P : cur;   // actions.py:152-158
+                if (a.apply_actions == 3) idx = act;                                               // TSController.switch_phase(index)
+                else if (S.action_space == TSC_ACT_PHASE_SWITCH) idx = act == 1 ? (cur + 1) % P : cur;   // actions.py:152-158
                 else idx = act;                                                                    // actions.py:106-108
                 if (idx < 0 || idx >= P) idx = cur;
             }
@@ -1270,23 +1271,34 @@ int tsc_retrieve(tsc_handle E, const tsc_outputs_t *out, void *stream) {
 int tsc_env_step(tsc_handle E, const int32_t *actions, int32_t controller, int32_t controller_arg, int32_t n_ticks,
                  const tsc_outputs_t *out, void *stream) {
     if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
-    if (controller == TSC_CTRL_EXTERNAL && !actions) return fail(TSC_EINVAL, "actions required for TSC_CTRL_EXTERNAL");
+    if (controller != TSC_CTRL_FIXED_TIME && !actions) return fail(TSC_EINVAL, "actions required unless TSC_CTRL_FIXED_TIME");
+    if (controller < TSC_CTRL_EXTERNAL || controller > TSC_CTRL_PHASE_INDEX) return fail(TSC_EINVAL, "unknown controller %d", controller);
     StepArgs a = blank_args(E);
-    a.apply_actions = controller == TSC_CTRL_FIXED_TIME ? 2 : 1;
+    a.apply_actions = controller == TSC_CTRL_FIXED_TIME ? 2 : (controller == TSC_CTRL_PHASE_INDEX ? 3 : 1);
     a.controller_arg = controller_arg; a.actions = actions; a.n_ticks = n_ticks;
     if (out) { a.do_retrieve = 1; a.out = *out; }
     return launch(E, a, stream);
+}
+
+// true when `p` is page-locked host memory CUDA can DMA to directly
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
 }
 
 int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t controller, int32_t controller_arg, int32_t n_ticks,
                       float *obs_host, float *reward_host, uint8_t *mask_host, float *reward_global_host) {
     if (!E) return fail(TSC_EINVAL, "null handle");
     CUDA_TRY(cudaSetDevice(E->device));
+    cudaStream_t st = 0;   // legacy default stream: ordered after work queued on any blocking stream
     const size_t io = (size_t) E->B * E->S.A;
-    if (controller == TSC_CTRL_EXTERNAL) {
-        if (!actions_host) return fail(TSC_EINVAL, "actions required for TSC_CTRL_EXTERNAL");
-        memcpy(E->h_actions, actions_host, io * sizeof(int));
-        CUDA_TRY(cudaMemcpyAsync(E->d_actions, E->h_actions, io * sizeof(int), cudaMemcpyHostToDevice, 0));
+    // page-locked caller buffers are used in place; pageable ones go through the handle's pinned staging
+    if (controller != TSC_CTRL_FIXED_TIME) {
+        if (!actions_host) return fail(TSC_EINVAL, "actions required unless TSC_CTRL_FIXED_TIME");
+        const int32_t *src = actions_host;
+        if (!is_pinned(actions_host)) { memcpy(E->h_actions, actions_host, io * sizeof(int)); src = E->h_actions; }
+        CUDA_TRY(cudaMemcpyAsync(E->d_actions, src, io * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     tsc_outputs_t o;
     memset(&o, 0, sizeof o);
@@ -1294,17 +1306,20 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     if (reward_host) o.reward = E->d_reward;
     if (mask_host) o.mask = E->d_mask;
     if (reward_global_host) o.reward_global = E->d_rg;
-    int rc = tsc_env_step(E, E->d_actions, controller, controller_arg, n_ticks, &o, nullptr);
+    int rc = tsc_env_step(E, E->d_actions, controller, controller_arg, n_ticks, &o, st);
     if (rc) return rc;
-    if (obs_host) CUDA_TRY(cudaMemcpyAsync(E->h_obs, E->d_obs, io * E->S.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, 0));
-    if (reward_host) CUDA_TRY(cudaMemcpyAsync(E->h_reward, E->d_reward, io * sizeof(float), cudaMemcpyDeviceToHost, 0));
-    if (mask_host) CUDA_TRY(cudaMemcpyAsync(E->h_mask, E->d_mask, io * E->S.n_actions, cudaMemcpyDeviceToHost, 0));
-    if (reward_global_host) CUDA_TRY(cudaMemcpyAsync(E->h_rg, E->d_rg, (size_t) E->B * sizeof(float), cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
-    if (obs_host) memcpy(obs_host, E->h_obs, io * E->S.obs_dim * sizeof(float));
-    if (reward_host) memcpy(reward_host, E->h_reward, io * sizeof(float));
-    if (mask_host) memcpy(mask_host, E->h_mask, io * E->S.n_actions);
-    if (reward_global_host) memcpy(reward_global_host, E->h_rg, (size_t) E->B * sizeof(float));
+    struct Out { void *user, *stage; const void *dev; size_t bytes; bool direct; } outs[4] = {
+        {obs_host, E->h_obs, E->d_obs, io * E->S.obs_dim * sizeof(float), false},
+        {reward_host, E->h_reward, E->d_reward, io * sizeof(float), false},
+        {mask_host, E->h_mask, E->d_mask, io * E->S.n_actions, false},
+        {reward_global_host, E->h_rg, E->d_rg, (size_t) E->B * sizeof(float), false}};
+    for (Out &x : outs) {
+        if (!x.user) continue;
+        x.direct = is_pinned(x.user);
+        CUDA_TRY(cudaMemcpyAsync(x.direct ? x.user : x.stage, x.dev, x.bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (Out &x : outs) if (x.user && !x.direct) memcpy(x.user, x.stage, x.bytes);
     return 0;
 }
 

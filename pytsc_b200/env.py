@@ -1,0 +1,160 @@
+"""Batched environment: B replicas of one scenario, device tensors in and out.
+
+The method names follow ``pytsc.TrafficSignalNetwork`` (``pytsc/__init__.py:
+17-182``) and the smac-style wrapper ``EPyMARLTrafficSignalNetwork``
+(``pytsc/wrappers/epymarl.py:11-111``), with a leading replica dimension:
+
+    env = BatchedTrafficSignalNetwork("hangzhou_4_4", n_replicas=4096,
+                                      signal={"reward_function": "max_pressure"})
+    obs, mask = env.reset()
+    reward, done, info = env.step(actions)        # actions: int32 [B, A] on the device
+    obs, mask, rewards = env.get_observations(), env.get_action_mask(), env.get_rewards()
+
+One ``step`` is one CUDA launch (``tsc_env_step``): phase program, delta_time
+engine ticks, Retriever reductions, per-signal stats, rewards, masks and
+observations.  Replicas shard across GPUs by giving each rank its own
+instance (``device=LOCAL_RANK``); nothing on the step path communicates.
+``all_reduce_episode_metrics`` is the one collective (NCCL, episode end).
+"""
+from __future__ import annotations
+
+from .backend.config import Config
+from .backend.network_parser import NetworkParser
+from .binding import Engine
+from .scenario import compile_scenario
+
+STEP_OUTPUTS = ("obs", "state", "reward", "reward_global", "mask", "sim", "metrics")
+LANE_OUTPUTS = ("lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed")
+
+
+class BatchedTrafficSignalNetwork:
+    def __init__(self, scenario, n_replicas=None, device=None, lane_outputs=False, **kwargs):
+        self.config = Config(scenario, **kwargs)
+        gpu = self.config.gpu
+        self.parsed_network = NetworkParser(self.config)
+        self.scenario = compile_scenario(self.config, self.parsed_network)
+        self.n_replicas = int(n_replicas if n_replicas is not None else gpu.get("n_replicas", 1))
+        dev = int(device if device is not None else gpu.get("device", 0))
+        self.engine = Engine(self.scenario, self.n_replicas, dev, int(gpu.get("vehicle_capacity", 0)) or 1024)
+        self.torch = self.engine.torch
+        self.device = self.engine.device
+        self.n_agents = self.engine.A
+        names = STEP_OUTPUTS + (LANE_OUTPUTS if lane_outputs else ())
+        self.out = self.engine.alloc_outputs(names)
+        sim = self.config.simulator
+        self.delta_time = int(sim["delta_time"])
+        self._episode_ticks = int(sim["episode_limit"])
+        self._sim_length = int(sim["sim_length"])
+        self._wait = int(sim["initial_wait_time"])
+        self.episode_count = 0
+        self.hour_count = 0
+        self._acc = self.torch.zeros(4, dtype=self.torch.float64, device=self.device)
+        self.reset()
+
+    # ---- sizes (pytsc/__init__.py:118-138) --------------------------------------------
+    def get_action_size(self):
+        return self.engine.dims["n_actions"]
+
+    def get_observation_size(self):
+        return self.engine.dims["obs_dim"]
+
+    def get_state_size(self):
+        return self.engine.dims["state_dim"]
+
+    @property
+    def episode_limit(self):
+        return int(self._episode_ticks / self.delta_time)
+
+    @property
+    def sim_step(self):
+        return self._tick - self._wait
+
+    @property
+    def episode_over(self):
+        return self.sim_step > 0 and self.sim_step % self._episode_ticks == 0
+
+    @property
+    def is_terminated(self):
+        return self.sim_step == self._sim_length
+
+    # ---- lifecycle ----------------------------------------------------------------------
+    def reset(self):
+        """Engine back to tick 0 (a new ``cityflow.Engine`` in the reference,
+        pytsc/__init__.py:164-176), programs on phase 0, first measurements."""
+        self.engine.reset()
+        self.engine.init_program(0)
+        self._tick = 0
+        if self._wait:
+            self.engine.step(self._wait)
+            self._tick = self._wait
+        self.engine.retrieve(self.out)
+        return self.out["obs"], self.out["mask"]
+
+    def restart(self):
+        """pytsc/__init__.py:164-176."""
+        if self.episode_over:
+            self.episode_count += 1
+        if self.is_terminated:
+            self.hour_count += 1
+            self.reset()
+
+    def close(self):
+        self.engine.close()
+
+    # ---- the step (pytsc/__init__.py:178-182) ---------------------------------------------
+    def step(self, actions=None, controller=None, green_time=25):
+        """``actions``: int32 [B, A] device tensor in the configured action space; or
+        ``controller="fixed_time"`` to let the in-kernel FixedTimeController act."""
+        if controller == "fixed_time":
+            self.engine.env_step(None, self.out, n_ticks=self.delta_time, controller=1, controller_arg=green_time)
+        else:
+            self.engine.env_step(actions, self.out, n_ticks=self.delta_time, controller=0)
+        self._tick += self.delta_time
+        self._acc[0] += self.out["reward_global"].sum()
+        self._acc[1] += self.out["metrics"][:, 0].sum()
+        self._acc[2] += self.n_replicas
+        return self.out["reward_global"], self.episode_over, self.get_env_info()
+
+    # getters return the tensors the last launch wrote (no copies, no syncs)
+    def get_observations(self):
+        return self.out["obs"]
+
+    def get_state(self):
+        return self.out["state"]
+
+    def get_action_mask(self):
+        return self.out["mask"]
+
+    def get_reward(self):
+        return self.out["reward_global"]
+
+    def get_rewards(self):
+        return self.out["reward"]
+
+    def get_env_info(self):
+        """Per-replica step statistics (backends/cityflow/metrics.py:221-232) as tensors."""
+        m, s = self.out["metrics"], self.out["sim"]
+        return {"time_step": s[:, 2], "average_travel_time": s[:, 1], "n_queued": m[:, 0], "mean_speed": m[:, 1],
+                "mean_delay": m[:, 2], "density": m[:, 3], "pressure": m[:, 4], "network_flow": m[:, 5],
+                "episode_count": self.episode_count, "episode_limit": self.episode_limit}
+
+    def check(self):
+        """Synchronise and raise if any replica overflowed its vehicle capacity."""
+        self.engine.check()
+
+    # ---- multi-GPU: the one collective ------------------------------------------------------
+    def all_reduce_episode_metrics(self, group=None):
+        """Global episode metrics over every rank's replicas: a single NCCL
+        all-reduce(SUM) of a 7-element fp64 vector."""
+        torch = self.torch
+        s = self.out["sim"]
+        vec = torch.stack([s[:, 1].sum(), s[:, 3].sum(), s[:, 0].sum(),
+                           self._acc[0], self._acc[1], self._acc[2],
+                           torch.tensor(float(self.n_replicas), dtype=torch.float64, device=self.device)])
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        v = vec.tolist()
+        n, steps = max(v[6], 1.0), max(v[5], 1.0)
+        return {"average_travel_time": v[0] / n, "finished_vehicles": v[1], "running_vehicles": v[2],
+                "mean_global_reward": v[3] / steps, "mean_n_queued": v[4] / steps, "replicas": int(v[6])}

@@ -75,3 +75,28 @@ def compare_snapshots(so, sg, tol=0.0):
             i = int(np.argmax(d))
             return f"{k} differs for uid {so['uid'][i]}: {so[k][i]!r} vs {sg[k][i]!r}"
     return None
+
+
+# ---- golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py) ----
+def golden_cases():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    import ast
+    with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    g["scenario"] = str(g["scenario"])
+    g["kwargs"] = ast.literal_eval(str(g["kwargs"]))
+    return g
+
+
+def golden_scenario(g, **gpu):
+    """Compile the scenario a golden case was recorded on."""
+    kw = {k: dict(v) for k, v in g["kwargs"].items()}
+    if gpu:
+        kw["gpu"] = gpu
+    cfg, parser, cs = build_scenario(g["scenario"], **kw)
+    assert cs.lane_ids == [str(x) for x in g["lane_ids"]]
+    assert cs.signal_ids == [str(x) for x in g["signal_ids"]]
+    return cfg, parser, cs
