@@ -31,7 +31,28 @@ typedef unsigned char u8;
 typedef unsigned short u16;
 typedef unsigned int u32;
 
+// Packed static tables: one 32-byte load per lane-link, one 48-byte load per cross,
+// instead of chains of dependent 4-byte loads through seven separate arrays.
+struct __align__(16) LLInfo {
+    int start_lane, end_lane;
+    int cross_off, cross_end;     // range in the cross table, ascending distance along the link
+    double length;
+    int type;                     // 3 go_straight, 2 turn_left, 1 turn_right
+    int sigbit;                   // signal | road-link << 16
+};
+static_assert(sizeof(LLInfo) == 32, "LLInfo must be 32 bytes");
+struct __align__(16) CrossEntry {
+    double dist;                  // distance of the cross along this lane-link
+    double foe_dist;              // ... along the other lane-link
+    double foe_len;               // length of the other lane-link
+    double foe_sl_len;            // length of the other link's start lane
+    int foe_ll, foe_start_lane, foe_end_lane, foe_type;
+};
+static_assert(sizeof(CrossEntry) == 48, "CrossEntry must be 48 bytes");
+
 struct DevScn {   // device copies of tsc_scenario_t tables
+    const LLInfo *llinfo;
+    const CrossEntry *cross;
     int L, K, D, A, N, T, horizon, max_raw, P;
     int n_in_total, n_out_total, n_spawn_lanes;
     const double *drv_length, *drv_max_speed;
@@ -65,7 +86,8 @@ struct RepHeader {   // 64 bytes, first thing in every replica image
     long long fin_enter;  // sum of creation ticks of finished vehicles
     u32 err;              // sticky error bits
     int n_ent;            // scratch: movers this tick
-    int pad[6];
+    int n_x;              // scratch: vehicles deferred to the cross phase this tick
+    int pad[5];
 };
 static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 
@@ -79,8 +101,9 @@ struct Layout {
     int o_cnt, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
     int o_pos, o_spd, o_rpos, o_vid, o_ellt, o_blk, o_drv, o_pj, img_bytes;
     // shared-memory-only scratch
-    int o_vid2, o_drv2, o_ellt2, o_pj2;
-    int o_npos, o_nspd, o_nrpos, o_nblk, o_newslot, o_nflag, o_off, o_leave, o_ent, o_fresh, o_entlist,
+    int o_vid2, o_ellt2, o_pj2;
+    int o_dn, o_dn2, o_xlist, o_avail, o_tmpl;
+    int o_npos, o_nspd, o_nrpos, o_nblk, o_nflag, o_off, o_leave, o_ent, o_fresh, o_entlist,
         o_entpos, o_entdrv, o_scan, o_lane_q, smem_bytes;
 };
 
@@ -110,9 +133,14 @@ __device__ __forceinline__ int trunc_int_x86(double x) {
     return (int) x;
 }
 
+#define SMEM_TEMPLATES 4   // vehicle templates cached in shared memory (more: read from global)
+
 struct Ctx {
     RepHeader *h;
-    u16 *cnt, *off, *wq, *leave, *ent, *newslot, *drv, *drv2, *entlist, *entdrv;
+    u16 *cnt, *off, *wq, *leave, *ent, *newslot, *entlist, *entdrv, *xlist;
+    u32 *dn, *dn2;        // per vehicle: drivable | next drivable << 16 (0xFFFF = route ends)
+    u32 *avail;           // bit per lane-link: its road-link is green in the signal's current phase
+    const double *tmpl;   // vehicle templates (shared-memory copy when they fit)
     u8 *sraw, *scur, *schg, *pj, *pj2, *nflag, *fresh;
     int *stop, *rpos, *vid, *vid2, *ellt, *ellt2, *nrpos, *scan;
     short *blk, *nblk;
@@ -120,8 +148,8 @@ struct Ctx {
     int tick;
 };
 
-__device__ __forceinline__ const double *tmpl_of(const DevScn &S, int vid) {
-    return S.tmpl + (S.T == 1 ? 0 : TSC_T_STRIDE * __ldg(S.veh_tmpl + vid));
+__device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, int vid) {
+    return c.tmpl + (S.T == 1 ? 0 : TSC_T_STRIDE * __ldg(S.veh_tmpl + vid));
 }
 
 // ---- A.4 car following -------------------------------------------------------
@@ -174,26 +202,24 @@ __device__ int reach_steps(const double *T, double v, double distance, bool turn
     return trunc_int_x86(ceil((target - v) / acc / dt)) + trunc_int_x86(ceil((distance - dUntil) / target / dt));
 }
 
-__device__ __forceinline__ bool ll_available(const DevScn &S, const Ctx &c, int ll) {
-    int a = __ldg(S.ll_signal + ll);
-    u32 m = __ldg(S.sig_phase_mask + a * S.max_raw + c.sraw[a]);
-    return (m >> __ldg(S.ll_roadlink + ll)) & 1u;
-}
+__device__ __forceinline__ bool ll_available(const Ctx &c, int ll) { return (c.avail[ll >> 5] >> (ll & 31)) & 1u; }
 
-// Which vehicle does lane-link `f` announce at its cross lying `dc` along it
-// (CityFlow notifyCross; closed form of the sequential scan)?
-// Returns the slot or -1; *d2 = its signed distance to the cross.
-__device__ int cross_claimant(const DevScn &S, const Ctx &c, int f, double dc, double *d2) {
-    int fl = S.L + f;
-    double flen = __ldg(S.drv_length + fl);
-    int el = __ldg(S.ll_end_lane + f);
-    int n = c.cnt[el];
+// Which vehicle does the lane-link described by `X` (the foe side of a cross)
+// announce at that cross (CityFlow notifyCross; closed form of the sequential
+// scan)?  Returns the slot or -1; *d2 = its signed distance to
+// the cross.  Conditions are ordered so that shared memory decides first and
+// the route table (global) is read only when everything else already holds.
+__device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X, double *d2) {
+    const int f = X.foe_ll, fl = S.L + f;
+    const double dc = X.foe_dist;
+    int n = c.cnt[X.foe_end_lane];
     if (n > 0) {   // the vehicle that has just moved onto the end lane
-        int t = c.off[el] + n - 1;
-        if (!c.pj[t] && __ldg(S.route_seq + c.rpos[t] - 1) == fl) {
-            double crossDistance = flen - dc;
-            double vehDistance = c.pos[t] - tmpl_of(S, c.vid[t])[TSC_T_LEN];
-            if (crossDistance + vehDistance < 0.0) { *d2 = -(c.pos[t] + crossDistance); return t; }
+        int t = c.off[X.foe_end_lane] + n - 1;
+        double crossDistance = X.foe_len - dc;
+        double vehDistance = c.pos[t] - tmpl_of(S, c, c.vid[t])[TSC_T_LEN];
+        if (crossDistance + vehDistance < 0.0 && !c.pj[t] && __ldg(S.route_seq + c.rpos[t] - 1) == fl) {
+            *d2 = -(c.pos[t] + crossDistance);
+            return t;
         }
     }
     n = c.cnt[fl];
@@ -202,33 +228,32 @@ __device__ int cross_claimant(const DevScn &S, const Ctx &c, int f, double dc, d
         int v = base + k;
         double vd = c.pos[v];
         if (vd > dc) {
-            if (vd - dc - tmpl_of(S, c.vid[v])[TSC_T_LEN] <= 0.0) { *d2 = dc - vd; return v; }
+            if (vd - dc - tmpl_of(S, c, c.vid[v])[TSC_T_LEN] <= 0.0) { *d2 = dc - vd; return v; }
         } else { *d2 = dc - vd; return v; }
     }
-    int sl = __ldg(S.ll_start_lane + f);
-    if (c.cnt[sl] > 0) {   // first vehicle of the incoming lane, heading here on green
-        int hd = c.off[sl];
-        if (__ldg(S.route_seq + c.rpos[hd] + 1) == fl && ll_available(S, c, f)) {
-            *d2 = (__ldg(S.drv_length + sl) - c.pos[hd]) + dc;
+    if (c.cnt[X.foe_start_lane] > 0 && ll_available(c, f)) {   // first vehicle of the incoming lane, heading here on green
+        int hd = c.off[X.foe_start_lane];
+        if ((int) (c.dn[hd] >> 16) == fl) {
+            *d2 = (X.foe_sl_len - c.pos[hd]) + dc;
             return hd;
         }
     }
     return -1;
 }
 
-// Cross::canPass (A.5).  *foe_out = announced vehicle on the other link.
-__device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T, int ll, int x, double dts,
+// Cross::canPass (A.5) for vehicle `me` on / approaching a lane-link of type t1,
+// at the cross `X`.  *foe_out = announced vehicle on the other link.
+__device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T, int t1, const CrossEntry &X, double dts,
                          double dt, int *foe_out) {
-    int fll = __ldg(S.xr_foe_ll + x);
     double d2;
-    int foe = cross_claimant(S, c, fll, __ldg(S.xr_foe_dist + x), &d2);
+    int foe = cross_claimant(S, c, X, &d2);
     *foe_out = foe;
     if (foe < 0) return true;
-    int t1 = __ldg(S.ll_type + ll), t2 = __ldg(S.ll_type + fll);
-    double d1 = __ldg(S.xr_dist + x) - dts;
+    int t2 = X.foe_type;
+    double d1 = X.dist - dts;
     double v = c.spd[me];
     if (!can_yield(T, v, d1)) return true;
-    const double *TF = tmpl_of(S, c.vid[foe]);
+    const double *TF = tmpl_of(S, c, c.vid[foe]);
     double vf = c.spd[foe];
     int yield = 0;
     if (!can_yield(TF, vf, d2)) yield = 1;
@@ -306,6 +331,41 @@ __device__ void block_scan_counts(const u16 *in, const u8 *extra_lane, int n_lan
     __syncthreads();
 }
 
+// Commit one vehicle's decision into the tick's buffers: clamp the speed, advance
+// along the route, and register the move if it leaves its drivable (A.4).
+__device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y, Ctx &c, int i, const double *T, int d, int rp,
+                                               double x, double v, double dlen, double ns, int blocker, double dt) {
+    ns = max2(ns, v - T[TSC_T_MAX_NEG_ACC] * dt);
+    double delta;
+    if (ns < 0) { delta = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC]; ns = 0; }
+    else delta = (v + ns) * dt / 2;
+    double nx = delta + x;
+    int q = rp, dd = d, hops = 0;
+    bool end = false;
+    double cl = dlen;
+    while (nx > cl) {   // walk forward through the drivables
+        nx -= cl;
+        int nxt = __ldg(S.route_seq + q + 1);
+        if (nxt < 0) { end = true; break; }
+        ++q; dd = nxt; ++hops;
+        cl = __ldg(S.drv_length + dd);
+    }
+    c.npos[i] = nx; c.nspd[i] = ns; c.nrpos[i] = q; c.nblk[i] = (short) blocker;
+    u8 fl = 8;                       // bit3: valid vehicle
+    if (hops > 0 || end) fl |= 1;    // leaves its drivable
+    if (end) fl |= 2;
+    if (hops > 1) fl |= 4;           // skipped a whole drivable
+    c.nflag[i] = fl;
+    if (fl & 1) {
+        atomicAdd((unsigned *) &c.leave[d & ~1], (d & 1) ? 0x10000u : 1u);
+        if (!end) {
+            atomicAdd((unsigned *) &c.ent[dd & ~1], (dd & 1) ? 0x10000u : 1u);
+            int k = atomicAdd(&c.h->n_ent, 1);
+            if (k < Y.ent_cap) { c.entlist[k] = (u16) i; c.entdrv[k] = (u16) dd; c.entpos[k] = nx; }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------
 // One engine tick for the replica held in shared memory (A.2)
 // ----------------------------------------------------------------------------
@@ -330,14 +390,16 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 bool ok = true;
                 if (n > 0) {
                     int t = c.off[l] + n - 1;
-                    ok = c.pos[t] > tmpl_of(S, c.vid[t])[TSC_T_LEN] + tmpl_of(S, v)[TSC_T_MIN_GAP];
+                    ok = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of(S, c, v)[TSC_T_MIN_GAP];
                 }
                 if (ok) {
                     int slot = c.off[l] + n;
+                    int rp0 = __ldg(S.veh_seq_start + v);
                     c.pos[slot] = 0.0; c.spd[slot] = 0.0;
-                    c.rpos[slot] = __ldg(S.veh_seq_start + v);
+                    c.rpos[slot] = rp0;
                     c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
-                    c.drv[slot] = (u16) l; c.pj[slot] = 0;
+                    c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
+                    c.pj[slot] = 0;
                     c.cnt[l] = (u16) (n + 1);
                     c.wq[s] = (u16) (hd + 1);
                     fr = 1;
@@ -348,15 +410,18 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         c.fresh[l] = fr;
     }
     for (int d = tid; d < D; d += NT) { c.leave[d] = 0; c.ent[d] = 0; }
-    if (tid == 0) c.h->n_ent = 0;
+    if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; }
     __syncthreads();
 
-    // ---- getAction: next speed / position of every running vehicle from the old state ----
+    // ---- getAction, phase 1: leader / gap, car following, red light; every vehicle, uniform cost.
+    //      Vehicles that must examine the crosses of a lane-link are deferred to phase 2. ----
     for (int i = tid; i < n_slots; i += NT) {
         int vid = c.vid[i];
         if (vid < 0) { c.nflag[i] = 0; continue; }
-        const double *T = tmpl_of(S, vid);
-        const int d = c.drv[i];
+        const double *T = tmpl_of(S, c, vid);
+        const u32 dnv = c.dn[i];
+        const int d = dnv & 0xFFFF;
+        const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
         const int rp = c.rpos[i];
         const double x = c.pos[i], v = c.spd[i];
         const double dlen = __ldg(S.drv_length + d);
@@ -366,22 +431,22 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         double gap = 0.0;
         if (i > c.off[d]) {
             leader = i - 1;
-            gap = c.pos[leader] - tmpl_of(S, c.vid[leader])[TSC_T_LEN] - x;
+            gap = c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN] - x;
         } else {
             double dist = dlen - x;
             const double horizon = T[TSC_T_MAX_SPEED] * T[TSC_T_MAX_SPEED] / T[TSC_T_USUAL_NEG_ACC] / 2 + T[TSC_T_MAX_SPEED] * dt * 2;
             for (int j = 1;; ++j) {
-                int nd = __ldg(S.route_seq + rp + j);
+                int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
                 if (nd < 0) break;
                 if (nd >= L) {
-                    int sl = __ldg(S.ll_start_lane + nd - L);
+                    int sl = __ldg(&S.llinfo[nd - L].start_lane);
                     int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
                     for (int e = e0; e < e1; ++e) {
                         int dl = L + __ldg(S.lane_ll + e);
                         int n = c.cnt[dl];
                         if (n > 0) {
                             int cand = c.off[dl] + n - 1;
-                            double cg = dist + c.pos[cand] - tmpl_of(S, c.vid[cand])[TSC_T_LEN];
+                            double cg = dist + c.pos[cand] - tmpl_of(S, c, c.vid[cand])[TSC_T_LEN];
                             if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
                         }
                     }
@@ -390,7 +455,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                     int n = c.cnt[nd] - c.fresh[nd];
                     if (n > 0) {
                         leader = c.off[nd] + n - 1;
-                        gap = dist + c.pos[leader] - tmpl_of(S, c.vid[leader])[TSC_T_LEN];
+                        gap = dist + c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN];
                         break;
                     }
                 }
@@ -403,26 +468,23 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
         ns = min2(ns, __ldg(S.drv_max_speed + d));
         double cf = T[TSC_T_MAX_SPEED];
-        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c.vid[leader])[TSC_T_MAX_NEG_ACC], dt);
+        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC], dt);
         ns = min2(ns, cf);
         // intersection related speed (A.5)
-        int blocker = -1;
         const bool on_ll = d >= L;
-        const int nd1 = __ldg(S.route_seq + rp + 1);
         if (on_ll || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {
             double vi = T[TSC_T_MAX_SPEED];
-            int ll = -1;
             bool done = false;
-            if (!on_ll && nd1 >= L) {
-                ll = nd1 - L;
-                int el = __ldg(S.ll_end_lane + ll);
+            if (!on_ll) {
+                const int ll = nd1 - L;
+                const int el = __ldg(&S.llinfo[ll].end_lane);
                 bool enter = true;
                 int n = c.cnt[el];
                 if (n > 0) {
                     int t = c.off[el] + n - 1;
-                    enter = c.pos[t] > tmpl_of(S, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
+                    enter = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
                 }
-                if (!ll_available(S, c, ll) || !enter) {
+                if (!ll_available(c, ll) || !enter) {
                     if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
                         // cannot stop before the line any more
                     } else {
@@ -430,63 +492,72 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                         done = true;
                     }
                 }
-                if (!done && __ldg(S.ll_type + ll) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
+                if (!done && __ldg(&S.llinfo[ll].type) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
             }
-            if (!done) {
-                if (ll < 0) ll = d - L;
-                double dts = on_ll ? x : -(dlen - x);
-                int x0 = __ldg(S.ll_cross_off + ll), x1 = __ldg(S.ll_cross_off + ll + 1);
-                for (int xi = x0; xi < x1; ++xi) {
-                    double dOn = __ldg(S.xr_dist + xi);
-                    if (dOn < dts) continue;
-                    int foe;
-                    if (!can_pass(S, c, i, T, ll, xi, dts, dt, &foe)) {
-                        vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST], dt));
-                        blocker = foe;
-                        break;
-                    }
-                }
+            if (!done) {   // phase 2 walks the crosses with a whole warp
+                c.npos[i] = vi; c.nspd[i] = ns;
+                c.xlist[atomicAdd(&c.h->n_x, 1)] = (u16) i;
+                continue;
             }
             ns = min2(ns, vi);
         }
-        ns = max2(ns, v - T[TSC_T_MAX_NEG_ACC] * dt);
-        double delta;
-        if (ns < 0) { delta = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC]; ns = 0; }
-        else delta = (v + ns) * dt / 2;
-        // walk forward through the drivables
-        double nx = delta + x;
-        int q = rp, dd = d, hops = 0;
-        bool end = false;
-        double cl = dlen;
-        while (nx > cl) {
-            nx -= cl;
-            int nxt = __ldg(S.route_seq + q + 1);
-            if (nxt < 0) { end = true; break; }
-            ++q; dd = nxt; ++hops;
-            cl = __ldg(S.drv_length + dd);
-        }
-        c.npos[i] = nx; c.nspd[i] = ns; c.nrpos[i] = q; c.nblk[i] = (short) blocker;
-        u8 fl = 8;                       // bit3: valid vehicle
-        if (hops > 0 || end) fl |= 1;    // leaves its drivable
-        if (end) fl |= 2;
-        if (hops > 1) fl |= 4;           // skipped a whole drivable
-        c.nflag[i] = fl;
-        if (fl & 1) {
-            atomicAdd((unsigned *) &c.leave[d & ~1], (d & 1) ? 0x10000u : 1u);
-            if (!end) {
-                atomicAdd((unsigned *) &c.ent[dd & ~1], (dd & 1) ? 0x10000u : 1u);
-                int k = atomicAdd(&c.h->n_ent, 1);
-                if (k < Y.ent_cap) { c.entlist[k] = (u16) i; c.entdrv[k] = (u16) dd; c.entpos[k] = nx; }
+        finish_vehicle(S, Y, c, i, T, d, rp, x, v, dlen, ns, -1, dt);
+    }
+    __syncthreads();
+
+    // ---- getAction, phase 2: one warp per deferred vehicle, one lane per cross.  canPass has no
+    //      side effects, so evaluating every cross ahead at once and taking the first refusal in
+    //      link order is the sequential scan of A.5(iii). ----
+    {
+        const int n_x = c.h->n_x;
+        const int lane = tid & 31;
+        for (int e = tid >> 5; e < n_x; e += NT / 32) {
+            const int i = c.xlist[e];
+            const double *T = tmpl_of(S, c, c.vid[i]);
+            const u32 dnv = c.dn[i];
+            const int d = dnv & 0xFFFF;
+            const bool on_ll = d >= L;
+            const int ll = on_ll ? d - L : (int) (dnv >> 16) - L;
+            const double x = c.pos[i], v = c.spd[i];
+            const double dlen = __ldg(S.drv_length + d);
+            const double dts = on_ll ? x : -(dlen - x);
+            const int4 head = __ldg((const int4 *) &S.llinfo[ll]);   // start_lane, end_lane, cross_off, cross_end
+            const int t1 = __ldg(&S.llinfo[ll].type);
+            double vi = c.npos[i], ns = c.nspd[i];
+            int blocker = -1;
+            for (int base = head.z; base < head.w; base += 32) {
+                const int xi = base + lane;
+                bool refuse = false;
+                int foe = -1;
+                double dOn = 0.0;
+                if (xi < head.w) {
+                    CrossEntry X;
+                    const int4 *src = (const int4 *) &S.cross[xi];
+                    int4 *dst = (int4 *) &X;
+                    dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+                    dOn = X.dist;
+                    if (!(dOn < dts)) refuse = !can_pass(S, c, i, T, t1, X, dts, dt, &foe);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, refuse);
+                if (m) {
+                    const int src_lane = __ffs(m) - 1;
+                    dOn = __shfl_sync(0xffffffffu, dOn, src_lane);
+                    foe = __shfl_sync(0xffffffffu, foe, src_lane);
+                    vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST], dt));
+                    blocker = foe;
+                    break;
+                }
             }
+            ns = min2(ns, vi);
+            if (lane == 0) finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker, dt);
         }
     }
     __syncthreads();
 
     // ---- updateLocation: new per-drivable counts, then a stable re-pack ----
-    // leave[] becomes the number of leavers, newcnt = cnt - leave + ent (kept in ent[])
+    // leave[] = number of leavers, new count = cnt - leave + ent (kept in ent[])
     for (int d = tid; d < D; d += NT) c.ent[d] = (u16) (c.cnt[d] - c.leave[d] + c.ent[d]);
     __syncthreads();
-    // reuse scan scratch; new offsets go to a temporary (nrpos is busy, so use scan+64..)
     u16 *noff = (u16 *) (c.scan + 64);
     block_scan_counts<NT>(c.ent, is_spawn_lane, L, noff, D, c.scan);
     const int n_ent = min(c.h->n_ent, Y.ent_cap);
@@ -500,7 +571,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         u8 fl = c.nflag[i];
         u16 ns = 0xFFFF;
         if (fl & 8) {
-            int d = c.drv[i];
+            int d = c.dn[i] & 0xFFFF;
             int rank = i - c.off[d];
             int nl = c.leave[d];
             if (!(fl & 1)) {
@@ -560,16 +631,16 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         c.vid2[dst] = c.vid[i];
         if (fl & 1) {
             int dd = __ldg(S.route_seq + q);
-            c.drv2[dst] = (u16) dd;
+            c.dn2[dst] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
             c.ellt2[dst] = dd >= L ? tick : INT_MAX;
             c.pj2[dst] = (fl & 4) ? 1 : 0;
         } else {
-            c.drv2[dst] = c.drv[i]; c.ellt2[dst] = c.ellt[i]; c.pj2[dst] = c.pj[i];
+            c.dn2[dst] = c.dn[i]; c.ellt2[dst] = c.ellt[i]; c.pj2[dst] = c.pj[i];
         }
     }
     { int *t = c.vid; c.vid = c.vid2; c.vid2 = t; }
     { int *t = c.ellt; c.ellt = c.ellt2; c.ellt2 = t; }
-    { u16 *t = c.drv; c.drv = c.drv2; c.drv2 = t; }
+    { u32 *t = c.dn; c.dn = c.dn2; c.dn2 = t; }
     { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
     for (int d = tid; d < D; d += NT) { c.cnt[d] = c.ent[d]; c.off[d] = noff[d]; }
     if (tid == 0) { c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1; }
@@ -914,40 +985,65 @@ __global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layo
     c.cnt = (u16 *) (smem + Y.o_cnt); c.wq = (u16 *) (smem + Y.o_wq);
     c.sraw = smem + Y.o_sraw; c.scur = smem + Y.o_scur; c.schg = smem + Y.o_schg; c.stop = (int *) (smem + Y.o_stop);
     c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd);
-    c.rpos = (int *) (smem + Y.o_rpos); c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt);
-    c.blk = (short *) (smem + Y.o_blk); c.drv = (u16 *) (smem + Y.o_drv); c.pj = smem + Y.o_pj;
+    c.rpos = (int *) (smem + Y.o_rpos); c.blk = (short *) (smem + Y.o_blk);
+    c.newslot = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
     c.npos = (double *) (smem + Y.o_npos); c.nspd = (double *) (smem + Y.o_nspd); c.nrpos = (int *) (smem + Y.o_nrpos);
-    c.vid2 = (int *) (smem + Y.o_vid2); c.drv2 = (u16 *) (smem + Y.o_drv2); c.ellt2 = (int *) (smem + Y.o_ellt2); c.pj2 = smem + Y.o_pj2;
-    c.nblk = (short *) (smem + Y.o_nblk); c.newslot = (u16 *) (smem + Y.o_newslot); c.nflag = smem + Y.o_nflag;
+    c.nblk = (short *) (smem + Y.o_nblk); c.nflag = smem + Y.o_nflag; c.xlist = (u16 *) (smem + Y.o_xlist);
     c.off = (u16 *) (smem + Y.o_off); c.leave = (u16 *) (smem + Y.o_leave); c.ent = (u16 *) (smem + Y.o_ent);
     c.fresh = smem + Y.o_fresh; c.entlist = (u16 *) (smem + Y.o_entlist); c.entpos = (double *) (smem + Y.o_entpos);
     c.entdrv = (u16 *) (smem + Y.o_entdrv); c.scan = (int *) (smem + Y.o_scan);
+    c.avail = (u32 *) (smem + Y.o_avail);
+    if (S.T <= SMEM_TEMPLATES) {
+        double *ts = (double *) (smem + Y.o_tmpl);
+        for (int k = tid; k < S.T * TSC_T_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
+        c.tmpl = ts;
+    } else c.tmpl = S.tmpl;
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
         // the identity fields ping-pong between two buffers every tick: start from the primary ones
-        c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt); c.drv = (u16 *) (smem + Y.o_drv); c.pj = smem + Y.o_pj;
-        c.vid2 = (int *) (smem + Y.o_vid2); c.ellt2 = (int *) (smem + Y.o_ellt2); c.drv2 = (u16 *) (smem + Y.o_drv2); c.pj2 = smem + Y.o_pj2;
+        c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt); c.dn = (u32 *) (smem + Y.o_dn); c.pj = smem + Y.o_pj;
+        c.vid2 = (int *) (smem + Y.o_vid2); c.ellt2 = (int *) (smem + Y.o_ellt2); c.dn2 = (u32 *) (smem + Y.o_dn2); c.pj2 = smem + Y.o_pj2;
         // ---- stage the replica image into shared memory ----
         copy16(smem, img, Y.o_meta_end, tid, NT);
         __syncthreads();
+        const int n_in = c.h->n_slots;
         {
-            const int n = c.h->n_slots;
-            const int n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
+            const int n8 = (n_in * 8 + 15) & ~15, n4 = (n_in * 4 + 15) & ~15, n2 = (n_in * 2 + 15) & ~15, n1 = (n_in + 15) & ~15;
             copy16(smem + Y.o_pos, img + Y.o_pos, n8, tid, NT);
             copy16(smem + Y.o_spd, img + Y.o_spd, n8, tid, NT);
             copy16(smem + Y.o_rpos, img + Y.o_rpos, n4, tid, NT);
             copy16(smem + Y.o_vid, img + Y.o_vid, n4, tid, NT);
             copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
             copy16(smem + Y.o_blk, img + Y.o_blk, n2, tid, NT);
-            copy16(smem + Y.o_drv, img + Y.o_drv, n2, tid, NT);
             copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
         }
         for (int l = tid; l < S.L; l += NT) c.fresh[l] = 0;
         __syncthreads();
+        // drivable | next drivable: the route table is read once per vehicle per launch, not once per tick
+        {
+            const u16 *drv16 = (const u16 *) (img + Y.o_drv);
+            for (int i = tid; i < n_in; i += NT) {
+                u32 nd = 0xFFFFu;
+                if (c.vid[i] >= 0) nd = (u32) (__ldg(S.route_seq + c.rpos[i] + 1) & 0xFFFF);
+                c.dn[i] = (u32) drv16[i] | (nd << 16);
+            }
+        }
         block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
 
         apply_controller<NT>(S, c, a, b);
+        __syncthreads();
+        // lane-link availability under the signals' current light phases: fixed for the whole launch
+        for (int w = tid; w < (S.K + 31) / 32; w += NT) {
+            u32 bits = 0;
+            for (int k = 0; k < 32 && w * 32 + k < S.K; ++k) {
+                int sb = __ldg(&S.llinfo[w * 32 + k].sigbit);
+                int sg = sb & 0xFFFF;
+                u32 m = __ldg(S.sig_phase_mask + sg * S.max_raw + c.sraw[sg]);
+                bits |= ((m >> (sb >> 16)) & 1u) << k;
+            }
+            c.avail[w] = bits;
+        }
         __syncthreads();
         for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT>(S, Y, c, is_spawn_lane);
         if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
@@ -964,8 +1060,13 @@ __global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layo
                 copy16(img + Y.o_vid, c.vid, n4, tid, NT);
                 copy16(img + Y.o_ellt, c.ellt, n4, tid, NT);
                 copy16(img + Y.o_blk, smem + Y.o_blk, n2, tid, NT);
-                copy16(img + Y.o_drv, c.drv, n2, tid, NT);
                 copy16(img + Y.o_pj, c.pj, n1, tid, NT);
+                u32 *drv_pairs = (u32 *) (img + Y.o_drv);     // two u16 drivables per 32-bit store
+                for (int i = tid; i < (n + 1) / 2; i += NT) {
+                    u32 lo = c.dn[2 * i] & 0xFFFFu;
+                    u32 hi = 2 * i + 1 < n ? (c.dn[2 * i + 1] & 0xFFFFu) : 0u;
+                    drv_pairs[i] = lo | (hi << 16);
+                }
             }
         }
         __syncthreads();
@@ -1046,21 +1147,22 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.o_vid = o; o = align16(o + 4 * Vcap);
     Y.o_ellt = o; o = align16(o + 4 * Vcap);
     Y.o_blk = o; o = align16(o + 2 * Vcap);
-    Y.o_drv = o; o = align16(o + 2 * Vcap);
+    Y.o_drv = o; o = align16(o + 2 * Vcap);     // HBM: u16 drivable; shared memory: the newslot scratch
     Y.o_pj = o; o = align16(o + Vcap);
     Y.img_bytes = o;
-    // scratch; npos/nspd/nrpos double as retrieve scratch: make sure they are large enough
+    // shared-memory-only part; npos/nspd/nrpos double as retrieve scratch: make sure they are large enough
     int need_np = 2 * S.L, need_ns = 2 * S.A + 160;
     int need_nr = (S.n_in_total * S.visibility * 8 + 3) / 4;
+    Y.o_dn = o; o = align16(o + 4 * Vcap);
+    Y.o_dn2 = o; o = align16(o + 4 * Vcap);
     Y.o_vid2 = o; o = align16(o + 4 * Vcap);
     Y.o_ellt2 = o; o = align16(o + 4 * Vcap);
-    Y.o_drv2 = o; o = align16(o + 2 * Vcap);
     Y.o_pj2 = o; o = align16(o + Vcap);
     Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
     Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
     Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
     Y.o_nblk = o; o = align16(o + 2 * Vcap);
-    Y.o_newslot = o; o = align16(o + 2 * Vcap);
+    Y.o_xlist = o; o = align16(o + 2 * Vcap);
     Y.o_nflag = o; o = align16(o + Vcap);
     Y.o_off = o; o = align16(o + 2 * (S.D + 2));
     Y.o_leave = o; o = align16(o + 2 * (S.D + 2));
@@ -1071,6 +1173,8 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.o_entpos = o; o = align16(o + 8 * Y.ent_cap);
     Y.o_scan = o; o = align16(o + 4 * 64 + 2 * (S.D + 2));
     Y.o_lane_q = o; o = align16(o + 4 * S.L);
+    Y.o_avail = o; o = align16(o + 4 * ((S.K + 31) / 32 + 1));
+    Y.o_tmpl = o; o = align16(o + 8 * TSC_T_STRIDE * SMEM_TEMPLATES);
     Y.smem_bytes = o;
 }
 
@@ -1115,6 +1219,31 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     S.visibility = s->visibility; S.yellow_time = s->yellow_time; S.obs_dim = s->obs_dim; S.state_dim = s->state_dim;
     S.n_actions = s->n_actions; S.reference_exact = s->reference_exact; S.max_lanes_per_signal = s->max_lanes_per_signal;
     S.max_obs_phases = s->max_obs_phases; S.v_size = s->veh_size_min_gap; S.flick = s->flickering_coef; S.interval = s->interval;
+    // packed lane-link / cross tables
+    {
+        std::vector<LLInfo> li(K > 0 ? K : 1);
+        for (int k = 0; k < K; ++k) {
+            li[k].start_lane = s->ll_start_lane[k]; li[k].end_lane = s->ll_end_lane[k];
+            li[k].cross_off = s->ll_cross_off[k]; li[k].cross_end = s->ll_cross_off[k + 1];
+            li[k].length = s->drv_length[L + k]; li[k].type = s->ll_type[k];
+            if (s->ll_signal[k] < 0 || s->ll_signal[k] >= A || s->ll_roadlink[k] < 0 || s->ll_roadlink[k] >= 32) {
+                tsc_destroy(E); return fail(TSC_EINVAL, "lane-link %d: bad signal / road-link index", k);
+            }
+            li[k].sigbit = s->ll_signal[k] | (s->ll_roadlink[k] << 16);
+        }
+        int nx = s->n_cross_entries;
+        std::vector<CrossEntry> ce(nx > 0 ? nx : 1);
+        for (int x = 0; x < nx; ++x) {
+            int f = s->xr_foe_ll[x];
+            if (f < 0 || f >= K) { tsc_destroy(E); return fail(TSC_EINVAL, "cross %d: bad lane-link index", x); }
+            ce[x].dist = s->xr_dist[x]; ce[x].foe_dist = s->xr_foe_dist[x];
+            ce[x].foe_len = s->drv_length[L + f]; ce[x].foe_sl_len = s->drv_length[s->ll_start_lane[f]];
+            ce[x].foe_ll = f; ce[x].foe_start_lane = s->ll_start_lane[f]; ce[x].foe_end_lane = s->ll_end_lane[f];
+            ce[x].foe_type = s->ll_type[f];
+        }
+        if ((rc = upload(E, li.data(), li.size(), &S.llinfo))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, ce.data(), ce.size(), &S.cross))) { tsc_destroy(E); return rc; }
+    }
     // spawn lanes and creation prefix tables
     E->h_is_spawn.assign(L, 0);
     for (int l = 0; l < L; ++l) if (s->lane_spawn_off[l + 1] > s->lane_spawn_off[l]) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
