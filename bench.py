@@ -366,7 +366,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=72)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
-    ap.add_argument("--vehicle-capacity", type=int, default=1024)
+    ap.add_argument("--vehicle-capacity", type=int, default=640,
+                    help="running vehicles per replica the shared-memory image is sized for (peak on this workload: 561)")
     ap.add_argument("--cpu-steps", type=int, default=360, help="env-steps per process of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

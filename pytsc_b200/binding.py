@@ -21,7 +21,8 @@ ERRORS = {-1: "TSC_EINVAL", -2: "TSC_ECUDA", -3: "TSC_ENOMEM", -4: "TSC_EOVERFLO
 # every symbol include/tsc_b200.h declares
 SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "tsc_get_dims", "tsc_reset",
            "tsc_set_phase", "tsc_init_program", "tsc_step", "tsc_retrieve", "tsc_env_step", "tsc_env_step_host",
-           "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info")
+           "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
+           "tsc_debug_timing")
 
 
 class tsc_outputs_t(C.Structure):
@@ -67,6 +68,7 @@ def load_library(path=None):
     L.tsc_launch_count.argtypes = [vp]
     L.tsc_launch_count.restype = C.c_int64
     L.tsc_kernel_info.argtypes = [vp, pi32, pi32, pi32, pi32]
+    L.tsc_debug_timing.argtypes = [vp, i32, vp, i32]
     for n in SYMBOLS:
         getattr(L, n)
     if path == LIB_PATH:
@@ -223,6 +225,18 @@ class Engine:
         out = {k: np.empty(self.B, np.int32) for k in ("tick", "n_running", "n_finished", "n_slots")}
         self._check(self.lib.tsc_counters(self.h, *[_np_ptr(out[k]) for k in ("tick", "n_running", "n_finished", "n_slots")]))
         return out
+
+    PHASES = ("stage_in", "prologue", "spawn", "phase1", "phase2", "count_scan", "newslot", "scatter", "retrieve", "stage_out",
+              "max_leader", "max_follow", "max_inter", "max_finish", "sum_leader", "sum_follow", "sum_inter", "sum_finish",
+              "sum_n", "n_x")
+
+    def debug_timing(self, enable=True):
+        """Read the per-phase cycle counters accumulated so far (dict), then enable / disable them."""
+        buf = np.zeros(32, np.uint64)
+        n = self.lib.tsc_debug_timing(self.h, int(enable), _np_ptr(buf), 32)
+        if n < 0:
+            self._check(n)
+        return dict(zip(self.PHASES, (int(x) for x in buf[:n])))
 
     def launch_count(self):
         return int(self.lib.tsc_launch_count(self.h))

@@ -102,7 +102,7 @@ struct Layout {
     int o_pos, o_spd, o_rpos, o_vid, o_ellt, o_blk, o_drv, o_pj, img_bytes;
     // shared-memory-only scratch
     int o_vid2, o_ellt2, o_pj2;
-    int o_dn, o_dn2, o_xlist, o_avail, o_tmpl;
+    int o_dn, o_dn2, o_xlist, o_avail, o_tmpl, o_spawn;
     int o_npos, o_nspd, o_nrpos, o_nblk, o_nflag, o_off, o_leave, o_ent, o_fresh, o_entlist,
         o_entpos, o_entdrv, o_scan, o_lane_q, smem_bytes;
 };
@@ -117,6 +117,7 @@ struct StepArgs {
     int init_program;      // >=0: TSProgram.set_initial_phase(index)
     const int *actions;    // [B][A]
     const int *raw_phase;  // [B][A]
+    unsigned long long *phase_cycles;   // debug: per-phase clock64 sums (thread 0 of every block), or NULL
     tsc_outputs_t out;
 };
 
@@ -143,10 +144,20 @@ struct Ctx {
     const double *tmpl;   // vehicle templates (shared-memory copy when they fit)
     u8 *sraw, *scur, *schg, *pj, *pj2, *nflag, *fresh;
     int *stop, *rpos, *vid, *vid2, *ellt, *ellt2, *nrpos, *scan;
+    int *sp_lane, *sp_vid, *sp_tick;   // head of every spawn lane's waiting buffer
     short *blk, *nblk;
     double *pos, *spd, *npos, *nspd, *entpos;
     int tick;
+    unsigned long long *pt;   // debug phase timing (NULL = off)
+    long long pt_last;
 };
+
+// phase ids of the debug timing
+enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1, PT_PHASE2, PT_COUNT_SCAN, PT_NEWSLOT, PT_SCATTER, PT_RETRIEVE, PT_STAGE_OUT,
+       PT_MAX_LEADER, PT_MAX_FOLLOW, PT_MAX_INTER, PT_MAX_FINISH, PT_SUM_LEADER, PT_SUM_FOLLOW, PT_SUM_INTER, PT_SUM_FINISH, PT_SUM_N, PT_NX, PT_N };
+__device__ __forceinline__ void pt_mark(Ctx &c, int k) {
+    if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
+}
 
 __device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, int vid) {
     return c.tmpl + (S.T == 1 ? 0 : TSC_T_STRIDE * __ldg(S.veh_tmpl + vid));
@@ -377,41 +388,46 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     const int L = S.L, D = S.D;
     const int n_slots = c.h->n_slots;
 
-    // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer ----
+    // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer.  The head of every
+    //      buffer (lane, vehicle, creation tick) is cached in shared memory, so a tick without an
+    //      arrival costs one compare per spawn lane. ----
     for (int s = tid; s < S.n_spawn_lanes; s += NT) {
-        int l = __ldg(S.spawn_lane + s);
-        int hd = c.wq[s];
-        int base = __ldg(S.lane_spawn_off + l);
+        const int l = c.sp_lane[s];
         u8 fr = 0;
-        if (base + hd < __ldg(S.lane_spawn_off + l + 1)) {
-            int v = __ldg(S.lane_spawn_vid + base + hd);
-            if (__ldg(S.veh_tick + v) <= tick) {
-                int n = c.cnt[l];
-                bool ok = true;
-                if (n > 0) {
-                    int t = c.off[l] + n - 1;
-                    ok = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of(S, c, v)[TSC_T_MIN_GAP];
-                }
-                if (ok) {
-                    int slot = c.off[l] + n;
-                    int rp0 = __ldg(S.veh_seq_start + v);
-                    c.pos[slot] = 0.0; c.spd[slot] = 0.0;
-                    c.rpos[slot] = rp0;
-                    c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
-                    c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
-                    c.pj[slot] = 0;
-                    c.cnt[l] = (u16) (n + 1);
-                    c.wq[s] = (u16) (hd + 1);
-                    fr = 1;
-                    atomicAdd(&c.h->n_running, 1);
-                }
+        if (c.sp_tick[s] <= tick) {
+            const int v = c.sp_vid[s];
+            int n = c.cnt[l];
+            bool ok = true;
+            if (n > 0) {
+                int t = c.off[l] + n - 1;
+                ok = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of(S, c, v)[TSC_T_MIN_GAP];
+            }
+            if (ok) {
+                int slot = c.off[l] + n;
+                int rp0 = __ldg(S.veh_seq_start + v);
+                c.pos[slot] = 0.0; c.spd[slot] = 0.0;
+                c.rpos[slot] = rp0;
+                c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
+                c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
+                c.pj[slot] = 0;
+                c.cnt[l] = (u16) (n + 1);
+                const int hd = c.wq[s] + 1;
+                c.wq[s] = (u16) hd;
+                const int at = __ldg(S.lane_spawn_off + l) + hd;
+                if (at < __ldg(S.lane_spawn_off + l + 1)) {
+                    const int nv = __ldg(S.lane_spawn_vid + at);
+                    c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
+                } else c.sp_tick[s] = INT_MAX;
+                fr = 1;
+                atomicAdd(&c.h->n_running, 1);
             }
         }
         c.fresh[l] = fr;
     }
     for (int d = tid; d < D; d += NT) { c.leave[d] = 0; c.ent[d] = 0; }
-    if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; }
+    if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; if (c.pt) { for (int k = 0; k < 9; ++k) c.scan[k] = 0; } }
     __syncthreads();
+    pt_mark(c, PT_SPAWN);
 
     // ---- getAction, phase 1: leader / gap, car following, red light; every vehicle, uniform cost.
     //      Vehicles that must examine the crosses of a lane-link are deferred to phase 2. ----
@@ -425,6 +441,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         const int rp = c.rpos[i];
         const double x = c.pos[i], v = c.spd[i];
         const double dlen = __ldg(S.drv_length + d);
+        long long tq0 = c.pt ? clock64() : 0;
         // leader and gap as of the end of the previous tick (A.7): vehicles that
         // entered from the waiting buffer this tick are not yet visible to others
         int leader = -1;
@@ -463,6 +480,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 if (dist > horizon) break;
             }
         }
+        long long tq1 = c.pt ? clock64() : 0;
         // next speed (A.4)
         double ns = T[TSC_T_MAX_SPEED];
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
@@ -470,6 +488,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         double cf = T[TSC_T_MAX_SPEED];
         if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC], dt);
         ns = min2(ns, cf);
+        long long tq2 = c.pt ? clock64() : 0;
         // intersection related speed (A.5)
         const bool on_ll = d >= L;
         if (on_ll || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {
@@ -501,9 +520,24 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             }
             ns = min2(ns, vi);
         }
+        long long tq3 = c.pt ? clock64() : 0;
         finish_vehicle(S, Y, c, i, T, d, rp, x, v, dlen, ns, -1, dt);
+        if (c.pt) {
+            long long tq4 = clock64();
+            int *mx = c.scan;   // free during phase 1
+            atomicMax(mx + 0, (int) (tq1 - tq0)); atomicMax(mx + 1, (int) (tq2 - tq1));
+            atomicMax(mx + 2, (int) (tq3 - tq2)); atomicMax(mx + 3, (int) (tq4 - tq3));
+            atomicAdd(mx + 4, (int) (tq1 - tq0)); atomicAdd(mx + 5, (int) (tq2 - tq1));
+            atomicAdd(mx + 6, (int) (tq3 - tq2)); atomicAdd(mx + 7, (int) (tq4 - tq3));
+            atomicAdd(mx + 8, 1);
+        }
     }
     __syncthreads();
+    if (c.pt && tid == 0) {
+        for (int k = 0; k < 9; ++k) { atomicAdd(c.pt + PT_MAX_LEADER + k, (unsigned long long) c.scan[k]); c.scan[k] = 0; }
+        atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x);
+    }
+    pt_mark(c, PT_PHASE1);
 
     // ---- getAction, phase 2: one warp per deferred vehicle, one lane per cross.  canPass has no
     //      side effects, so evaluating every cross ahead at once and taking the first refusal in
@@ -553,6 +587,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         }
     }
     __syncthreads();
+    pt_mark(c, PT_PHASE2);
 
     // ---- updateLocation: new per-drivable counts, then a stable re-pack ----
     // leave[] = number of leavers, new count = cnt - leave + ent (kept in ent[])
@@ -566,6 +601,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         if (noff[D] > Y.Vcap) c.h->err |= ERR_OVERFLOW;
     }
     const bool overflow = noff[D] > Y.Vcap;
+    pt_mark(c, PT_COUNT_SCAN);
     // destination slot of every vehicle
     for (int i = tid; i < n_slots; i += NT) {
         u8 fl = c.nflag[i];
@@ -598,6 +634,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         c.newslot[i] = ns;
     }
     __syncthreads();
+    pt_mark(c, PT_NEWSLOT);
     if (overflow) {   // keep the old state; the sticky flag reports it
         if (tid == 0) c.h->tick = tick + 1;
         __syncthreads();
@@ -645,6 +682,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     for (int d = tid; d < D; d += NT) { c.cnt[d] = c.ent[d]; c.off[d] = noff[d]; }
     if (tid == 0) { c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1; }
     __syncthreads();
+    pt_mark(c, PT_SCATTER);
 }
 
 // ----------------------------------------------------------------------------
@@ -736,7 +774,6 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     int *l_q = (int *) (smem + Y.o_lane_q);   // [L]
     double *s_loc = c.nspd;              // [A] local reward term
     double *s_prs = c.nspd + A;          // [A] pressure
-    double *s_red = c.nspd + 2 * A;      // [4*32] reduction scratch
 
     // --- Retriever._compute_lane_measurements (retriever.py:54-85) ---
     for (int l = tid; l < L; l += NT) {
@@ -803,7 +840,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         __syncthreads();
     }
 
-    // --- TrafficSignal.update_stats (traffic_signal.py:101-141), obs, state, mask ---
+    // --- TrafficSignal.update_stats (traffic_signal.py:101-141), local reward term, mask ---
     for (int s = tid; s < A; s += NT) {
         int i0 = __ldg(S.sig_in_off + s), i1 = __ldg(S.sig_in_off + s + 1);
         int o0 = __ldg(S.sig_out_off + s), o1 = __ldg(S.sig_out_off + s + 1);
@@ -833,32 +870,13 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         s_loc[s] = -S.flick * chg - metric - 1e-6;
         s_prs[s] = pressure;
 
-        // observation / state vectors
-        const int per = 12, ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
-        const bool ex = S.reference_exact != 0;
-        if (O.state || (O.obs && S.obs_type == TSC_OBS_LANE_FEATURES)) {
-            bool tr = ex && nin * per < ML * per;   // pad_list only converts when it pads
-            for (int rep = 0; rep < 2; ++rep) {
-                float *dst = rep == 0 ? ((O.obs && S.obs_type == TSC_OBS_LANE_FEATURES) ? O.obs + ((size_t) b * A + s) * S.obs_dim : nullptr)
-                                      : (O.state ? O.state + ((size_t) b * A + s) * S.state_dim : nullptr);
-                if (!dst) continue;
-                int k = 0;
-                for (int e = i0; e < i1 && e - i0 < ML; ++e) {
-                    int l = __ldg(S.sig_in_lane + e);
-                    for (int f = 0; f < 9; ++f) dst[k++] = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
-                    dst[k++] = (float) l_q[l];
-                    dst[k++] = ref_trunc(l_occ[l], tr);
-                    dst[k++] = ref_trunc(l_ms[l], tr);
-                }
-                for (; k < ML * per; ++k) dst[k] = -1.0f;
-                for (int p = 0; p < MP; ++p) dst[k++] = p < P ? (p == cur ? 1.0f : 0.0f) : 0.0f;
-            }
-        }
         if (O.obs && S.obs_type == TSC_OBS_POSITION_MATRIX) {
+            // variable-length rows (observations.py:72-88 drops entries <= 0): one thread per signal
+            const int ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
+            const bool ex = S.reference_exact != 0;
             float *dst = O.obs + ((size_t) b * A + s) * S.obs_dim;
             const int body = ML * (vis + 9);
-            // count entries first: pad_list truncates only if it pads
-            int total = 0;
+            int total = 0;   // pad_list truncates only if it pads
             for (int e = i0; e < i1; ++e) {
                 total += 9;
                 for (int k = 0; k < vis; ++k) total += win_in[e * vis + k] > 0;
@@ -911,11 +929,12 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         }
     }
 
-    // --- network metrics (metrics.py) and the global reward: warp 0 ---
-    if (tid < 32) {
+    // --- network metrics (metrics.py) and the global reward: the last warp (the first ones own the signals) ---
+    if (tid >= NT - 32) {
+        const int ln = tid & 31;
         int qsum = 0, vsum = 0;
         double wspeed = 0, occs = 0, nms = 0;
-        for (int l = tid; l < L; l += 32) {
+        for (int l = ln; l < L; l += 32) {
             int n = c.cnt[l];
             qsum += l_q[l]; vsum += n;
             wspeed += l_ms[l] * n;
@@ -923,7 +942,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             nms += l_ms[l] / __ldg(S.drv_max_speed + l);
         }
         int chg = 0;
-        for (int s = tid; s < A; s += 32) chg += c.schg[s];
+        for (int s = ln; s < A; s += 32) chg += c.schg[s];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
@@ -933,7 +952,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             occs += __shfl_xor_sync(0xffffffffu, occs, o);
             nms += __shfl_xor_sync(0xffffffffu, nms, o);
         }
-        if (tid == 0) {
+        if (ln == 0) {
             double flicker = (double) chg / (double) A;
             double psum = A <= 128 ? np_sum(s_prs, A) : 0.0;
             if (A > 128) for (int s = 0; s < A; ++s) psum += s_prs[s];
@@ -961,8 +980,40 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             }
         }
     }
-    __syncthreads();
-    (void) s_red;
+
+    // --- lane-feature observation / state rows (observations.py:305-329, 352-374): one element per
+    //     thread, rows are contiguous so the stores coalesce ---
+    {
+        const int per = 12, ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
+        const int row = ML * per + MP;                 // == obs_dim (lane features) == state_dim
+        const bool ex = S.reference_exact != 0;
+        float *obs = (O.obs && S.obs_type == TSC_OBS_LANE_FEATURES) ? O.obs + (size_t) b * A * row : nullptr;
+        float *state = O.state ? O.state + (size_t) b * A * row : nullptr;
+        if (obs || state) {
+            for (int idx = tid; idx < A * row; idx += NT) {
+                const int s = idx / row, k = idx - s * row;
+                const int i0 = __ldg(S.sig_in_off + s), nin = __ldg(S.sig_in_off + s + 1) - i0;
+                float val;
+                if (k < ML * per) {
+                    const int e = k / per, f = k - e * per;
+                    if (e < nin) {
+                        const bool tr = ex && nin < ML;      // pad_list only converts when it pads
+                        const int l = __ldg(S.sig_in_lane + i0 + e);
+                        if (f < 9) val = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
+                        else if (f == 9) val = (float) l_q[l];
+                        else val = ref_trunc(f == 10 ? l_occ[l] : l_ms[l], tr);
+                    } else val = -1.0f;
+                } else {
+                    const int ph = k - ML * per;
+                    val = (ph < __ldg(S.sig_n_phases + s) && ph == c.scur[s]) ? 1.0f : 0.0f;
+                }
+                if (obs) obs[idx] = val;
+                if (state) state[idx] = val;
+            }
+        }
+    }
+    // no trailing barrier: nothing below writes what the slower warps still read (the caller
+    // synchronises before the next replica is staged in)
 }
 
 // ----------------------------------------------------------------------------
@@ -975,8 +1026,8 @@ __device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, in
     for (int i = tid; i < bytes / 16; i += nt) d[i] = s[i];
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
                                                       const u8 *is_spawn_lane, const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -993,11 +1044,15 @@ __global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layo
     c.fresh = smem + Y.o_fresh; c.entlist = (u16 *) (smem + Y.o_entlist); c.entpos = (double *) (smem + Y.o_entpos);
     c.entdrv = (u16 *) (smem + Y.o_entdrv); c.scan = (int *) (smem + Y.o_scan);
     c.avail = (u32 *) (smem + Y.o_avail);
+    c.sp_lane = (int *) (smem + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
+    for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
     if (S.T <= SMEM_TEMPLATES) {
         double *ts = (double *) (smem + Y.o_tmpl);
         for (int k = tid; k < S.T * TSC_T_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
     } else c.tmpl = S.tmpl;
+    c.pt = a.phase_cycles;
+    c.pt_last = clock64();
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
@@ -1019,6 +1074,14 @@ __global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layo
             copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
         }
         for (int l = tid; l < S.L; l += NT) c.fresh[l] = 0;
+        for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+            const int l = __ldg(S.spawn_lane + s);
+            const int at = __ldg(S.lane_spawn_off + l) + c.wq[s];
+            if (at < __ldg(S.lane_spawn_off + l + 1)) {
+                const int nv = __ldg(S.lane_spawn_vid + at);
+                c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
+            } else { c.sp_vid[s] = -1; c.sp_tick[s] = INT_MAX; }
+        }
         __syncthreads();
         // drivable | next drivable: the route table is read once per vehicle per launch, not once per tick
         {
@@ -1030,23 +1093,27 @@ __global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layo
             }
         }
         block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
+        pt_mark(c, PT_STAGE_IN);
 
         apply_controller<NT>(S, c, a, b);
         __syncthreads();
         // lane-link availability under the signals' current light phases: fixed for the whole launch
-        for (int w = tid; w < (S.K + 31) / 32; w += NT) {
-            u32 bits = 0;
-            for (int k = 0; k < 32 && w * 32 + k < S.K; ++k) {
-                int sb = __ldg(&S.llinfo[w * 32 + k].sigbit);
+        for (int k0 = 0; k0 < S.K; k0 += NT) {      // uniform trip count: every lane takes part in the ballot
+            const int k = k0 + tid;
+            bool on = false;
+            if (k < S.K) {
+                int sb = __ldg(&S.llinfo[k].sigbit);
                 int sg = sb & 0xFFFF;
-                u32 m = __ldg(S.sig_phase_mask + sg * S.max_raw + c.sraw[sg]);
-                bits |= ((m >> (sb >> 16)) & 1u) << k;
+                on = (__ldg(S.sig_phase_mask + sg * S.max_raw + c.sraw[sg]) >> (sb >> 16)) & 1u;
             }
-            c.avail[w] = bits;
+            const u32 bits = __ballot_sync(0xffffffffu, on);
+            if ((tid & 31) == 0 && k < S.K) c.avail[k >> 5] = bits;
         }
         __syncthreads();
+        pt_mark(c, PT_PROLOGUE);
         for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT>(S, Y, c, is_spawn_lane);
         if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
+        pt_mark(c, PT_RETRIEVE);
 
         // ---- write the image back ----
         if (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0) {
@@ -1070,6 +1137,7 @@ __global__ void __launch_bounds__(NT) tsc_step_kernel(const DevScn S, const Layo
             }
         }
         __syncthreads();
+        pt_mark(c, PT_STAGE_OUT);
     }
 }
 
@@ -1092,7 +1160,13 @@ static int fail(int code, const char *fmt, ...) {
         if (e__ != cudaSuccess) return fail(TSC_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
     } while (0)
 
-static constexpr int NT = 256;
+// Threads per replica block: 256 by default, TSC_B200_THREADS=512 selects the wide variant.
+typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
+static step_kernel_t kernel_for(int nt, int minb) {
+    if (nt == 512) return tsc_step_kernel<512, 1>;
+    if (nt == 128) return minb >= 6 ? tsc_step_kernel<128, 6> : tsc_step_kernel<128, 4>;
+    return minb >= 4 ? tsc_step_kernel<256, 4> : (minb == 3 ? tsc_step_kernel<256, 3> : tsc_step_kernel<256, 2>);
+}
 
 struct tsc_engine {
     int device = 0, B = 0;
@@ -1107,8 +1181,9 @@ struct tsc_engine {
     int32_t *h_actions = nullptr;      // pinned staging for the *_host path
     float *h_obs = nullptr, *h_reward = nullptr, *h_rg = nullptr;
     u8 *h_mask = nullptr;
-    int grid = 0, regs = 0;
+    int grid = 0, regs = 0, nt = 256, minb = 2;
     int64_t launches = 0;
+    unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
     std::vector<unsigned char> init_image;   // host copy of the tick-0 image
     // host copies needed by snapshot/load
     std::vector<int> h_route_seq, h_veh_seq_start;
@@ -1132,7 +1207,7 @@ static int align16(int x) { return (x + 15) & ~15; }
 
 static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.Vcap = Vcap;
-    Y.ent_cap = Vcap < 512 ? Vcap : 512;
+    Y.ent_cap = Vcap / 2 < 64 ? 64 : (Vcap / 2 > 2048 ? 2048 : Vcap / 2);   // vehicles changing drivable in one tick
     int o = sizeof(RepHeader);
     Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
     Y.o_wq = o; o = align16(o + 2 * (S.n_spawn_lanes + 1));
@@ -1152,7 +1227,7 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.img_bytes = o;
     // shared-memory-only part; npos/nspd/nrpos double as retrieve scratch: make sure they are large enough
     int need_np = 2 * S.L, need_ns = 2 * S.A + 160;
-    int need_nr = (S.n_in_total * S.visibility * 8 + 3) / 4;
+    int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
     Y.o_dn = o; o = align16(o + 4 * Vcap);
     Y.o_dn2 = o; o = align16(o + 4 * Vcap);
     Y.o_vid2 = o; o = align16(o + 4 * Vcap);
@@ -1175,6 +1250,7 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.o_lane_q = o; o = align16(o + 4 * S.L);
     Y.o_avail = o; o = align16(o + 4 * ((S.K + 31) / 32 + 1));
     Y.o_tmpl = o; o = align16(o + 8 * TSC_T_STRIDE * SMEM_TEMPLATES);
+    Y.o_spawn = o; o = align16(o + 12 * (S.n_spawn_lanes + 1));
     Y.smem_bytes = o;
 }
 
@@ -1275,14 +1351,20 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         return fail(TSC_ENOMEM, "replica working set %d B exceeds %zu B of shared memory per block; lower vehicle_capacity",
                     need, (size_t) prop.sharedMemPerBlockOptin);
     }
-    CUDA_TRY(cudaFuncSetAttribute(tsc_step_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, E->Y.smem_bytes));
+    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 128 || v == 256 || v == 512) E->nt = v; }
+    // blocks per SM the shared-memory footprint allows decides the register budget (launch bounds variant)
+    E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
+    if (E->minb < 1) E->minb = 1;
+    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 8) E->minb = v; }
+    step_kernel_t kern = kernel_for(E->nt, E->minb);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E->Y.smem_bytes));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsc_step_kernel<NT>, NT, E->Y.smem_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E->nt, E->Y.smem_bytes));
     if (per_sm < 1) per_sm = 1;
     E->grid = prop.multiProcessorCount * per_sm;
     if (E->grid > n_replicas) E->grid = n_replicas;
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, tsc_step_kernel<NT>));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
     E->regs = fa.numRegs;
 
     CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) n_replicas * E->Y.img_bytes));
@@ -1318,6 +1400,7 @@ void tsc_destroy(tsc_handle E) {
     if (!E) return;
     cudaSetDevice(E->device);
     for (void *p : E->dev_allocs) cudaFree(p);
+    cudaFree(E->d_phase_cycles);
     cudaFree(E->images); cudaFree(E->d_actions); cudaFree(E->d_obs); cudaFree(E->d_reward); cudaFree(E->d_rg); cudaFree(E->d_mask);
     cudaFreeHost(E->h_actions); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_reward); cudaFreeHost(E->h_rg); cudaFreeHost(E->h_mask);
     delete E;
@@ -1356,7 +1439,7 @@ int tsc_reset(tsc_handle E, void *stream) {
 
 static int launch(tsc_handle E, const StepArgs &a, void *stream) {
     CUDA_TRY(cudaSetDevice(E->device));
-    tsc_step_kernel<NT><<<E->grid, NT, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    kernel_for(E->nt, E->minb)<<<E->grid, E->nt, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
     E->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1366,6 +1449,7 @@ static StepArgs blank_args(tsc_handle E) {
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.B = E->B; a.init_program = -1;
+    a.phase_cycles = E->d_phase_cycles;
     return a;
 }
 
@@ -1556,10 +1640,27 @@ int tsc_counters(tsc_handle E, int32_t *tick, int32_t *n_running, int32_t *n_fin
 
 int64_t tsc_launch_count(tsc_handle E) { return E ? E->launches : 0; }
 
+int tsc_debug_timing(tsc_handle E, int32_t enable, uint64_t *cycles_out, int32_t n) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (cycles_out && E->d_phase_cycles) {
+        unsigned long long tmp[PT_N];
+        CUDA_TRY(cudaMemcpy(tmp, E->d_phase_cycles, sizeof tmp, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n; ++k) cycles_out[k] = k < PT_N ? tmp[k] : 0;
+    } else if (cycles_out) {
+        for (int k = 0; k < n; ++k) cycles_out[k] = 0;
+    }
+    if (enable && !E->d_phase_cycles) CUDA_TRY(cudaMalloc((void **) &E->d_phase_cycles, PT_N * sizeof(unsigned long long)));
+    if (enable) CUDA_TRY(cudaMemset(E->d_phase_cycles, 0, PT_N * sizeof(unsigned long long)));
+    if (!enable && E->d_phase_cycles) { cudaFree(E->d_phase_cycles); E->d_phase_cycles = nullptr; }
+    return PT_N;
+}
+
 int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t *grid, int32_t *regs) {
     if (!E) return fail(TSC_EINVAL, "null handle");
     if (smem_bytes) *smem_bytes = E->Y.smem_bytes;
-    if (threads) *threads = NT;
+    if (threads) *threads = E->nt;
     if (grid) *grid = E->grid;
     if (regs) *regs = E->regs;
     return 0;

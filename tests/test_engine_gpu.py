@@ -38,7 +38,7 @@ def test_lockstep_with_oracle(cuda_lib, name, ticks, kw, mode):
     cfg, parser, cs = build_scenario(name, **kw)
     orc = oracle_engine(cfg)
     B = 3
-    eng = Engine(cs, B, 0, vehicle_capacity=2048)
+    eng = Engine(cs, B, 0, vehicle_capacity=1280)
     inter = signal_inter_indices(parser)
     A = eng.A
     rng = np.random.RandomState(1)
@@ -72,7 +72,7 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     import torch
     from pytsc_b200.binding import Engine
     cfg, parser, cs = build_scenario("hangzhou_4_4")
-    e1, e5 = Engine(cs, 2, 0, 2048), Engine(cs, 2, 0, 2048)
+    e1, e5 = Engine(cs, 2, 0, 1280), Engine(cs, 2, 0, 1280)
     raw = torch.full((2, e1.A), 1, dtype=torch.int32, device="cuda")
     e1.set_phase(raw); e5.set_phase(raw)
     for k in range(60):

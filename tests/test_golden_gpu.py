@@ -32,7 +32,7 @@ def test_env_step_replays_reference(cuda_lib, case):
     g = load_golden(case)
     cfg, parser, cs = golden_scenario(g, reference_exact=True)
     B = 2
-    eng = Engine(cs, B, 0, vehicle_capacity=2048)
+    eng = Engine(cs, B, 0, vehicle_capacity=1280)
     bufs = eng.alloc_outputs()
     eng.init_program(0)
     eng.retrieve(bufs)
@@ -85,7 +85,7 @@ def test_untruncated_observations(cuda_lib, case):
     from pytsc_b200.binding import Engine
     g = load_golden(case)
     cfg, parser, cs = golden_scenario(g, reference_exact=False)
-    eng = Engine(cs, 1, 0, vehicle_capacity=2048)
+    eng = Engine(cs, 1, 0, vehicle_capacity=1280)
     bufs = eng.alloc_outputs(["obs"])
     eng.init_program(0)
     lane_feat = cs.lane_feat.reshape(-1, 9)

@@ -1,8 +1,9 @@
 #!/bin/bash
-# parity tests, then bench at two vehicle capacities (no CPU baseline)
+# parity tests, phase timing, then bench (no CPU baseline) at the given capacities
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
-for cap in 1024 741; do
+for cap in ${CAPS:-1024 600}; do
+  python tools/phase_timing.py $cap
   timeout 300 python bench.py --no-cpu-baseline --vehicle-capacity $cap > gpurun_out/bench_cap$cap.json 2> gpurun_out/bench_cap$cap.err
   python - <<PY
 import json

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""GPU box: per-phase cycle breakdown of tsc_step_kernel on the bench workload.
+usage: python tools/phase_timing.py [vehicle_capacity] [replicas]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from pytsc_b200.backend.config import Config
+from pytsc_b200.backend.network_parser import NetworkParser
+from pytsc_b200.binding import Engine
+from pytsc_b200.scenario import compile_scenario
+
+cap = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+cfg = Config(bench.SCENARIO, **bench.SCENARIO_KW)
+cs = compile_scenario(cfg, NetworkParser(cfg))
+eng = Engine(cs, B, 0, vehicle_capacity=cap)
+bufs = eng.alloc_outputs(["obs", "reward", "reward_global", "mask", "lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed", "sim"])
+eng.init_program(0)
+for _ in range(400):
+    eng.env_step(None, bufs, n_ticks=5, controller=1, controller_arg=25)
+torch.cuda.synchronize()
+eng.debug_timing(True)
+N = 100
+t0 = time.perf_counter()
+for _ in range(N):
+    eng.env_step(None, bufs, n_ticks=5, controller=1, controller_arg=25)
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+cyc = eng.debug_timing(False)
+extra = {k: cyc.pop(k) for k in list(cyc) if k.startswith(("max_", "sum_", "n_x"))}
+tot = sum(cyc.values())
+info = eng.kernel_info()
+print(f"cap {cap} B {B} kernel {info}  {1e3 * wall / N:.3f} ms/step (with timing on)  running {int(bufs['sim'][0,0])}")
+per = B * N
+for k, v in cyc.items():
+    print(f"  {k:11s} {100 * v / tot:5.1f}%  {v / per:9.0f} cycles / replica-step" + (f"  ({v / per / 5:7.0f} / tick)" if k in ("spawn", "phase1", "phase2", "count_scan", "newslot", "scatter") else ""))
+print(f"  total       {tot / per:9.0f} cycles / replica-step")
+ticks = per * 5
+nveh = max(extra["sum_n"], 1)
+print(f"  phase 1 per tick: vehicles {nveh / ticks:.0f}, deferred to phase 2 {extra['n_x'] / ticks:.1f}")
+for k in ("leader", "follow", "inter", "finish"):
+    print(f"    {k:7s} slowest thread {extra['max_' + k] / ticks:7.0f} cycles/tick   mean per vehicle {extra['sum_' + k] / nveh:7.0f}")
+eng.check()
