@@ -259,8 +259,10 @@ class PortEnv:
     def is_terminated(self):
         return self.sim_step == self.config.simulator["sim_length"]
 
-    def step(self, actions):
-        switch = self.config.signal["action_space"] == "phase_switch"
+    def step(self, actions, phase_indices=False):
+        """``phase_indices=True``: ``actions`` are pytsc phase indices whatever the action
+        space (what ``TSController.switch_phase`` receives)."""
+        switch = self.config.signal["action_space"] == "phase_switch" and not phase_indices
         for i, s in enumerate(self.signals.values()):
             if switch:       # common/actions.py:144-158
                 idx = (s.current_phase_index + 1) % s.n_phases if actions[i] == 1 else s.current_phase_index

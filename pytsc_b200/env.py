@@ -23,6 +23,28 @@ from .backend.network_parser import NetworkParser
 from .binding import Engine
 from .scenario import compile_scenario
 
+def shard_replicas(total_replicas: int, world_size: int, rank: int):
+    """Contiguous block of replicas owned by ``rank``: (first, count).  Replicas are
+    independent scenario instances, so this is the whole partitioning scheme."""
+    base, extra = divmod(int(total_replicas), int(world_size))
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def reduce_episode_metrics(vec, group=None):
+    """SUM all-reduce of the episode-metric vector ``[sum ATT, finished, running, sum reward,
+    sum queue, replica-steps, replicas]`` over the process group (NCCL on GPUs, gloo in the CPU
+    tests); a no-op without an initialised group.  Returns the global metrics as a dict."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    v = vec.tolist()
+    n, steps = max(v[6], 1.0), max(v[5], 1.0)
+    return {"average_travel_time": v[0] / n, "finished_vehicles": v[1], "running_vehicles": v[2],
+            "mean_global_reward": v[3] / steps, "mean_n_queued": v[4] / steps, "replicas": int(v[6])}
+
+
 STEP_OUTPUTS = ("obs", "state", "reward", "reward_global", "mask", "sim", "metrics")
 LANE_OUTPUTS = ("lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed")
 
@@ -151,10 +173,4 @@ class BatchedTrafficSignalNetwork:
         vec = torch.stack([s[:, 1].sum(), s[:, 3].sum(), s[:, 0].sum(),
                            self._acc[0], self._acc[1], self._acc[2],
                            torch.tensor(float(self.n_replicas), dtype=torch.float64, device=self.device)])
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
-        v = vec.tolist()
-        n, steps = max(v[6], 1.0), max(v[5], 1.0)
-        return {"average_travel_time": v[0] / n, "finished_vehicles": v[1], "running_vehicles": v[2],
-                "mean_global_reward": v[3] / steps, "mean_n_queued": v[4] / steps, "replicas": int(v[6])}
+        return reduce_episode_metrics(vec, group)

@@ -100,3 +100,103 @@ def golden_scenario(g, **gpu):
     assert cs.lane_ids == [str(x) for x in g["lane_ids"]]
     assert cs.signal_ids == [str(x) for x in g["signal_ids"]]
     return cfg, parser, cs
+
+
+# ---- a CPU stand-in for binding.Engine (host-logic tests only) ---------------------------
+class FakeDeviceEngine:
+    """Test double with the ``binding.Engine`` surface the plugin classes use
+    (``pytsc_b200/backend/simulator.py``), computing its outputs with the CPU
+    oracle.  It lets the host-side plugin logic -- Simulator, Retriever,
+    TrafficSignal, MetricsParser, ``register()`` -- be exercised on a machine
+    without a GPU.  Never used by the product."""
+
+    def __init__(self, scenario, n_replicas, device=0, vehicle_capacity=0, port_kwargs=None, scenario_name=None):
+        import torch
+        from oracle.pytsc_port import PortEnv
+        self.torch = torch
+        self.device = torch.device("cpu")
+        self.scenario = scenario
+        self.port = PortEnv(scenario_name, **(port_kwargs or {}))
+        cs = scenario
+        self.B, self.L, self.A = n_replicas, cs.n_lanes, cs.n_signals
+        self.dims = dict(B=n_replicas, L=cs.n_lanes, A=cs.n_signals, obs_dim=cs.obs_dim, state_dim=cs.state_dim,
+                         n_actions=cs.n_actions, n_in=cs.n_in_total, n_out=cs.n_out_total, vis=cs.visibility)
+        self._launches = 0
+
+    def alloc_outputs(self, names=None):
+        from pytsc_b200.binding import OUTPUT_SPECS
+        t = self.torch
+        return {n: t.zeros(OUTPUT_SPECS[n][0](self.dims), dtype=getattr(t, OUTPUT_SPECS[n][1])) for n in (names or OUTPUT_SPECS)}
+
+    def init_program(self, phase_index=0):
+        pass          # PortEnv starts every signal on phase 0 already
+
+    def reset(self):
+        raise NotImplementedError
+
+    def step(self, n_ticks=1):
+        self.port.engine.next_steps(n_ticks)
+        self._launches += 1
+
+    def retrieve(self, bufs):
+        p = self.port
+        p.retrieve_step_measurements()
+        for s in p.signals.values():
+            p._update_stats(s)
+        self._fill(bufs)
+        self._launches += 1
+
+    def env_step(self, actions, bufs, n_ticks=5, controller=0, controller_arg=0):
+        assert n_ticks == self.port.config.simulator["delta_time"]
+        acts = [int(a) for a in actions[0].tolist()]
+        self.port.step(acts, phase_indices=(controller == 2))
+        self._fill(bufs)
+        self._launches += 1
+
+    def _fill(self, bufs):
+        t, p, cs = self.torch, self.port, self.scenario
+        lm = p.step_measurements["lane"]
+        ids = cs.lane_ids
+        sig = list(p.signals.values())
+        vals = {
+            "lane_count": [lm[l]["n_vehicles"] for l in ids],
+            "lane_queued": [lm[l]["n_queued"] for l in ids],
+            "lane_occupancy": [float(lm[l]["occupancy"]) for l in ids],
+            "lane_mean_speed": [float(lm[l]["mean_speed"]) for l in ids],
+            "lane_meas64": [[float(lm[l]["occupancy"]), float(lm[l]["mean_speed"])] for l in ids],
+            "pos_in": [s.inc_position_matrices[l] for s in sig for l in s.incoming_lanes],
+            "pos_out": [s.out_position_matrices[l] for s in sig for l in s.outgoing_lanes],
+            "sig_stats64": [[s.n_queued, s.occupancy, s.mean_speed, s.mean_delay, s.outgoing_occupancy, s.pressure,
+                             s.norm_time_on_phase, s.current_phase_index] for s in sig],
+        }
+        sm = p.step_measurements["sim"]
+        vals["sim"] = [sm["n_vehicles"], sm["average_travel_time"], sm["time_step"], p.engine.get_finished_vehicle_count()]
+        st = p.step_stats()
+        flick = float(np.mean([bool(s.phase_changed) for s in sig]))
+        vals["metrics"] = [st["n_queued"], st["mean_speed"], st["mean_delay"], st["density"], st["pressure"],
+                           st["network_flow"], flick, float(p.norm_mean_speed)]
+        for k, buf in bufs.items():
+            if k in vals:
+                buf[:] = t.as_tensor(np.asarray(vals[k]), dtype=buf.dtype)
+
+    def check(self):
+        pass
+
+    def close(self):
+        pass
+
+    def launch_count(self):
+        return self._launches
+
+
+def reference_pytsc():
+    """The reference package with the gpu backend registered, or None when it is
+    not importable on this machine (installed, baseline/_ref, or /root/reference)."""
+    try:
+        import logging
+        import pytsc_b200
+        p = pytsc_b200.register()
+        logging.disable(logging.CRITICAL)
+        return p
+    except ImportError:
+        return None

@@ -1,0 +1,98 @@
+"""GPU: the public Python API on the real device engine.
+
+* ``BatchedTrafficSignalNetwork`` (device tensors in / out) replayed against the
+  golden fixtures;
+* the UNMODIFIED reference facade ``pytsc.TrafficSignalNetwork(scenario, "gpu")``
+  on top of the plugin classes, compared with the same fixtures (runs where the
+  reference package is importable -- ``baseline/_ref`` travels to the GPU box --
+  and is skipped otherwise).
+"""
+import numpy as np
+import pytest
+
+from helpers import load_golden, reference_pytsc
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+@pytest.mark.parametrize("case", ["hangzhou_4_4__lf_pressure_select", "syn_1x1__pm_queue_switch",
+                                  "manhattan_16_3__lf_queue_select"])
+def test_batched_env_replays_reference(cuda_lib, case):
+    import torch
+    from pytsc_b200 import BatchedTrafficSignalNetwork
+    g = load_golden(case)
+    kw = {k: dict(v) for k, v in g["kwargs"].items()}
+    B = 5
+    env = BatchedTrafficSignalNetwork(g["scenario"], n_replicas=B, device=0, **kw)
+    assert env.n_agents == len(g["signal_ids"])
+    assert env.get_observation_size() == g["obs"].shape[-1] and env.get_action_size() == g["mask"].shape[-1]
+    obs, mask = env.reset()
+    assert np.array_equal(mask[B - 1].cpu().numpy(), g["mask0"])
+    T = int(g["n_steps"])
+    for t in range(T):
+        act = torch.from_numpy(np.repeat(g["actions"][t][None], B, 0).astype(np.int32)).cuda()
+        r, done, info = env.step(act)
+        assert done == ((t + 1) % env.episode_limit == 0)
+        assert np.array_equal(env.get_observations()[B - 1].cpu().numpy().astype(np.float64), g["obs"][t])
+        assert np.array_equal(env.get_action_mask()[0].cpu().numpy(), g["mask"][t])
+        np.testing.assert_allclose(r.cpu().numpy(), np.full(B, g["reward_global"][t]), rtol=REL_TOL)
+        np.testing.assert_allclose(env.get_rewards()[2].cpu().numpy(), g["reward"][t], rtol=REL_TOL)
+        assert float(info["n_queued"][1]) == g["metrics"][t][0]
+        env.restart()
+    env.check()
+    m = env.all_reduce_episode_metrics()
+    assert m["replicas"] == B
+    assert m["average_travel_time"] == pytest.approx(g["sim"][T - 1][1], rel=1e-12)
+    assert m["finished_vehicles"] == B * g["sim"][T - 1][3]
+    env.close()
+
+
+def test_batched_env_in_kernel_fixed_time(cuda_lib):
+    """controller="fixed_time" (in-kernel FixedTimeController) == feeding the same
+    controller's actions from outside."""
+    import torch
+    from pytsc_b200 import BatchedTrafficSignalNetwork
+    kw = dict(signal=dict(observation_space="lane_features", reward_function="queue_length",
+                          action_space="phase_selection", round_robin=False))
+    a = BatchedTrafficSignalNetwork("hangzhou_4_4", n_replicas=2, **kw)
+    b = BatchedTrafficSignalNetwork("hangzhou_4_4", n_replicas=2, **kw)
+    cur = torch.zeros((2, a.n_agents), dtype=torch.int64, device="cuda")
+    top = torch.zeros_like(cur)
+    for t in range(80):
+        green = (cur % 2 == 0)
+        nxt = torch.where(green & (top < 25), cur, (cur + 1) % 16)
+        top = torch.where(nxt == cur, top + 5, torch.full_like(top, 5))
+        cur = nxt
+        a.step(controller="fixed_time", green_time=25)
+        b.step(cur.to(torch.int32))
+        assert torch.equal(a.get_observations(), b.get_observations()), t
+        assert torch.equal(a.get_rewards(), b.get_rewards()), t
+        assert torch.equal(a.get_action_mask(), b.get_action_mask()), t
+    a.check(); b.check()
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("case", ["hangzhou_4_4__lf_pressure_select", "hangzhou_4_4__pm_queue_select_rr",
+                                  "jinan_3_4__lf_queue_select"])
+def test_reference_facade_on_device(cuda_lib, case):
+    pytsc = reference_pytsc()
+    if pytsc is None:
+        pytest.skip("reference pytsc not importable on this machine")
+    g = load_golden(case)
+    kw = {k: dict(v) for k, v in g["kwargs"].items()}
+    kw["gpu"] = dict(n_replicas=2, view_replica=1, vehicle_capacity=1280)
+    net = pytsc.TrafficSignalNetwork(g["scenario"], "gpu", **kw)
+    assert np.array_equal(np.asarray(net.get_action_mask(), np.uint8), g["mask0"])
+    for t in range(int(g["n_steps"])):
+        r, done, info = net.step([int(a) for a in g["actions"][t]])
+        assert r == pytest.approx(g["reward_global"][t], rel=1e-12)
+        np.testing.assert_allclose(np.asarray(net.get_rewards(), np.float64), g["reward"][t], rtol=1e-12)
+        assert np.array_equal(np.asarray(net.get_action_mask(), np.uint8), g["mask"][t])
+        assert np.array_equal(np.asarray(net.get_observations(), np.float64), g["obs"][t])
+        assert np.array_equal(np.asarray(net.get_state(), np.float64), g["state"][t])
+        assert info["n_queued"] == g["metrics"][t][0]
+        assert info["average_travel_time"] == pytest.approx(g["sim"][t][1], rel=1e-12)
+        if done:
+            net.restart()
+    net.simulator.close_simulator()
