@@ -159,35 +159,46 @@ __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
     if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
 }
 
+// Device-side vehicle template row: the ABI's TSC_T_STRIDE doubles followed by constants derived on
+// the host with the same IEEE operations the CityFlow formulas would repeat for every vehicle.
+enum { TD_A = TSC_T_STRIDE,      // 0.5 / maxNegAcc            ("a" of the no-collision quadratic)
+       TD_HALF_OVER_A,           // 0.5 / a
+       TD_HEADWAY_DEN,           // headwayTime + interval / 2
+       TD_SPARE, TD_STRIDE };
+// The engine runs at CityFlow's interval of 1.0 s only (tsc_create rejects anything else), so
+// x * DT and x / DT are exact identities and fold away.
+#define DT 1.0
+
 __device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, int vid) {
-    return c.tmpl + (S.T == 1 ? 0 : TSC_T_STRIDE * __ldg(S.veh_tmpl + vid));
+    return c.tmpl + (S.T == 1 ? 0 : TD_STRIDE * __ldg(S.veh_tmpl + vid));
 }
 
 // ---- A.4 car following -------------------------------------------------------
-__device__ double no_collision_speed(double vL, double dL, double vF, double dF, double gap, double dt, double target) {
-    double c = vF * dt / 2 + target - 0.5 * vL * vL / dL - gap;
-    double a = 0.5 / dF;
-    double b = 0.5 * dt;
+// a = 0.5 / dF and 0.5 / a come from the follower's template row.
+__device__ __forceinline__ double no_collision_speed(double vL, double dL, double vF, double a, double half_over_a, double gap,
+                                                     double target) {
+    double c = vF * DT / 2 + target - 0.5 * vL * vL / dL - gap;
+    double b = 0.5 * DT;
     if (b * b < 4 * a * c) return -100;
-    double v1 = 0.5 / a * (sqrt(b * b - 4 * a * c) - b);
-    double v2 = 2 * vL - dL * dt + 2 * (gap - target) / dt;
+    double v1 = half_over_a * (sqrt(b * b - 4 * a * c) - b);
+    double v2 = 2 * vL - dL * DT + 2 * (gap - target) / DT;
     return min2(v1, v2);
 }
 
-__device__ double car_follow_speed(const double *T, double v, double gap, double vL, double leaderMaxNegAcc, double dt) {
-    double s = no_collision_speed(vL, leaderMaxNegAcc, v, T[TSC_T_MAX_NEG_ACC], gap, dt, 0);
+__device__ __forceinline__ double car_follow_speed(const double *T, double v, double gap, double vL, double leaderMaxNegAcc) {
+    double s = no_collision_speed(vL, leaderMaxNegAcc, v, T[TD_A], T[TD_HALF_OVER_A], gap, 0);
     double assumeDecel = 0;
     if (v > vL) assumeDecel = v - vL;
-    s = min2(s, no_collision_speed(vL, assumeDecel, v, T[TSC_T_MAX_NEG_ACC], gap, dt, T[TSC_T_MIN_GAP]));
-    s = min2(s, (gap + (vL + assumeDecel / 2) * dt - v * dt / 2) / (T[TSC_T_HEADWAY] + dt / 2));
+    s = min2(s, no_collision_speed(vL, assumeDecel, v, T[TD_A], T[TD_HALF_OVER_A], gap, T[TSC_T_MIN_GAP]));
+    s = min2(s, (gap + (vL + assumeDecel / 2) * DT - v * DT / 2) / T[TD_HEADWAY_DEN]);
     return s;
 }
 
-__device__ double stop_before_speed(const double *T, double v, double distance, double dt) {
-    double nxt = v + T[TSC_T_USUAL_POS_ACC] * dt;
-    double brake = (v + nxt) * dt / 2 + (nxt * nxt / T[TSC_T_USUAL_NEG_ACC] / 2);
-    if (brake < distance) return v + T[TSC_T_USUAL_POS_ACC] * dt;
-    double take = 2 * distance / (v + 1e-8) / dt;
+__device__ double stop_before_speed(const double *T, double v, double distance) {
+    double nxt = v + T[TSC_T_USUAL_POS_ACC] * DT;
+    double brake = (v + nxt) * DT / 2 + (nxt * nxt / T[TSC_T_USUAL_NEG_ACC] / 2);
+    if (brake < distance) return v + T[TSC_T_USUAL_POS_ACC] * DT;
+    double take = 2 * distance / (v + 1e-8) / DT;
     if (take >= 1) return v - v / trunc_int_x86(take);
     return v - v / take;
 }
@@ -197,7 +208,8 @@ __device__ __forceinline__ bool can_yield(const double *T, double v, double dist
     return (dist > 0 && minBrake < dist - T[TSC_T_YIELD_DIST]) || (dist < 0 && dist + T[TSC_T_LEN] < 0);
 }
 
-__device__ int reach_steps(const double *T, double v, double distance, bool turn, double dt) {
+__device__ int reach_steps(const double *T, double v, double distance, bool turn) {
+    const double dt = DT;
     double target = turn ? T[TSC_T_TURN_SPEED] : T[TSC_T_MAX_SPEED];
     double acc = T[TSC_T_USUAL_POS_ACC];
     if (distance <= 0) return -1;
@@ -255,7 +267,7 @@ __device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X
 // Cross::canPass (A.5) for vehicle `me` on / approaching a lane-link of type t1,
 // at the cross `X`.  *foe_out = announced vehicle on the other link.
 __device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T, int t1, const CrossEntry &X, double dts,
-                         double dt, int *foe_out) {
+                         int *foe_out) {
     double d2;
     int foe = cross_claimant(S, c, X, &d2);
     *foe_out = foe;
@@ -272,15 +284,15 @@ __device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T,
         if (t1 > t2) yield = -1;
         else if (t1 < t2) {
             if (d2 > 0) {
-                int fs = reach_steps(TF, vf, d2, t2 != 3, dt);
-                int ms = reach_steps(T, v, d1, t1 != 3, dt);
+                int fs = reach_steps(TF, vf, d2, t2 != 3);
+                int ms = reach_steps(T, v, d1, t1 != 3);
                 if (fs > ms) yield = -1;
             } else if (d2 + TF[TSC_T_LEN] < 0) yield = -1;
             if (yield == 0) yield = 1;
         } else {
             if (d2 > 0) {
-                int fs = reach_steps(TF, vf, d2, t2 != 3, dt);
-                int ms = reach_steps(T, v, d1, t1 != 3, dt);
+                int fs = reach_steps(TF, vf, d2, t2 != 3);
+                int ms = reach_steps(T, v, d1, t1 != 3);
                 if (fs > ms) yield = -1;
                 else if (fs < ms) yield = 1;
                 else {
@@ -345,7 +357,8 @@ __device__ void block_scan_counts(const u16 *in, const u8 *extra_lane, int n_lan
 // Commit one vehicle's decision into the tick's buffers: clamp the speed, advance
 // along the route, and register the move if it leaves its drivable (A.4).
 __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y, Ctx &c, int i, const double *T, int d, int rp,
-                                               double x, double v, double dlen, double ns, int blocker, double dt) {
+                                               double x, double v, double dlen, double ns, int blocker) {
+    const double dt = DT;
     ns = max2(ns, v - T[TSC_T_MAX_NEG_ACC] * dt);
     double delta;
     if (ns < 0) { delta = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC]; ns = 0; }
@@ -384,7 +397,7 @@ template <int NT>
 __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *is_spawn_lane) {
     const int tid = threadIdx.x;
     const int tick = c.h->tick;
-    const double dt = S.interval;
+    const double dt = DT;
     const int L = S.L, D = S.D;
     const int n_slots = c.h->n_slots;
 
@@ -451,7 +464,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             gap = c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN] - x;
         } else {
             double dist = dlen - x;
-            const double horizon = T[TSC_T_MAX_SPEED] * T[TSC_T_MAX_SPEED] / T[TSC_T_USUAL_NEG_ACC] / 2 + T[TSC_T_MAX_SPEED] * dt * 2;
+            const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
             for (int j = 1;; ++j) {
                 int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
                 if (nd < 0) break;
@@ -486,7 +499,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
         ns = min2(ns, __ldg(S.drv_max_speed + d));
         double cf = T[TSC_T_MAX_SPEED];
-        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC], dt);
+        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
         ns = min2(ns, cf);
         long long tq2 = c.pt ? clock64() : 0;
         // intersection related speed (A.5)
@@ -507,7 +520,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                     if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
                         // cannot stop before the line any more
                     } else {
-                        vi = min2(vi, stop_before_speed(T, v, dlen - x, dt));
+                        vi = min2(vi, stop_before_speed(T, v, dlen - x));
                         done = true;
                     }
                 }
@@ -521,7 +534,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             ns = min2(ns, vi);
         }
         long long tq3 = c.pt ? clock64() : 0;
-        finish_vehicle(S, Y, c, i, T, d, rp, x, v, dlen, ns, -1, dt);
+        finish_vehicle(S, Y, c, i, T, d, rp, x, v, dlen, ns, -1);
         if (c.pt) {
             long long tq4 = clock64();
             int *mx = c.scan;   // free during phase 1
@@ -570,20 +583,20 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                     int4 *dst = (int4 *) &X;
                     dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
                     dOn = X.dist;
-                    if (!(dOn < dts)) refuse = !can_pass(S, c, i, T, t1, X, dts, dt, &foe);
+                    if (!(dOn < dts)) refuse = !can_pass(S, c, i, T, t1, X, dts, &foe);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, refuse);
                 if (m) {
                     const int src_lane = __ffs(m) - 1;
                     dOn = __shfl_sync(0xffffffffu, dOn, src_lane);
                     foe = __shfl_sync(0xffffffffu, foe, src_lane);
-                    vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST], dt));
+                    vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST]));
                     blocker = foe;
                     break;
                 }
             }
             ns = min2(ns, vi);
-            if (lane == 0) finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker, dt);
+            if (lane == 0) finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
         }
     }
     __syncthreads();
@@ -1048,7 +1061,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
     if (S.T <= SMEM_TEMPLATES) {
         double *ts = (double *) (smem + Y.o_tmpl);
-        for (int k = tid; k < S.T * TSC_T_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
+        for (int k = tid; k < S.T * TD_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
     } else c.tmpl = S.tmpl;
     c.pt = a.phase_cycles;
@@ -1249,7 +1262,7 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.o_scan = o; o = align16(o + 4 * 64 + 2 * (S.D + 2));
     Y.o_lane_q = o; o = align16(o + 4 * S.L);
     Y.o_avail = o; o = align16(o + 4 * ((S.K + 31) / 32 + 1));
-    Y.o_tmpl = o; o = align16(o + 8 * TSC_T_STRIDE * SMEM_TEMPLATES);
+    Y.o_tmpl = o; o = align16(o + 8 * TD_STRIDE * SMEM_TEMPLATES);
     Y.o_spawn = o; o = align16(o + 12 * (S.n_spawn_lanes + 1));
     Y.smem_bytes = o;
 }
@@ -1285,7 +1298,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     UP(ll_start_lane, K) UP(ll_end_lane, K) UP(ll_signal, K) UP(ll_roadlink, K) UP(ll_type, K) UP(ll_cross_off, K + 1)
     UP(xr_dist, s->n_cross_entries) UP(xr_foe_ll, s->n_cross_entries) UP(xr_foe_dist, s->n_cross_entries)
     UP(sig_phase_mask, A * s->max_raw_phases) UP(route_seq, s->n_route_seq)
-    UP(veh_tick, N) UP(veh_seq_start, N) UP(veh_tmpl, N) UP(veh_priority, N) UP(tmpl, s->n_templates * TSC_T_STRIDE)
+    UP(veh_tick, N) UP(veh_seq_start, N) UP(veh_tmpl, N) UP(veh_priority, N)
     UP(lane_pytsc_length, L) UP(lane_feat, L * 9) UP(sig_in_off, A + 1) UP(sig_in_lane, s->n_in_total)
     UP(sig_out_off, A + 1) UP(sig_out_lane, s->n_out_total) UP(sig_n_phases, A) UP(sig_phase_raw, A * s->max_phases)
     UP(sig_phase_green, A * s->max_phases) UP(sig_min_time, A * s->max_phases) UP(sig_max_time, A * s->max_phases)
@@ -1295,6 +1308,21 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     S.visibility = s->visibility; S.yellow_time = s->yellow_time; S.obs_dim = s->obs_dim; S.state_dim = s->state_dim;
     S.n_actions = s->n_actions; S.reference_exact = s->reference_exact; S.max_lanes_per_signal = s->max_lanes_per_signal;
     S.max_obs_phases = s->max_obs_phases; S.v_size = s->veh_size_min_gap; S.flick = s->flickering_coef; S.interval = s->interval;
+    {   // vehicle templates, extended with the per-template constants of the car-following law
+        std::vector<double> td((size_t) s->n_templates * TD_STRIDE, 0.0);
+        for (int t = 0; t < s->n_templates; ++t) {
+            const double *src = s->tmpl + (size_t) t * TSC_T_STRIDE;
+            double *dst = td.data() + (size_t) t * TD_STRIDE;
+            for (int k = 0; k < TSC_T_STRIDE; ++k) dst[k] = src[k];
+            const double a = 0.5 / src[TSC_T_MAX_NEG_ACC];
+            dst[TD_A] = a;
+            dst[TD_HALF_OVER_A] = 0.5 / a;
+            dst[TD_HEADWAY_DEN] = src[TSC_T_HEADWAY] + s->interval / 2;
+            const double approach = src[TSC_T_MAX_SPEED] * src[TSC_T_MAX_SPEED] / src[TSC_T_USUAL_NEG_ACC] / 2 + src[TSC_T_MAX_SPEED] * s->interval * 2;
+            if (src[TSC_T_APPROACH_DIST] != approach) { tsc_destroy(E); return fail(TSC_EINVAL, "template %d: TSC_T_APPROACH_DIST is not maxSpeed^2/usualNegAcc/2 + 2 maxSpeed interval", t); }
+        }
+        if ((rc = upload(E, td.data(), td.size(), &S.tmpl))) { tsc_destroy(E); return rc; }
+    }
     // packed lane-link / cross tables
     {
         std::vector<LLInfo> li(K > 0 ? K : 1);
