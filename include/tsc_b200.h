@@ -235,8 +235,8 @@ int64_t tsc_launch_count(tsc_handle h);
 
 /* Debug: per-phase clock64() sums seen by thread 0 of every block since timing was (re)enabled.
  * Copies up to n counters into cycles_out (may be NULL), then enables (zeroing) or disables the
- * instrumentation; returns the number of phases (stage-in, prologue, spawn, phase 1, phase 2,
- * count+scan, new slots, scatter, retrieve, stage-out).  Syncs.  Off by default (no overhead). */
+ * instrumentation; returns the number of counters (stage-in, prologue, spawn, getAction 1a / 1b / 1c / 2,
+ * count+scan, new slots, scatter, retrieve, stage-out, then three list-length sums).  Syncs.  Off by default (no overhead). */
 int  tsc_debug_timing(tsc_handle h, int32_t enable, uint64_t *cycles_out, int32_t n);
 
 /* Name, bytes of dynamic shared memory, threads per block and grid of the step kernel. */

@@ -226,9 +226,8 @@ class Engine:
         self._check(self.lib.tsc_counters(self.h, *[_np_ptr(out[k]) for k in ("tick", "n_running", "n_finished", "n_slots")]))
         return out
 
-    PHASES = ("stage_in", "prologue", "spawn", "phase1", "phase2", "count_scan", "newslot", "scatter", "retrieve", "stage_out",
-              "max_leader", "max_follow", "max_inter", "max_finish", "sum_leader", "sum_follow", "sum_inter", "sum_finish",
-              "sum_n", "n_x")
+    PHASES = ("stage_in", "prologue", "spawn", "phase1a", "phase1b", "phase1c", "phase2", "count_scan", "newslot", "scatter",
+              "retrieve", "stage_out", "n_heads", "n_zone", "n_cross")
 
     def debug_timing(self, enable=True):
         """Read the per-phase cycle counters accumulated so far (dict), then enable / disable them."""

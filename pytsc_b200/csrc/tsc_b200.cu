@@ -87,7 +87,8 @@ struct RepHeader {   // 64 bytes, first thing in every replica image
     u32 err;              // sticky error bits
     int n_ent;            // scratch: movers this tick
     int n_x;              // scratch: vehicles deferred to the cross phase this tick
-    int pad[5];
+    int n_h, n_a;         // scratch: head vehicles / vehicles in an intersection zone this tick
+    int pad[3];
 };
 static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 
@@ -153,8 +154,8 @@ struct Ctx {
 };
 
 // phase ids of the debug timing
-enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1, PT_PHASE2, PT_COUNT_SCAN, PT_NEWSLOT, PT_SCATTER, PT_RETRIEVE, PT_STAGE_OUT,
-       PT_MAX_LEADER, PT_MAX_FOLLOW, PT_MAX_INTER, PT_MAX_FINISH, PT_SUM_LEADER, PT_SUM_FOLLOW, PT_SUM_INTER, PT_SUM_FINISH, PT_SUM_N, PT_NX, PT_N };
+enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1A, PT_PHASE1, PT_PHASE1C, PT_PHASE2, PT_COUNT_SCAN, PT_NEWSLOT, PT_SCATTER, PT_RETRIEVE,
+       PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_N };
 __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
     if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
 }
@@ -438,12 +439,68 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         c.fresh[l] = fr;
     }
     for (int d = tid; d < D; d += NT) { c.leave[d] = 0; c.ent[d] = 0; }
-    if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; if (c.pt) { for (int k = 0; k < 9; ++k) c.scan[k] = 0; } }
+    if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; }
     __syncthreads();
     pt_mark(c, PT_SPAWN);
 
-    // ---- getAction, phase 1: leader / gap, car following, red light; every vehicle, uniform cost.
-    //      Vehicles that must examine the crosses of a lane-link are deferred to phase 2. ----
+    // ---- getAction is split so that every sub-phase runs the same code in all its lanes:
+    //      1a  head vehicles (one per non-empty drivable): look-ahead leader + gap
+    //      1b  every vehicle: car following; vehicles in an intersection zone go on a list
+    //      1c  listed vehicles: red light / blocked exit / turn speed; those that must examine
+    //          the crosses of a lane-link go on a second list
+    //      2   one warp per vehicle of the second list, one lane per cross ----
+    u16 *hlist = c.xlist;      // dead before 1c fills xlist
+    u16 *alist = c.newslot;    // dead before the new slots are computed
+    for (int d = tid; d < D; d += NT)
+        if (c.cnt[d] > 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) d;
+    __syncthreads();
+
+    // 1a: leader and gap of head vehicles as of the end of the previous tick (A.7): vehicles that
+    // entered from the waiting buffer this tick are not yet visible to others
+    for (int e = tid, n_h = c.h->n_h; e < n_h; e += NT) {
+        const int d = hlist[e];
+        const int i = c.off[d];
+        const double *T = tmpl_of(S, c, c.vid[i]);
+        const u32 dnv = c.dn[i];
+        const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
+        const int rp = c.rpos[i];
+        int leader = -1;
+        double gap = 0.0;
+        double dist = __ldg(S.drv_length + d) - c.pos[i];
+        const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
+        for (int j = 1;; ++j) {
+            int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
+            if (nd < 0) break;
+            if (nd >= L) {
+                int sl = __ldg(&S.llinfo[nd - L].start_lane);
+                int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
+                for (int q = e0; q < e1; ++q) {
+                    int dl = L + __ldg(S.lane_ll + q);
+                    int n = c.cnt[dl];
+                    if (n > 0) {
+                        int cand = c.off[dl] + n - 1;
+                        double cg = dist + c.pos[cand] - tmpl_of(S, c, c.vid[cand])[TSC_T_LEN];
+                        if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
+                    }
+                }
+                if (leader >= 0) break;
+            } else {
+                int n = c.cnt[nd] - c.fresh[nd];
+                if (n > 0) {
+                    leader = c.off[nd] + n - 1;
+                    gap = dist + c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN];
+                    break;
+                }
+            }
+            dist += __ldg(S.drv_length + nd);
+            if (dist > horizon) break;
+        }
+        c.nblk[i] = (short) leader; c.npos[i] = gap;
+    }
+    __syncthreads();
+    pt_mark(c, PT_PHASE1A);
+
+    // 1b: next speed from acceleration, speed limits and the car-following law (A.4)
     for (int i = tid; i < n_slots; i += NT) {
         int vid = c.vid[i];
         if (vid < 0) { c.nflag[i] = 0; continue; }
@@ -451,106 +508,71 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         const u32 dnv = c.dn[i];
         const int d = dnv & 0xFFFF;
         const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
-        const int rp = c.rpos[i];
         const double x = c.pos[i], v = c.spd[i];
         const double dlen = __ldg(S.drv_length + d);
-        long long tq0 = c.pt ? clock64() : 0;
-        // leader and gap as of the end of the previous tick (A.7): vehicles that
-        // entered from the waiting buffer this tick are not yet visible to others
-        int leader = -1;
-        double gap = 0.0;
+        int leader;
+        double gap;
         if (i > c.off[d]) {
             leader = i - 1;
             gap = c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN] - x;
-        } else {
-            double dist = dlen - x;
-            const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
-            for (int j = 1;; ++j) {
-                int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
-                if (nd < 0) break;
-                if (nd >= L) {
-                    int sl = __ldg(&S.llinfo[nd - L].start_lane);
-                    int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
-                    for (int e = e0; e < e1; ++e) {
-                        int dl = L + __ldg(S.lane_ll + e);
-                        int n = c.cnt[dl];
-                        if (n > 0) {
-                            int cand = c.off[dl] + n - 1;
-                            double cg = dist + c.pos[cand] - tmpl_of(S, c, c.vid[cand])[TSC_T_LEN];
-                            if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
-                        }
-                    }
-                    if (leader >= 0) break;
-                } else {
-                    int n = c.cnt[nd] - c.fresh[nd];
-                    if (n > 0) {
-                        leader = c.off[nd] + n - 1;
-                        gap = dist + c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN];
-                        break;
-                    }
-                }
-                dist += __ldg(S.drv_length + nd);
-                if (dist > horizon) break;
-            }
-        }
-        long long tq1 = c.pt ? clock64() : 0;
-        // next speed (A.4)
+        } else { leader = c.nblk[i]; gap = c.npos[i]; }
         double ns = T[TSC_T_MAX_SPEED];
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
         ns = min2(ns, __ldg(S.drv_max_speed + d));
         double cf = T[TSC_T_MAX_SPEED];
         if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
         ns = min2(ns, cf);
-        long long tq2 = c.pt ? clock64() : 0;
-        // intersection related speed (A.5)
-        const bool on_ll = d >= L;
-        if (on_ll || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {
-            double vi = T[TSC_T_MAX_SPEED];
-            bool done = false;
-            if (!on_ll) {
-                const int ll = nd1 - L;
-                const int el = __ldg(&S.llinfo[ll].end_lane);
-                bool enter = true;
-                int n = c.cnt[el];
-                if (n > 0) {
-                    int t = c.off[el] + n - 1;
-                    enter = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
-                }
-                if (!ll_available(c, ll) || !enter) {
-                    if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
-                        // cannot stop before the line any more
-                    } else {
-                        vi = min2(vi, stop_before_speed(T, v, dlen - x));
-                        done = true;
-                    }
-                }
-                if (!done && __ldg(&S.llinfo[ll].type) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
-            }
-            if (!done) {   // phase 2 walks the crosses with a whole warp
-                c.npos[i] = vi; c.nspd[i] = ns;
-                c.xlist[atomicAdd(&c.h->n_x, 1)] = (u16) i;
-                continue;
-            }
-            ns = min2(ns, vi);
+        if (d >= L || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {   // intersection related speed applies (A.5)
+            c.nspd[i] = ns;
+            alist[atomicAdd(&c.h->n_a, 1)] = (u16) i;
+            continue;
         }
-        long long tq3 = c.pt ? clock64() : 0;
-        finish_vehicle(S, Y, c, i, T, d, rp, x, v, dlen, ns, -1);
-        if (c.pt) {
-            long long tq4 = clock64();
-            int *mx = c.scan;   // free during phase 1
-            atomicMax(mx + 0, (int) (tq1 - tq0)); atomicMax(mx + 1, (int) (tq2 - tq1));
-            atomicMax(mx + 2, (int) (tq3 - tq2)); atomicMax(mx + 3, (int) (tq4 - tq3));
-            atomicAdd(mx + 4, (int) (tq1 - tq0)); atomicAdd(mx + 5, (int) (tq2 - tq1));
-            atomicAdd(mx + 6, (int) (tq3 - tq2)); atomicAdd(mx + 7, (int) (tq4 - tq3));
-            atomicAdd(mx + 8, 1);
-        }
+        finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
     }
     __syncthreads();
-    if (c.pt && tid == 0) {
-        for (int k = 0; k < 9; ++k) { atomicAdd(c.pt + PT_MAX_LEADER + k, (unsigned long long) c.scan[k]); c.scan[k] = 0; }
-        atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x);
-    }
     pt_mark(c, PT_PHASE1);
+
+    // 1c: intersection related speed, part (i)-(ii) of A.5
+    for (int e = tid, n_a = c.h->n_a; e < n_a; e += NT) {
+        const int i = alist[e];
+        const double *T = tmpl_of(S, c, c.vid[i]);
+        const u32 dnv = c.dn[i];
+        const int d = dnv & 0xFFFF;
+        const double x = c.pos[i], v = c.spd[i];
+        const double dlen = __ldg(S.drv_length + d);
+        double ns = c.nspd[i];
+        double vi = T[TSC_T_MAX_SPEED];
+        bool done = false;
+        if (d < L) {
+            const int ll = (int) (dnv >> 16) - L;
+            const int el = __ldg(&S.llinfo[ll].end_lane);
+            bool enter = true;
+            int n = c.cnt[el];
+            if (n > 0) {
+                int t = c.off[el] + n - 1;
+                enter = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
+            }
+            if (!ll_available(c, ll) || !enter) {
+                if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
+                    // cannot stop before the line any more
+                } else {
+                    vi = min2(vi, stop_before_speed(T, v, dlen - x));
+                    done = true;
+                }
+            }
+            if (!done && __ldg(&S.llinfo[ll].type) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
+        }
+        if (!done) {   // phase 2 walks the crosses with a whole warp
+            c.npos[i] = vi;
+            c.xlist[atomicAdd(&c.h->n_x, 1)] = (u16) i;
+            continue;
+        }
+        ns = min2(ns, vi);
+        finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
+    }
+    __syncthreads();
+    if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); atomicAdd(c.pt + PT_NH, (unsigned long long) c.h->n_h); }
+    pt_mark(c, PT_PHASE1C);
 
     // ---- getAction, phase 2: one warp per deferred vehicle, one lane per cross.  canPass has no
     //      side effects, so evaluating every cross ahead at once and taking the first refusal in

@@ -29,17 +29,14 @@ for _ in range(N):
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 cyc = eng.debug_timing(False)
-extra = {k: cyc.pop(k) for k in list(cyc) if k.startswith(("max_", "sum_", "n_x"))}
+extra = {k: cyc.pop(k) for k in list(cyc) if k.startswith("n_")}
 tot = sum(cyc.values())
 info = eng.kernel_info()
 print(f"cap {cap} B {B} kernel {info}  {1e3 * wall / N:.3f} ms/step (with timing on)  running {int(bufs['sim'][0,0])}")
 per = B * N
+TICK = ("spawn", "phase1a", "phase1b", "phase1c", "phase2", "count_scan", "newslot", "scatter")
 for k, v in cyc.items():
-    print(f"  {k:11s} {100 * v / tot:5.1f}%  {v / per:9.0f} cycles / replica-step" + (f"  ({v / per / 5:7.0f} / tick)" if k in ("spawn", "phase1", "phase2", "count_scan", "newslot", "scatter") else ""))
+    print(f"  {k:11s} {100 * v / tot:5.1f}%  {v / per:9.0f} cycles / replica-step" + (f"  ({v / per / 5:7.0f} / tick)" if k in TICK else ""))
 print(f"  total       {tot / per:9.0f} cycles / replica-step")
-ticks = per * 5
-nveh = max(extra["sum_n"], 1)
-print(f"  phase 1 per tick: vehicles {nveh / ticks:.0f}, deferred to phase 2 {extra['n_x'] / ticks:.1f}")
-for k in ("leader", "follow", "inter", "finish"):
-    print(f"    {k:7s} slowest thread {extra['max_' + k] / ticks:7.0f} cycles/tick   mean per vehicle {extra['sum_' + k] / nveh:7.0f}")
+print("  per tick: " + ", ".join(f"{k[2:]} {v / (per * 5):.1f}" for k, v in extra.items()))
 eng.check()
