@@ -207,7 +207,11 @@ int  tsc_env_step(tsc_handle h, const int32_t *actions, int32_t controller, int3
 
 /* Same through HOST buffers: copies `actions_host` in, runs the fused step and
  * copies obs / reward / mask / reward_global back (any may be NULL), then
- * synchronises.  This is the end-to-end path bench.py times as `e2e`. */
+ * synchronises.  The batch is stepped in chunks of whole grid waves (at most 16
+ * chunks, TSC_B200_HOST_CHUNKS) on an internal stream while the observation rows
+ * of finished chunks are copied out on another; page-locked caller buffers are
+ * used in place.  This is the end-to-end path
+ * bench.py times as `e2e`. */
 int  tsc_env_step_host(tsc_handle h, const int32_t *actions_host, int32_t controller, int32_t controller_arg,
                        int32_t n_ticks, float *obs_host, float *reward_host, uint8_t *mask_host,
                        float *reward_global_host);

@@ -109,7 +109,8 @@ struct Layout {
 };
 
 struct StepArgs {
-    int B;
+    int b0;                // first replica of this launch
+    int B;                 // one past the last replica of this launch
     int n_ticks;
     int apply_actions;     // 0 none, 1 external actions, 2 fixed-time controller, 3 external phase indices
     int controller_arg;
@@ -1089,7 +1090,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     c.pt = a.phase_cycles;
     c.pt_last = clock64();
 
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    for (int b = a.b0 + blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
         // the identity fields ping-pong between two buffers every tick: start from the primary ones
         c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt); c.dn = (u32 *) (smem + Y.o_dn); c.pj = smem + Y.o_pj;
@@ -1203,6 +1204,8 @@ static step_kernel_t kernel_for(int nt, int minb) {
     return minb >= 4 ? tsc_step_kernel<256, 4> : (minb == 3 ? tsc_step_kernel<256, 3> : tsc_step_kernel<256, 2>);
 }
 
+#define MAX_HOST_CHUNKS 16
+
 struct tsc_engine {
     int device = 0, B = 0;
     DevScn S{};
@@ -1219,6 +1222,10 @@ struct tsc_engine {
     int grid = 0, regs = 0, nt = 256, minb = 2;
     int64_t launches = 0;
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
+    cudaStream_t host_compute = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
+    cudaEvent_t host_ev[1 + MAX_HOST_CHUNKS] = {};
+    int host_chunks = MAX_HOST_CHUNKS;   // upper bound on chunks per host step (TSC_B200_HOST_CHUNKS)
+    bool host_zero_copy = false;        // TSC_B200_HOST_ZERO_COPY=1: kernel stores straight into mapped page-locked buffers
     std::vector<unsigned char> init_image;   // host copy of the tick-0 image
     // host copies needed by snapshot/load
     std::vector<int> h_route_seq, h_veh_seq_start;
@@ -1439,6 +1446,11 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     CUDA_TRY(cudaMallocHost((void **) &E->h_reward, io * sizeof(float)));
     CUDA_TRY(cudaMallocHost((void **) &E->h_rg, (size_t) n_replicas * sizeof(float)));
     CUDA_TRY(cudaMallocHost((void **) &E->h_mask, io * S.n_actions));
+    CUDA_TRY(cudaStreamCreateWithFlags(&E->host_compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&E->host_copy, cudaStreamNonBlocking));
+    for (auto &ev : E->host_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char *env = getenv("TSC_B200_HOST_CHUNKS")) { int v = atoi(env); if (v >= 1 && v <= MAX_HOST_CHUNKS) E->host_chunks = v; }
+    if (const char *env = getenv("TSC_B200_HOST_ZERO_COPY")) E->host_zero_copy = atoi(env) != 0;
     *out = E;
     int r = tsc_reset(E, nullptr);
     if (r) { tsc_destroy(E); *out = nullptr; return r; }
@@ -1451,6 +1463,9 @@ void tsc_destroy(tsc_handle E) {
     cudaSetDevice(E->device);
     for (void *p : E->dev_allocs) cudaFree(p);
     cudaFree(E->d_phase_cycles);
+    if (E->host_compute) cudaStreamDestroy(E->host_compute);
+    if (E->host_copy) cudaStreamDestroy(E->host_copy);
+    for (auto &ev : E->host_ev) if (ev) cudaEventDestroy(ev);
     cudaFree(E->images); cudaFree(E->d_actions); cudaFree(E->d_obs); cudaFree(E->d_reward); cudaFree(E->d_rg); cudaFree(E->d_mask);
     cudaFreeHost(E->h_actions); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_reward); cudaFreeHost(E->h_rg); cudaFreeHost(E->h_mask);
     delete E;
@@ -1489,7 +1504,9 @@ int tsc_reset(tsc_handle E, void *stream) {
 
 static int launch(tsc_handle E, const StepArgs &a, void *stream) {
     CUDA_TRY(cudaSetDevice(E->device));
-    kernel_for(E->nt, E->minb)<<<E->grid, E->nt, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    int grid = E->grid < a.B - a.b0 ? E->grid : a.B - a.b0;
+    if (grid <= 0) return 0;
+    kernel_for(E->nt, E->minb)<<<grid, E->nt, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
     E->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1498,7 +1515,7 @@ static int launch(tsc_handle E, const StepArgs &a, void *stream) {
 static StepArgs blank_args(tsc_handle E) {
     StepArgs a;
     memset(&a, 0, sizeof a);
-    a.B = E->B; a.init_program = -1;
+    a.b0 = 0; a.B = E->B; a.init_program = -1;
     a.phase_cycles = E->d_phase_cycles;
     return a;
 }
@@ -1552,37 +1569,80 @@ static bool is_pinned(const void *p) {
 
 int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t controller, int32_t controller_arg, int32_t n_ticks,
                       float *obs_host, float *reward_host, uint8_t *mask_host, float *reward_global_host) {
-    if (!E) return fail(TSC_EINVAL, "null handle");
+    if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
+    if (controller < TSC_CTRL_EXTERNAL || controller > TSC_CTRL_PHASE_INDEX) return fail(TSC_EINVAL, "unknown controller %d", controller);
     CUDA_TRY(cudaSetDevice(E->device));
-    cudaStream_t st = 0;   // legacy default stream: ordered after work queued on any blocking stream
-    const size_t io = (size_t) E->B * E->S.A;
+    const size_t A = (size_t) E->S.A, io = (size_t) E->B * A;
+    // Replicas are independent, so the batch is cut into chunks: while chunk k+1 is being stepped on
+    // the compute stream, chunk k's observations / rewards / masks travel to the host on the copy
+    // stream.  Both streams are ordered after whatever the caller queued on the default stream.
+    cudaStream_t sc = E->host_compute, sd = E->host_copy;
+    CUDA_TRY(cudaEventRecord(E->host_ev[0], 0));
+    CUDA_TRY(cudaStreamWaitEvent(sc, E->host_ev[0], 0));
     // page-locked caller buffers are used in place; pageable ones go through the handle's pinned staging
     if (controller != TSC_CTRL_FIXED_TIME) {
         if (!actions_host) return fail(TSC_EINVAL, "actions required unless TSC_CTRL_FIXED_TIME");
         const int32_t *src = actions_host;
         if (!is_pinned(actions_host)) { memcpy(E->h_actions, actions_host, io * sizeof(int)); src = E->h_actions; }
-        CUDA_TRY(cudaMemcpyAsync(E->d_actions, src, io * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(E->d_actions, src, io * sizeof(int), cudaMemcpyHostToDevice, sc));
     }
-    tsc_outputs_t o;
-    memset(&o, 0, sizeof o);
-    if (obs_host) o.obs = E->d_obs;
-    if (reward_host) o.reward = E->d_reward;
-    if (mask_host) o.mask = E->d_mask;
-    if (reward_global_host) o.reward_global = E->d_rg;
-    int rc = tsc_env_step(E, E->d_actions, controller, controller_arg, n_ticks, &o, st);
-    if (rc) return rc;
-    struct Out { void *user, *stage; const void *dev; size_t bytes; bool direct; } outs[4] = {
-        {obs_host, E->h_obs, E->d_obs, io * E->S.obs_dim * sizeof(float), false},
-        {reward_host, E->h_reward, E->d_reward, io * sizeof(float), false},
-        {mask_host, E->h_mask, E->d_mask, io * E->S.n_actions, false},
-        {reward_global_host, E->h_rg, E->d_rg, (size_t) E->B * sizeof(float), false}};
-    for (Out &x : outs) {
-        if (!x.user) continue;
-        x.direct = is_pinned(x.user);
-        CUDA_TRY(cudaMemcpyAsync(x.direct ? x.user : x.stage, x.dev, x.bytes, cudaMemcpyDeviceToHost, st));
+    struct Out { void *user, *stage; const void *dev; size_t row; bool direct; } outs[4] = {
+        {obs_host, E->h_obs, E->d_obs, A * E->S.obs_dim * sizeof(float), false},
+        {reward_host, E->h_reward, E->d_reward, A * sizeof(float), false},
+        {mask_host, E->h_mask, E->d_mask, A * E->S.n_actions, false},
+        {reward_global_host, E->h_rg, E->d_rg, sizeof(float), false}};
+    bool all_pinned = true;
+    for (Out &x : outs) if (x.user) { x.direct = is_pinned(x.user); all_pinned = all_pinned && x.direct; }
+    StepArgs a = blank_args(E);
+    a.apply_actions = controller == TSC_CTRL_FIXED_TIME ? 2 : (controller == TSC_CTRL_PHASE_INDEX ? 3 : 1);
+    a.controller_arg = controller_arg; a.actions = E->d_actions; a.n_ticks = n_ticks;
+    a.do_retrieve = 1;
+    if (obs_host) a.out.obs = E->d_obs;
+    if (reward_host) a.out.reward = E->d_reward;
+    if (mask_host) a.out.mask = E->d_mask;
+    if (reward_global_host) a.out.reward_global = E->d_rg;
+    if (E->host_zero_copy && all_pinned) {
+        // Page-locked buffers are mapped into the device address space (UVA): the kernel's coalesced
+        // row stores go straight over PCIe while other replicas are still being stepped -- one launch,
+        // no separate copy phase.
+        void *dp = nullptr;
+        if (obs_host) { CUDA_TRY(cudaHostGetDevicePointer(&dp, obs_host, 0)); a.out.obs = (float *) dp; }
+        if (reward_host) { CUDA_TRY(cudaHostGetDevicePointer(&dp, reward_host, 0)); a.out.reward = (float *) dp; }
+        if (mask_host) { CUDA_TRY(cudaHostGetDevicePointer(&dp, mask_host, 0)); a.out.mask = (uint8_t *) dp; }
+        if (reward_global_host) { CUDA_TRY(cudaHostGetDevicePointer(&dp, reward_global_host, 0)); a.out.reward_global = (float *) dp; }
+        int rc = launch(E, a, sc);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(sc));
+        return 0;
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    for (Out &x : outs) if (x.user && !x.direct) memcpy(x.user, x.stage, x.bytes);
+    // chunk = a whole number of waves of the persistent grid, so that no launch ends on a partly
+    // filled wave; at most MAX_HOST_CHUNKS chunks
+    const int total_waves = (E->B + E->grid - 1) / E->grid;
+    int wpc = E->host_chunks > 0 ? (total_waves + E->host_chunks - 1) / E->host_chunks : 1;
+    if (wpc < 1) wpc = 1;
+    const int chunk = wpc * E->grid;
+    int k = 0;
+    for (int b0 = 0; b0 < E->B; b0 += chunk, ++k) {
+        a.b0 = b0;
+        a.B = b0 + chunk < E->B ? b0 + chunk : E->B;
+        int rc = launch(E, a, sc);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(E->host_ev[1 + k], sc));
+        CUDA_TRY(cudaStreamWaitEvent(sd, E->host_ev[1 + k], 0));
+        const bool last = a.B == E->B;
+        for (int o = 0; o < 4; ++o) {
+            Out &x = outs[o];
+            if (!x.user) continue;
+            // the observation rows are the bulk: they leave chunk by chunk; the small outputs leave once
+            size_t r0 = o == 0 ? (size_t) a.b0 : 0, nr = o == 0 ? (size_t) (a.B - a.b0) : (size_t) E->B;
+            if (o != 0 && !last) continue;
+            char *dst = (char *) (x.direct ? x.user : x.stage) + r0 * x.row;
+            CUDA_TRY(cudaMemcpyAsync(dst, (const char *) x.dev + r0 * x.row, nr * x.row, cudaMemcpyDeviceToHost, sd));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(sd));
+    CUDA_TRY(cudaStreamSynchronize(sc));
+    for (Out &x : outs) if (x.user && !x.direct) memcpy(x.user, x.stage, (size_t) E->B * x.row);
     return 0;
 }
 

@@ -104,3 +104,36 @@ def test_untruncated_observations(cuda_lib, case):
             ph[int(g["sig_stats"][t][a, 7])] = 1.0
             _close(obs[a], np.asarray(exp + ph), REL_TOL, f"{case} step {t} agent {a}")
     eng.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_path_equals_device_path(cuda_lib, pinned):
+    """tsc_env_step_host (chunked: step chunk k+1 while chunk k is copied out) returns exactly what
+    tsc_env_step writes to device buffers -- pageable and page-locked host buffers, B not a multiple
+    of the chunk count."""
+    import torch
+    from pytsc_b200.binding import Engine
+    g = load_golden("hangzhou_4_4__lf_pressure_select")
+    cfg, parser, cs = golden_scenario(g, reference_exact=True)
+    B = 37
+    dev, host = Engine(cs, B, 0, vehicle_capacity=640), Engine(cs, B, 0, vehicle_capacity=640)
+    bufs = dev.alloc_outputs(["obs", "reward", "mask", "reward_global"])
+    dev.init_program(0); host.init_program(0)
+    mk = (lambda *s, dt: torch.empty(*s, dtype=dt, pin_memory=True).numpy()) if pinned else (lambda *s, dt: torch.empty(*s, dtype=dt).numpy())
+    h_obs = mk(B, dev.A, dev.dims["obs_dim"], dt=torch.float32)
+    h_rew = mk(B, dev.A, dt=torch.float32)
+    h_mask = mk(B, dev.A, dev.dims["n_actions"], dt=torch.uint8)
+    h_rg = mk(B, dt=torch.float32)
+    h_act = mk(B, dev.A, dt=torch.int32)
+    for t in range(40):
+        h_act[:] = g["actions"][t][None]
+        dev.env_step(torch.from_numpy(h_act.copy()).cuda(), bufs, n_ticks=5)
+        host.env_step_host(h_act, obs=h_obs, reward=h_rew, mask=h_mask, reward_global=h_rg, n_ticks=5)
+        torch.cuda.synchronize()
+        assert np.array_equal(bufs["obs"].cpu().numpy(), h_obs), t
+        assert np.array_equal(bufs["reward"].cpu().numpy(), h_rew), t
+        assert np.array_equal(bufs["mask"].cpu().numpy(), h_mask), t
+        assert np.array_equal(bufs["reward_global"].cpu().numpy(), h_rg), t
+        assert np.array_equal(h_obs[B - 1].astype(np.float64), g["obs"][t])
+    dev.check(); host.check()
+    dev.close(); host.close()
