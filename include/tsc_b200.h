@@ -17,6 +17,9 @@
  *   engine.get_average_travel_time()           retriever.py:110   |
  *   engine.get_current_time()                  simulator.py:50, retriever.py:111           /
  *   TrafficSignalNetwork.step(actions)         pytsc/__init__.py:178-182  (fused fast path) -> tsc_env_step
+ *   {FixedTime,Greedy,MaxPressure,SOTL,Random}Controller.get_action
+ *                                              pytsc/controllers/controllers.py:39-268      -> tsc_env_step(controller=...),
+ *                                                                                              tsc_controller_act
  *
  * Conventions
  *   - plain C: pointers and sizes only, no C++/torch types; `stream` is a
@@ -41,7 +44,7 @@
 extern "C" {
 #endif
 
-#define TSC_ABI_VERSION 1
+#define TSC_ABI_VERSION 2
 
 enum {
     TSC_OK = 0,
@@ -65,7 +68,16 @@ enum { TSC_ACT_PHASE_SELECTION = 0, TSC_ACT_PHASE_SWITCH = 1 };
 /* who picks the next phase in tsc_env_step: the caller's actions interpreted by the scenario's action
  * space; the in-kernel fixed-time controller; or the caller's actions taken as pytsc phase indices
  * (TSController.switch_phase, backends/cityflow/traffic_signal.py:51-59) whatever the action space. */
-enum { TSC_CTRL_EXTERNAL = 0, TSC_CTRL_FIXED_TIME = 1, TSC_CTRL_PHASE_INDEX = 2 };
+enum { TSC_CTRL_EXTERNAL = 0, TSC_CTRL_FIXED_TIME = 1, TSC_CTRL_PHASE_INDEX = 2,
+       /* pytsc's rule-based controllers evaluated on the device from the position-matrix windows of the
+        * current state (controllers/controllers.py): they return pytsc phase indices, applied like
+        * TSC_CTRL_PHASE_INDEX.  controller_arg: GREEDY / MAX_PRESSURE / RANDOM = seed of the counter-based
+        * generator that breaks ties (the reference draws np.random.choice among tied actions);
+        * SOTL = TSC_SOTL_ARG(theta, mu, phi_min) (reference defaults 3, 4, 5). */
+       TSC_CTRL_GREEDY = 3, TSC_CTRL_MAX_PRESSURE = 4, TSC_CTRL_SOTL = 5, TSC_CTRL_RANDOM = 6 };
+#define TSC_SOTL_ARG(theta, mu, phi_min) (((theta) & 0xFF) | (((mu) & 0xFF) << 8) | (((phi_min) & 0xFFFF) << 16))
+/* score written by tsc_controller_act for an action the mask forbids (the reference's float("-inf")) */
+#define TSC_SCORE_MASKED INT32_MIN
 
 /* A compiled scenario: flat, read-only tables built on the host by
  * pytsc_b200.scenario.compile_scenario().  All pointers are HOST pointers,
@@ -86,6 +98,7 @@ typedef struct tsc_scenario {
     int32_t max_raw_phases;       /* row stride of sig_phase_mask */
     int32_t max_phases;           /* P: row stride of the pytsc phase tables */
     int32_t n_in_total, n_out_total, n_nbr_total;
+    int32_t n_ctl_total;          /* length of ctl_in_lane / ctl_out_lane */
 
     /* --- engine tables (CityFlow semantics) --- */
     const double  *drv_length;        /* [D] */
@@ -127,6 +140,11 @@ typedef struct tsc_scenario {
     const int32_t *nbr_off;           /* [A+1] CSR: reward neighbours in the reference's summation order */
     const int32_t *nbr_idx;
     const double  *nbr_weight;        /* gamma**k */
+    /* rule-based controllers: phase_to_inc_out_lanes (backends/cityflow/network_parser.py:212-257) of
+     * pytsc phase p of signal s = entries ctl_off[s*P+p] .. ctl_off[s*P+p+1] */
+    const int32_t *ctl_off;           /* [A*P+1] */
+    const int32_t *ctl_in_lane;       /* incoming lane of the entry */
+    const int32_t *ctl_out_lane;      /* LAST outgoing lane listed for it (what controllers.py:165-169 ends up using), -1 = none */
 
     /* --- options --- */
     int32_t reward_type, obs_type, action_space, round_robin;
@@ -204,6 +222,15 @@ int  tsc_retrieve(tsc_handle h, const tsc_outputs_t *out, void *stream);
  * (controllers/controllers.py:26-54). */
 int  tsc_env_step(tsc_handle h, const int32_t *actions, int32_t controller, int32_t controller_arg,
                   int32_t n_ticks, const tsc_outputs_t *out, void *stream);
+
+/* What pytsc's rule-based controller `controller` (TSC_CTRL_FIXED_TIME, _GREEDY, _MAX_PRESSURE, _SOTL,
+ * _RANDOM) would choose from the current state, without applying it: actions_out device int32 [B][A]
+ * pytsc phase indices; scores_out (may be NULL) device int32 [B][A][P]: per phase index the queue
+ * (GREEDY, controllers.py:95-114) or pressure (MAX_PRESSURE, :151-176) the reference computes for it,
+ * TSC_SCORE_MASKED where the mask forbids it or the signal is on yellow; SOTL: [0] = flow on the current
+ * phase, [1] = flow on the next green phase (:222-238), rest 0. */
+int  tsc_controller_act(tsc_handle h, int32_t controller, int32_t controller_arg, int32_t *actions_out,
+                        int32_t *scores_out, void *stream);
 
 /* Same through HOST buffers: copies `actions_host` in, runs the fused step and
  * copies obs / reward / mask / reward_global back (any may be NULL), then

@@ -22,7 +22,16 @@ ERRORS = {-1: "TSC_EINVAL", -2: "TSC_ECUDA", -3: "TSC_ENOMEM", -4: "TSC_EOVERFLO
 SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "tsc_get_dims", "tsc_reset",
            "tsc_set_phase", "tsc_init_program", "tsc_step", "tsc_retrieve", "tsc_env_step", "tsc_env_step_host",
            "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
-           "tsc_debug_timing")
+           "tsc_debug_timing", "tsc_controller_act")
+
+# tsc_env_step / tsc_controller_act controller codes (include/tsc_b200.h)
+CONTROLLERS = {"external": 0, "fixed_time": 1, "phase_index": 2, "greedy": 3, "max_pressure": 4, "sotl": 5, "random": 6}
+SCORE_MASKED = -2 ** 31
+
+
+def sotl_arg(theta=3, mu=4, phi_min=5):
+    """TSC_SOTL_ARG: the SOTLController parameters (controllers/controllers.py:190-197) in one int32."""
+    return (theta & 0xFF) | ((mu & 0xFF) << 8) | ((phi_min & 0xFFFF) << 16)
 
 
 class tsc_outputs_t(C.Structure):
@@ -69,6 +78,7 @@ def load_library(path=None):
     L.tsc_launch_count.restype = C.c_int64
     L.tsc_kernel_info.argtypes = [vp, pi32, pi32, pi32, pi32]
     L.tsc_debug_timing.argtypes = [vp, i32, vp, i32]
+    L.tsc_controller_act.argtypes = [vp, i32, i32, vp, vp, vp]
     for n in SYMBOLS:
         getattr(L, n)
     if path == LIB_PATH:
@@ -185,6 +195,16 @@ class Engine:
         o = self._outputs(bufs)
         self._check(self.lib.tsc_env_step(self.h, _ptr(actions), controller, controller_arg, n_ticks,
                                           C.byref(o) if bufs is not None else None, self._stream()))
+
+    def controller_act(self, controller, controller_arg=0, scores=False):
+        """What pytsc's rule-based ``controller`` would do now: int32 [B, A] phase indices (and the
+        [B, A, P] scores behind them), without touching the programs."""
+        torch = self.torch
+        acts = torch.empty((self.B, self.A), dtype=torch.int32, device=self.device)
+        sc = torch.empty((self.B, self.A, self.scenario.max_phases), dtype=torch.int32, device=self.device) if scores else None
+        self._check(self.lib.tsc_controller_act(self.h, CONTROLLERS.get(controller, controller), controller_arg,
+                                                _ptr(acts), _ptr(sc), self._stream()))
+        return (acts, sc) if scores else acts
 
     def env_step_host(self, actions, obs=None, reward=None, mask=None, reward_global=None, n_ticks=5,
                       controller=0, controller_arg=0):

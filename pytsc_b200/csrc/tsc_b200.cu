@@ -72,6 +72,7 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     const u8 *sig_phase_green;
     const int *nbr_off, *nbr_idx;
     const double *nbr_weight;
+    const int *ctl_off, *ctl_in_lane, *ctl_out_lane;   // rule-based controllers: lanes served by every pytsc phase
     int reward_type, obs_type, action_space, round_robin, visibility, yellow_time;
     int obs_dim, state_dim, n_actions, reference_exact, max_lanes_per_signal, max_obs_phases;
     double v_size, flick, interval;
@@ -98,6 +99,7 @@ static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 
 struct Layout {
     int Vcap, ent_cap;
+    int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
     // persistent part: identical byte offsets in the HBM image and in shared memory
     int o_cnt, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
     int o_pos, o_spd, o_rpos, o_vid, o_ellt, o_blk, o_drv, o_pj, img_bytes;
@@ -112,8 +114,12 @@ struct StepArgs {
     int b0;                // first replica of this launch
     int B;                 // one past the last replica of this launch
     int n_ticks;
-    int apply_actions;     // 0 none, 1 external actions, 2 fixed-time controller, 3 external phase indices
+    int apply_actions;     // 0 none, 1 external actions, 2 fixed-time controller, 3 external phase indices,
+                           // 4 greedy, 5 max pressure, 6 SOTL, 7 random (rule-based controllers on the device)
     int controller_arg;
+    int decide_only;       // 1: report what the controller would choose, leave the programs alone
+    int *ctl_actions;      // [B][A] out: the controller's phase indices, or NULL
+    int *ctl_scores;       // [B][A][P] out: per-phase scores behind the decision, or NULL
     int do_retrieve;
     int set_raw_phase;     // 1: raw_phase input given
     int init_program;      // >=0: TSProgram.set_initial_phase(index)
@@ -136,7 +142,8 @@ __device__ __forceinline__ int trunc_int_x86(double x) {
     return (int) x;
 }
 
-#define SMEM_TEMPLATES 4   // vehicle templates cached in shared memory (more: read from global)
+#define SMEM_TEMPLATES 4
+#define SCATTER_PER 4    // vehicles per thread the register-staged re-pack can hold   // vehicle templates cached in shared memory (more: read from global)
 
 struct Ctx {
     RepHeader *h;
@@ -395,13 +402,19 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
 // ----------------------------------------------------------------------------
 // One engine tick for the replica held in shared memory (A.2)
 // ----------------------------------------------------------------------------
-template <int NT>
+template <int NT, bool STAGED>
 __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *is_spawn_lane) {
     const int tid = threadIdx.x;
     const int tick = c.h->tick;
     const double dt = DT;
     const int L = S.L, D = S.D;
     const int n_slots = c.h->n_slots;
+    if (c.h->err) {   // a replica that overflowed or lost its order is frozen: its result is reported invalid by tsc_check
+        __syncthreads();
+        if (tid == 0) c.h->tick = tick + 1;
+        __syncthreads();
+        return;
+    }
 
     // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer.  The head of every
     //      buffer (lane, vehicle, creation tick) is cached in shared memory, so a tick without an
@@ -671,7 +684,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     }
     __syncthreads();
     pt_mark(c, PT_NEWSLOT);
-    if (overflow) {   // keep the old state; the sticky flag reports it
+    if (overflow || c.h->err) {   // keep the old state; the sticky flag reports it
+        __syncthreads();
         if (tid == 0) c.h->tick = tick + 1;
         __syncthreads();
         return;
@@ -686,35 +700,78 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             atomicSub(&c.h->n_running, 1);
         }
     }
-    // scatter: kinematics come from the n* arrays; the identity fields ping-pong
-    // between two buffers, so nothing is read after it may have been overwritten
-    for (int s = tid; s < S.n_spawn_lanes; s += NT) {
-        int l = __ldg(S.spawn_lane + s);
-        c.vid2[noff[l] + c.ent[l]] = -1;      // the lane's spare slot stays empty
-    }
-    for (int i = tid; i < n_slots; i += NT) {
-        u16 dst = c.newslot[i];
-        if (dst == 0xFFFF) continue;
-        u8 fl = c.nflag[i];
-        int q = c.nrpos[i];
-        c.pos[dst] = c.npos[i]; c.spd[dst] = c.nspd[i]; c.rpos[dst] = q;
-        int bk = c.nblk[i];
-        if (bk >= 0) { u16 nb = c.newslot[bk]; bk = (nb == 0xFFFF) ? -1 : (int) nb; }
-        c.blk[dst] = (short) bk;
-        c.vid2[dst] = c.vid[i];
-        if (fl & 1) {
-            int dd = __ldg(S.route_seq + q);
-            c.dn2[dst] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
-            c.ellt2[dst] = dd >= L ? tick : INT_MAX;
-            c.pj2[dst] = (fl & 4) ? 1 : 0;
-        } else {
-            c.dn2[dst] = c.dn[i]; c.ellt2[dst] = c.ellt[i]; c.pj2[dst] = c.pj[i];
+    // scatter: kinematics come from the n* arrays into the (distinct) persistent columns.  The
+    // identity columns are permuted in place: every thread first pulls its vehicles' identities into
+    // registers, a barrier retires all reads, then they are stored at the new slots.  Replicas too
+    // large for that (Vcap > SCATTER_PER * NT) ping-pong between two copies instead, and so do
+    // replicas small enough to afford the second copy: it is the faster of the two (1.330 vs 1.343 ms).
+    if (STAGED) {
+        int r_vid[SCATTER_PER], r_ellt[SCATTER_PER];
+        u32 r_dn[SCATTER_PER];
+        u16 r_dst[SCATTER_PER];
+        u8 r_pj[SCATTER_PER];
+#pragma unroll
+        for (int k = 0; k < SCATTER_PER; ++k) {
+            const int i = tid + k * NT;
+            r_dst[k] = 0xFFFF;
+            if (i >= n_slots) continue;
+            const u16 dst = c.newslot[i];
+            if (dst == 0xFFFF) continue;
+            r_dst[k] = dst;
+            const u8 fl = c.nflag[i];
+            const int q = c.nrpos[i];
+            c.pos[dst] = c.npos[i]; c.spd[dst] = c.nspd[i]; c.rpos[dst] = q;
+            int bk = c.nblk[i];
+            if (bk >= 0) { u16 nb = c.newslot[bk]; bk = (nb == 0xFFFF) ? -1 : (int) nb; }
+            c.blk[dst] = (short) bk;
+            r_vid[k] = c.vid[i];
+            if (fl & 1) {
+                int dd = __ldg(S.route_seq + q);
+                r_dn[k] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
+                r_ellt[k] = dd >= L ? tick : INT_MAX;
+                r_pj[k] = (fl & 4) ? 1 : 0;
+            } else { r_dn[k] = c.dn[i]; r_ellt[k] = c.ellt[i]; r_pj[k] = c.pj[i]; }
         }
+        __syncthreads();
+        for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+            int l = c.sp_lane[s];
+            c.vid[noff[l] + c.ent[l]] = -1;      // the lane's spare slot stays empty
+        }
+#pragma unroll
+        for (int k = 0; k < SCATTER_PER; ++k) {
+            const u16 dst = r_dst[k];
+            if (dst == 0xFFFF) continue;
+            c.vid[dst] = r_vid[k]; c.dn[dst] = r_dn[k]; c.ellt[dst] = r_ellt[k]; c.pj[dst] = r_pj[k];
+        }
+    } else {
+        for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+            int l = c.sp_lane[s];
+            c.vid2[noff[l] + c.ent[l]] = -1;      // the lane's spare slot stays empty
+        }
+        for (int i = tid; i < n_slots; i += NT) {
+            u16 dst = c.newslot[i];
+            if (dst == 0xFFFF) continue;
+            u8 fl = c.nflag[i];
+            int q = c.nrpos[i];
+            c.pos[dst] = c.npos[i]; c.spd[dst] = c.nspd[i]; c.rpos[dst] = q;
+            int bk = c.nblk[i];
+            if (bk >= 0) { u16 nb = c.newslot[bk]; bk = (nb == 0xFFFF) ? -1 : (int) nb; }
+            c.blk[dst] = (short) bk;
+            c.vid2[dst] = c.vid[i];
+            if (fl & 1) {
+                int dd = __ldg(S.route_seq + q);
+                c.dn2[dst] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
+                c.ellt2[dst] = dd >= L ? tick : INT_MAX;
+                c.pj2[dst] = (fl & 4) ? 1 : 0;
+            } else {
+                c.dn2[dst] = c.dn[i]; c.ellt2[dst] = c.ellt[i]; c.pj2[dst] = c.pj[i];
+            }
+        }
+        { int *t = c.vid; c.vid = c.vid2; c.vid2 = t; }
+        { int *t = c.ellt; c.ellt = c.ellt2; c.ellt2 = t; }
+        { u32 *t = c.dn; c.dn = c.dn2; c.dn2 = t; }
+        { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
     }
-    { int *t = c.vid; c.vid = c.vid2; c.vid2 = t; }
-    { int *t = c.ellt; c.ellt = c.ellt2; c.ellt2 = t; }
-    { u32 *t = c.dn; c.dn = c.dn2; c.dn2 = t; }
-    { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
     for (int d = tid; d < D; d += NT) { c.cnt[d] = c.ent[d]; c.off[d] = noff[d]; }
     if (tid == 0) { c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1; }
     __syncthreads();
@@ -767,8 +824,154 @@ __device__ double np_sum(const double *a, int n) {
     return res;
 }
 
+// ---- Retriever._compute_lane_position_matrix (retriever.py:20-52) seen through a window: the last
+//      (incoming side, traffic_signal.py:124) or first (outgoing side, :135) `vis` bins of lane l's
+//      padded list.  w[k] = -1 for an empty bin, else -1 + sum over its vehicles of (1 + speed / max). ----
+__device__ void lane_window(const DevScn &S, const Ctx &c, int l, bool tail, double *w) {
+    const int vis = S.visibility;
+    const double plen = __ldg(S.lane_pytsc_length + l);
+    const double mspeed = __ldg(S.drv_max_speed + l);
+    const int bins = (int) (plen / S.v_size);
+    const int n = c.cnt[l], base = c.off[l];
+    for (int k = 0; k < vis; ++k) w[k] = -1.0;
+    if (bins > 0 && n > 0) {
+        const int len = bins < vis ? vis : bins;     // padded length
+        const int lo = tail ? len - vis : 0;         // window start in the padded list
+        const double bin_size = plen / bins;
+        for (int k = 0; k < n; ++k) {
+            double p = round6(c.pos[base + k]);
+            if (p < 0) p = 0; else if (p > plen) p = plen;
+            int bi = trunc_int_x86(py_floordiv(p, bin_size));
+            if (bi >= bins) bi = bins - 1;
+            const int wi = bi - lo;
+            if (wi >= 0 && wi < vis) {
+                const double nsp = round6(c.spd[base + k]) / mspeed;
+                w[wi] += 1.0;
+                w[wi] += nsp;
+            }
+        }
+    }
+}
+
+// ---- get_allowable_phase_switches (common/traffic_signal.py:329-361 free, 375-404 round robin):
+//      bit p = pytsc phase index p may be selected now ----
+__device__ u32 allowable_phases(const DevScn &S, const Ctx &c, int s) {
+    const int cur = c.scur[s], t = c.stop[s], P = __ldg(S.sig_n_phases + s);
+    u32 allow = 0;
+    if (__ldg(S.sig_phase_green + s * S.P + cur)) {
+        const int mn = __ldg(S.sig_min_time + s * S.P + cur), mx = __ldg(S.sig_max_time + s * S.P + cur);
+        const int nxt = (cur + 1) % P;
+        if (t < mn) allow = 1u << cur;
+        else if (t < mx) allow = (1u << cur) | (1u << nxt);
+        else if (t == mx) allow = 1u << nxt;
+    } else if (S.round_robin) {
+        allow = 1u << ((cur + 1) % P);
+    } else {
+        for (int p = 0; p < P; ++p)
+            if (__ldg(S.sig_phase_green + s * S.P + p) && p != cur - 1) allow |= 1u << p;
+    }
+    return allow;
+}
+
+// counter-based generator for tie breaks (the reference draws np.random.choice): splitmix64 of
+// (seed, replica, signal, tick)
+__device__ __forceinline__ u32 ctl_random(int seed, int b, int s, int tick) {
+    unsigned long long z = (unsigned long long) (u32) seed * 0x9E3779B97F4A7C15ull + ((unsigned long long) (u32) b << 32 | (u32) s);
+    z ^= (unsigned long long) (u32) tick * 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (u32) (z >> 16);
+}
+
+// ---- pytsc's rule-based controllers (controllers/controllers.py:57-268) for every signal of the
+//      replica, from the state as it is now: decided[s] = the pytsc phase index get_action returns ----
 template <int NT>
-__device__ void apply_controller(const DevScn &S, Ctx &c, const StepArgs &a, int b) {
+__device__ void controller_decide(const DevScn &S, Ctx &c, const StepArgs &a, int b, int *decided) {
+    const int mode = a.apply_actions, L = S.L, A = S.A, vis = S.visibility;
+    // per lane: bins of the incoming-side window holding exactly one standing vehicle (== 0.0,
+    // controllers.py:111), holding any vehicle (>= 0.0, :163, :236), and the same on the outgoing side (:168)
+    u8 *tail_zero = (u8 *) c.npos, *tail_any = tail_zero + L, *head_any = tail_any + L;
+    if (mode != 7) {
+        for (int l = threadIdx.x; l < L; l += NT) {
+            int z = 0, n = 0, h = 0;
+            if (c.cnt[l] > 0) {
+                double w[16];
+                lane_window(S, c, l, true, w);
+                for (int k = 0; k < vis; ++k) { z += w[k] == 0.0; n += w[k] >= 0.0; }
+                lane_window(S, c, l, false, w);
+                for (int k = 0; k < vis; ++k) h += w[k] >= 0.0;
+            }
+            tail_zero[l] = (u8) z; tail_any[l] = (u8) n; head_any[l] = (u8) h;
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < A; s += NT) {
+        const int P = __ldg(S.sig_n_phases + s), cur = c.scur[s], t = c.stop[s];
+        const int nxt = (cur + 1) % P;
+        const bool green = __ldg(S.sig_phase_green + s * S.P + cur) != 0;
+        const u32 allow = allowable_phases(S, c, s);
+        int *sc = a.ctl_scores ? a.ctl_scores + ((size_t) b * A + s) * S.P : nullptr;
+        if (sc) for (int p = 0; p < S.P; ++p) sc[p] = (mode == 4 || mode == 5) ? INT_MIN : 0;
+        int idx = nxt;
+        if (mode == 2) {            // FixedTimeController (controllers.py:39-54)
+            idx = (green && t < a.controller_arg) ? cur : nxt;
+        } else if (mode == 4 || mode == 5) {   // Greedy (:66-114) / MaxPressure (:123-176)
+            if (green) {
+                int best = INT_MIN, n_tie = 0;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int pick = pass ? (int) (ctl_random(a.controller_arg, b, s, c.h->tick) % (u32) (n_tie > 0 ? n_tie : 1)) : 0;
+                    int seen = 0;
+                    for (int p = 0; p < P; ++p) {
+                        if (!((allow >> p) & 1u)) continue;
+                        int score = 0;
+                        for (int e = __ldg(S.ctl_off + s * S.P + p), e1 = __ldg(S.ctl_off + s * S.P + p + 1); e < e1; ++e) {
+                            const int li = __ldg(S.ctl_in_lane + e);
+                            if (mode == 4) score += tail_zero[li];
+                            else {
+                                const int lo = __ldg(S.ctl_out_lane + e);
+                                const int d = (int) tail_any[li] - (lo >= 0 ? (int) head_any[lo] : 0);
+                                score += d < 0 ? -d : d;
+                            }
+                        }
+                        if (!pass) {
+                            if (sc) sc[p] = score;
+                            if (score > best) { best = score; n_tie = 1; } else if (score == best) ++n_tie;
+                        } else if (score == best) {
+                            if (seen == pick) { idx = p; break; }
+                            ++seen;
+                        }
+                    }
+                }
+            }
+        } else if (mode == 6) {     // SOTL (:199-238)
+            if ((allow >> cur) & 1u) {
+                const int theta = a.controller_arg & 0xFF, mu = (a.controller_arg >> 8) & 0xFF, phi_min = (a.controller_arg >> 16) & 0xFFFF;
+                int flow[2];
+                for (int q = 0; q < 2; ++q) {
+                    const int p = q ? (cur + 2) % P : cur;      // next_green_phase_index (common/traffic_signal.py:228-238)
+                    int f = 0;
+                    for (int e = __ldg(S.ctl_off + s * S.P + p), e1 = __ldg(S.ctl_off + s * S.P + p + 1); e < e1; ++e)
+                        f += tail_any[__ldg(S.ctl_in_lane + e)];
+                    flow[q] = f;
+                }
+                if (sc) { sc[0] = flow[0]; if (S.P > 1) sc[1] = flow[1]; }
+                idx = (t >= phi_min && !(0 < flow[0] && flow[0] < mu) && flow[1] >= theta) ? nxt : cur;
+            }
+        } else {                    // Random (:252-268): uniform over the allowed phase indices
+            const int n = __popc(allow);
+            int pick = n ? (int) (ctl_random(a.controller_arg, b, s, c.h->tick) % (u32) n) : 0;
+            for (int p = 0; p < P; ++p)
+                if ((allow >> p) & 1u) { if (pick == 0) { idx = p; break; } --pick; }
+        }
+        decided[s] = idx;
+        if (a.ctl_actions) a.ctl_actions[(size_t) b * A + s] = idx;
+    }
+    __syncthreads();
+}
+
+template <int NT>
+__device__ void apply_controller(const DevScn &S, Ctx &c, const StepArgs &a, int b, const int *decided) {
     for (int s = threadIdx.x; s < S.A; s += NT) {
         if (a.set_raw_phase) c.sraw[s] = (u8) a.raw_phase[(size_t) b * S.A + s];
         if (a.init_program >= 0) {
@@ -781,6 +984,9 @@ __device__ void apply_controller(const DevScn &S, Ctx &c, const StepArgs &a, int
             int idx;
             if (a.apply_actions == 2) {   // FixedTimeController.get_action (controllers.py:39-54)
                 idx = (__ldg(S.sig_phase_green + s * S.P + cur) && t < a.controller_arg) ? cur : (cur + 1) % P;
+            } else if (a.apply_actions >= 4) {   // the rule-based controller's choice (controller_decide)
+                idx = decided[s];
+                if (idx < 0 || idx >= P) idx = cur;
             } else {
                 int act = a.actions[(size_t) b * S.A + s];
                 if (a.apply_actions == 3) idx = act;                                               // TSController.switch_phase(index)
@@ -843,29 +1049,8 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         for (int e = tid; e < n_in + n_out; e += NT) {
             bool inc = e < n_in;
             int l = inc ? __ldg(S.sig_in_lane + e) : __ldg(S.sig_out_lane + e - n_in);
-            double plen = __ldg(S.lane_pytsc_length + l);
-            double mspeed = __ldg(S.drv_max_speed + l);
-            int bins = (int) (plen / S.v_size);
-            int n = c.cnt[l], base = c.off[l];
             double w[16];
-            for (int k = 0; k < vis; ++k) w[k] = -1.0;
-            if (bins > 0 && n > 0) {
-                int len = bins < vis ? vis : bins;           // padded length
-                int lo = inc ? len - vis : 0;                // window start in the padded list
-                double bin_size = plen / bins;
-                for (int k = 0; k < n; ++k) {
-                    double p = round6(c.pos[base + k]);
-                    if (p < 0) p = 0; else if (p > plen) p = plen;
-                    int bi = trunc_int_x86(py_floordiv(p, bin_size));
-                    if (bi >= bins) bi = bins - 1;
-                    int wi = bi - lo;
-                    if (wi >= 0 && wi < vis) {
-                        double nsp = round6(c.spd[base + k]) / mspeed;
-                        w[wi] += 1.0;
-                        w[wi] += nsp;
-                    }
-                }
-            }
+            lane_window(S, c, l, inc, w);
             if (inc) {
                 if (S.obs_type == TSC_OBS_POSITION_MATRIX) for (int k = 0; k < vis; ++k) win_in[e * vis + k] = w[k];
                 if (O.pos_in) for (int k = 0; k < vis; ++k) O.pos_in[((size_t) b * n_in + e) * vis + k] = (float) w[k];
@@ -932,19 +1117,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         }
         // action mask (common/traffic_signal.py:329-361, 375-404; actions.py:119-131, 169-188)
         if (O.mask) {
-            u32 allow = 0;
-            if (__ldg(S.sig_phase_green + s * S.P + cur)) {
-                int mn = __ldg(S.sig_min_time + s * S.P + cur), mx = __ldg(S.sig_max_time + s * S.P + cur);
-                int nxt = (cur + 1) % P;
-                if (t < mn) allow = 1u << cur;
-                else if (t < mx) allow = (1u << cur) | (1u << nxt);
-                else if (t == mx) allow = 1u << nxt;
-            } else if (S.round_robin) {
-                allow = 1u << ((cur + 1) % P);
-            } else {
-                for (int p = 0; p < P; ++p)
-                    if (__ldg(S.sig_phase_green + s * S.P + p) && p != cur - 1) allow |= 1u << p;
-            }
+            const u32 allow = allowable_phases(S, c, s);
             u8 *m = O.mask + ((size_t) b * A + s) * S.n_actions;
             if (S.action_space == TSC_ACT_PHASE_SWITCH) {
                 m[0] = (allow >> cur) & 1; m[1] = (allow >> ((cur + 1) % P)) & 1;
@@ -1062,7 +1235,9 @@ __device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, in
     for (int i = tid; i < bytes / 16; i += nt) d[i] = s[i];
 }
 
-template <int NT, int MINB>
+// CTL: the rule-based controllers are compiled in (kept out of the plain variant: their code costs the
+// hot path 2-3 % through register allocation alone).  STAGED: register-staged re-pack (see engine_tick).
+template <int NT, int MINB, bool CTL, bool STAGED>
 __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
                                                       const u8 *is_spawn_lane, const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -1131,7 +1306,9 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
         pt_mark(c, PT_STAGE_IN);
 
-        apply_controller<NT>(S, c, a, b);
+        int *decided = (int *) c.nspd;       // free between ticks
+        if (CTL && (a.apply_actions >= 4 || a.decide_only)) controller_decide<NT>(S, c, a, b, decided);
+        if (!a.decide_only) apply_controller<NT>(S, c, a, b, decided);
         __syncthreads();
         // lane-link availability under the signals' current light phases: fixed for the whole launch
         for (int k0 = 0; k0 < S.K; k0 += NT) {      // uniform trip count: every lane takes part in the ballot
@@ -1147,12 +1324,12 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         }
         __syncthreads();
         pt_mark(c, PT_PROLOGUE);
-        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT>(S, Y, c, is_spawn_lane);
+        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT, STAGED>(S, Y, c, is_spawn_lane);
         if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
         pt_mark(c, PT_RETRIEVE);
 
         // ---- write the image back ----
-        if (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0) {
+        if (!a.decide_only && (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0)) {
             copy16(img, smem, Y.o_meta_end, tid, NT);
             const int n = c.h->n_slots;
             const int n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
@@ -1196,12 +1373,14 @@ static int fail(int code, const char *fmt, ...) {
         if (e__ != cudaSuccess) return fail(TSC_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
     } while (0)
 
-// Threads per replica block: 256 by default, TSC_B200_THREADS=512 selects the wide variant.
+// Kernel variants.  256 threads per replica block while at least two replicas fit an SM's shared memory
+// (launch bounds 3 -> 80 registers, 2 -> 128); one 512-thread block per SM for replicas larger than
+// that, register-staged when even one copy of the identity columns is too much.
 typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
-static step_kernel_t kernel_for(int nt, int minb) {
-    if (nt == 512) return tsc_step_kernel<512, 1>;
-    if (nt == 128) return minb >= 6 ? tsc_step_kernel<128, 6> : tsc_step_kernel<128, 4>;
-    return minb >= 4 ? tsc_step_kernel<256, 4> : (minb == 3 ? tsc_step_kernel<256, 3> : tsc_step_kernel<256, 2>);
+static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged) {
+    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true> : tsc_step_kernel<512, 1, true, false>;
+    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false> : tsc_step_kernel<256, 2, true, false>;
+    return minb >= 3 ? tsc_step_kernel<256, 3, false, false> : tsc_step_kernel<256, 2, false, false>;
 }
 
 #define MAX_HOST_CHUNKS 16
@@ -1219,7 +1398,8 @@ struct tsc_engine {
     int32_t *h_actions = nullptr;      // pinned staging for the *_host path
     float *h_obs = nullptr, *h_reward = nullptr, *h_rg = nullptr;
     u8 *h_mask = nullptr;
-    int grid = 0, regs = 0, nt = 256, minb = 2;
+    int grid = 0, grid_ctl = 0, regs = 0, nt = 256, minb = 2;
+    step_kernel_t kern = nullptr, kern_ctl = nullptr;   // plain variant / with the rule-based controllers
     int64_t launches = 0;
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
     cudaStream_t host_compute = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
@@ -1247,8 +1427,9 @@ static int upload(tsc_engine *E, const Tp *host, size_t n, const Tp **dev) {
 
 static int align16(int x) { return (x + 15) & ~15; }
 
-static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
+static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.Vcap = Vcap;
+    Y.staged = staged;
     Y.ent_cap = Vcap / 2 < 64 ? 64 : (Vcap / 2 > 2048 ? 2048 : Vcap / 2);   // vehicles changing drivable in one tick
     int o = sizeof(RepHeader);
     Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
@@ -1271,10 +1452,11 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     int need_np = 2 * S.L, need_ns = 2 * S.A + 160;
     int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
     Y.o_dn = o; o = align16(o + 4 * Vcap);
-    Y.o_dn2 = o; o = align16(o + 4 * Vcap);
-    Y.o_vid2 = o; o = align16(o + 4 * Vcap);
-    Y.o_ellt2 = o; o = align16(o + 4 * Vcap);
-    Y.o_pj2 = o; o = align16(o + Vcap);
+    const int V2 = Y.staged ? 0 : Vcap;    // second copy of the identity columns: only for the ping-pong re-pack
+    Y.o_dn2 = o; o = align16(o + 4 * V2);
+    Y.o_vid2 = o; o = align16(o + 4 * V2);
+    Y.o_ellt2 = o; o = align16(o + 4 * V2);
+    Y.o_pj2 = o; o = align16(o + V2);
     Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
     Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
     Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
@@ -1309,6 +1491,10 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     if (s->visibility > 16 || s->visibility < 1) return fail(TSC_EINVAL, "visibility must be in 1..16");
     if (s->max_phases > 32) return fail(TSC_EINVAL, "more than 32 phases per signal");
     if (s->n_lanes + s->n_lanelinks >= 65535) return fail(TSC_EINVAL, "too many drivables for one replica block");
+    if (!s->ctl_off || s->ctl_off[s->n_signals * s->max_phases] != s->n_ctl_total) return fail(TSC_EINVAL, "ctl_off does not end at n_ctl_total");
+    for (int e = 0; e < s->n_ctl_total; ++e)
+        if (s->ctl_in_lane[e] < 0 || s->ctl_in_lane[e] >= s->n_lanes || s->ctl_out_lane[e] >= s->n_lanes)
+            return fail(TSC_EINVAL, "controller table entry %d: bad lane index", e);
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(TSC_EINVAL, "device %d not available (%d devices)", device, ndev);
@@ -1332,6 +1518,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     UP(sig_out_off, A + 1) UP(sig_out_lane, s->n_out_total) UP(sig_n_phases, A) UP(sig_phase_raw, A * s->max_phases)
     UP(sig_phase_green, A * s->max_phases) UP(sig_min_time, A * s->max_phases) UP(sig_max_time, A * s->max_phases)
     UP(nbr_off, A + 1) UP(nbr_idx, s->n_nbr_total) UP(nbr_weight, s->n_nbr_total)
+    UP(ctl_off, A * s->max_phases + 1) UP(ctl_in_lane, s->n_ctl_total) UP(ctl_out_lane, s->n_ctl_total)
 #undef UP
     S.reward_type = s->reward_type; S.obs_type = s->obs_type; S.action_space = s->action_space; S.round_robin = s->round_robin;
     S.visibility = s->visibility; S.yellow_time = s->yellow_time; S.obs_dim = s->obs_dim; S.state_dim = s->state_dim;
@@ -1399,29 +1586,45 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     int Vcap = vehicle_capacity > 0 ? vehicle_capacity : 1024;
     Vcap = (Vcap + E->n_spawn_lanes + 31) & ~31;
     if (Vcap > 65000) { tsc_destroy(E); return fail(TSC_EINVAL, "vehicle_capacity too large for one replica block"); }
-    build_layout(E->Y, S, Vcap);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    // Pick the variant from what fits: 256-thread blocks (ping-pong re-pack) while >= 2 replicas fit an
+    // SM; else one 512-thread block per SM; register-staged (13 bytes less per vehicle slot) only when
+    // that is what makes the replica fit.  TSC_B200_THREADS / TSC_B200_STAGED / TSC_B200_MIN_BLOCKS override.
+    int staged = 0;
+    build_layout(E->Y, S, Vcap, 0);
+    E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
+    if (E->minb < 2) E->nt = 512;
+    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 256 || v == 512) E->nt = v; }
+    if (E->nt == 512 && (size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin && Vcap <= SCATTER_PER * 512) staged = 1;
+    if (const char *env = getenv("TSC_B200_STAGED")) { int v = atoi(env); if (v == 0 || (v == 1 && E->nt == 512 && Vcap <= SCATTER_PER * 512)) staged = v; }
+    if (staged) build_layout(E->Y, S, Vcap, 1);
     if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) {
         int need = E->Y.smem_bytes;
         tsc_destroy(E);
         return fail(TSC_ENOMEM, "replica working set %d B exceeds %zu B of shared memory per block; lower vehicle_capacity",
                     need, (size_t) prop.sharedMemPerBlockOptin);
     }
-    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 128 || v == 256 || v == 512) E->nt = v; }
-    // blocks per SM the shared-memory footprint allows decides the register budget (launch bounds variant)
+    // blocks per SM the shared-memory footprint allows decides the register budget (launch bounds variant);
+    // measured on B200 (Hangzhou, B = 4096): 4 blocks x 64 registers loses to 3 blocks x 80 (1.41 vs 1.34 ms)
     E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
     if (E->minb < 1) E->minb = 1;
-    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 8) E->minb = v; }
-    step_kernel_t kern = kernel_for(E->nt, E->minb);
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E->Y.smem_bytes));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E->nt, E->Y.smem_bytes));
-    if (per_sm < 1) per_sm = 1;
-    E->grid = prop.multiProcessorCount * per_sm;
-    if (E->grid > n_replicas) E->grid = n_replicas;
+    if (E->minb > 3) E->minb = 3;
+    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
+    E->kern = kernel_for(E->nt, E->minb, false, staged != 0);
+    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0);
+    for (int k = 0; k < 2; ++k) {
+        step_kernel_t kern = k ? E->kern_ctl : E->kern;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E->Y.smem_bytes));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E->nt, E->Y.smem_bytes));
+        if (per_sm < 1) per_sm = 1;
+        int grid = prop.multiProcessorCount * per_sm;
+        if (grid > n_replicas) grid = n_replicas;
+        (k ? E->grid_ctl : E->grid) = grid;
+    }
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, E->kern));
     E->regs = fa.numRegs;
 
     CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) n_replicas * E->Y.img_bytes));
@@ -1504,9 +1707,11 @@ int tsc_reset(tsc_handle E, void *stream) {
 
 static int launch(tsc_handle E, const StepArgs &a, void *stream) {
     CUDA_TRY(cudaSetDevice(E->device));
-    int grid = E->grid < a.B - a.b0 ? E->grid : a.B - a.b0;
+    const bool ctl = a.apply_actions >= 4 || a.decide_only;
+    int grid = ctl ? E->grid_ctl : E->grid;
+    if (grid > a.B - a.b0) grid = a.B - a.b0;
     if (grid <= 0) return 0;
-    kernel_for(E->nt, E->minb)<<<grid, E->nt, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
     E->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1548,13 +1753,39 @@ int tsc_retrieve(tsc_handle E, const tsc_outputs_t *out, void *stream) {
     return launch(E, a, stream);
 }
 
+// TSC_CTRL_* -> the kernel's apply_actions code; whether the controller reads the caller's actions
+static int controller_mode(int controller) {
+    switch (controller) {
+        case TSC_CTRL_EXTERNAL: return 1;
+        case TSC_CTRL_FIXED_TIME: return 2;
+        case TSC_CTRL_PHASE_INDEX: return 3;
+        case TSC_CTRL_GREEDY: return 4;
+        case TSC_CTRL_MAX_PRESSURE: return 5;
+        case TSC_CTRL_SOTL: return 6;
+        case TSC_CTRL_RANDOM: return 7;
+    }
+    return 0;
+}
+static bool controller_needs_actions(int controller) { return controller == TSC_CTRL_EXTERNAL || controller == TSC_CTRL_PHASE_INDEX; }
+
+int tsc_controller_act(tsc_handle E, int32_t controller, int32_t controller_arg, int32_t *actions_out, int32_t *scores_out,
+                       void *stream) {
+    if (!E || !actions_out) return fail(TSC_EINVAL, "null argument");
+    if (!controller_mode(controller) || controller_needs_actions(controller))
+        return fail(TSC_EINVAL, "controller %d is not a rule-based controller", controller);
+    StepArgs a = blank_args(E);
+    a.apply_actions = controller_mode(controller); a.controller_arg = controller_arg;
+    a.decide_only = 1; a.ctl_actions = actions_out; a.ctl_scores = scores_out;
+    return launch(E, a, stream);
+}
+
 int tsc_env_step(tsc_handle E, const int32_t *actions, int32_t controller, int32_t controller_arg, int32_t n_ticks,
                  const tsc_outputs_t *out, void *stream) {
     if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
-    if (controller != TSC_CTRL_FIXED_TIME && !actions) return fail(TSC_EINVAL, "actions required unless TSC_CTRL_FIXED_TIME");
-    if (controller < TSC_CTRL_EXTERNAL || controller > TSC_CTRL_PHASE_INDEX) return fail(TSC_EINVAL, "unknown controller %d", controller);
+    if (!controller_mode(controller)) return fail(TSC_EINVAL, "unknown controller %d", controller);
+    if (controller_needs_actions(controller) && !actions) return fail(TSC_EINVAL, "actions required by controller %d", controller);
     StepArgs a = blank_args(E);
-    a.apply_actions = controller == TSC_CTRL_FIXED_TIME ? 2 : (controller == TSC_CTRL_PHASE_INDEX ? 3 : 1);
+    a.apply_actions = controller_mode(controller);
     a.controller_arg = controller_arg; a.actions = actions; a.n_ticks = n_ticks;
     if (out) { a.do_retrieve = 1; a.out = *out; }
     return launch(E, a, stream);
@@ -1570,7 +1801,7 @@ static bool is_pinned(const void *p) {
 int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t controller, int32_t controller_arg, int32_t n_ticks,
                       float *obs_host, float *reward_host, uint8_t *mask_host, float *reward_global_host) {
     if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
-    if (controller < TSC_CTRL_EXTERNAL || controller > TSC_CTRL_PHASE_INDEX) return fail(TSC_EINVAL, "unknown controller %d", controller);
+    if (!controller_mode(controller)) return fail(TSC_EINVAL, "unknown controller %d", controller);
     CUDA_TRY(cudaSetDevice(E->device));
     const size_t A = (size_t) E->S.A, io = (size_t) E->B * A;
     // Replicas are independent, so the batch is cut into chunks: while chunk k+1 is being stepped on
@@ -1580,8 +1811,8 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     CUDA_TRY(cudaEventRecord(E->host_ev[0], 0));
     CUDA_TRY(cudaStreamWaitEvent(sc, E->host_ev[0], 0));
     // page-locked caller buffers are used in place; pageable ones go through the handle's pinned staging
-    if (controller != TSC_CTRL_FIXED_TIME) {
-        if (!actions_host) return fail(TSC_EINVAL, "actions required unless TSC_CTRL_FIXED_TIME");
+    if (controller_needs_actions(controller)) {
+        if (!actions_host) return fail(TSC_EINVAL, "actions required by controller %d", controller);
         const int32_t *src = actions_host;
         if (!is_pinned(actions_host)) { memcpy(E->h_actions, actions_host, io * sizeof(int)); src = E->h_actions; }
         CUDA_TRY(cudaMemcpyAsync(E->d_actions, src, io * sizeof(int), cudaMemcpyHostToDevice, sc));
@@ -1594,7 +1825,7 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     bool all_pinned = true;
     for (Out &x : outs) if (x.user) { x.direct = is_pinned(x.user); all_pinned = all_pinned && x.direct; }
     StepArgs a = blank_args(E);
-    a.apply_actions = controller == TSC_CTRL_FIXED_TIME ? 2 : (controller == TSC_CTRL_PHASE_INDEX ? 3 : 1);
+    a.apply_actions = controller_mode(controller);
     a.controller_arg = controller_arg; a.actions = E->d_actions; a.n_ticks = n_ticks;
     a.do_retrieve = 1;
     if (obs_host) a.out.obs = E->d_obs;

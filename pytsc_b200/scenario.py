@@ -20,7 +20,7 @@ import numpy as np
 from . import bundle
 from .roadnet import RoadNet, VEHICLE_KEYS, expand_flows
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 T_STRIDE = 12
 REWARD_TYPES = {"queue_length": 0, "max_pressure": 1}
 OBS_TYPES = {"lane_features": 0, "position_matrix": 1}
@@ -40,6 +40,7 @@ class tsc_scenario_t(C.Structure):
         ("abi_version", _i), ("n_lanes", _i), ("n_lanelinks", _i), ("n_signals", _i), ("n_vehicles", _i),
         ("n_templates", _i), ("n_route_seq", _i), ("n_cross_entries", _i), ("horizon_ticks", _i),
         ("max_raw_phases", _i), ("max_phases", _i), ("n_in_total", _i), ("n_out_total", _i), ("n_nbr_total", _i),
+        ("n_ctl_total", _i),
         ("drv_length", _pd), ("drv_max_speed", _pd), ("lane_ll_off", _pi), ("lane_ll", _pi),
         ("lane_spawn_off", _pi), ("lane_spawn_vid", _pi), ("ll_start_lane", _pi), ("ll_end_lane", _pi),
         ("ll_signal", _pi), ("ll_roadlink", _pi), ("ll_type", _pi), ("ll_cross_off", _pi),
@@ -50,6 +51,7 @@ class tsc_scenario_t(C.Structure):
         ("sig_out_off", _pi), ("sig_out_lane", _pi), ("sig_n_phases", _pi), ("sig_phase_raw", _pi),
         ("sig_phase_green", _pu8), ("sig_min_time", _pi), ("sig_max_time", _pi),
         ("nbr_off", _pi), ("nbr_idx", _pi), ("nbr_weight", _pd),
+        ("ctl_off", _pi), ("ctl_in_lane", _pi), ("ctl_out_lane", _pi),
         ("reward_type", _i), ("obs_type", _i), ("action_space", _i), ("round_robin", _i), ("visibility", _i),
         ("yellow_time", _i), ("obs_dim", _i), ("state_dim", _i), ("n_actions", _i), ("reference_exact", _i),
         ("max_lanes_per_signal", _i), ("max_obs_phases", _i),
@@ -234,6 +236,22 @@ def compile_scenario(config, parser, flows=None, flow_file=None) -> CompiledScen
         wts.append(w)
     a["nbr_off"], a["nbr_idx"] = _csr(nbr)
     _, a["nbr_weight"] = _csr(wts, f64)
+    # rule-based controllers (controllers/controllers.py:95-114, 151-176, 222-238): the incoming lanes a
+    # pytsc phase serves and, per incoming lane, the LAST outgoing lane listed for it -- MaxPressure's
+    # inner loop overwrites instead of accumulating, so only that one counts
+    ctl_in, ctl_out = [], []
+    for t in signal_ids:
+        cfg = ts[t]
+        for p in range(P):
+            ins, outs = [], []
+            if p < cfg["n_phases"]:
+                for inc_lane, out_lanes in cfg["phase_to_inc_out_lanes"].get(cfg["phases"][p], {}).items():
+                    ins.append(lane_idx[inc_lane])
+                    outs.append(lane_idx[out_lanes[-1]] if out_lanes else -1)
+            ctl_in.append(ins)
+            ctl_out.append(outs)
+    a["ctl_off"], a["ctl_in_lane"] = _csr(ctl_in)
+    _, a["ctl_out_lane"] = _csr(ctl_out)
 
     vis = int(sig["visibility"])
     obs_type = OBS_TYPES[sig["observation_space"]]
@@ -244,7 +262,7 @@ def compile_scenario(config, parser, flows=None, flow_file=None) -> CompiledScen
              n_templates=len(sp["templates"]) or 1, n_route_seq=len(seq), n_cross_entries=len(xs),
              horizon_ticks=horizon, max_raw_phases=max_raw, max_phases=P,
              n_in_total=int(a["sig_in_off"][-1]), n_out_total=int(a["sig_out_off"][-1]),
-             n_nbr_total=int(a["nbr_off"][-1]),
+             n_nbr_total=int(a["nbr_off"][-1]), n_ctl_total=int(a["ctl_off"][-1]),
              reward_type=REWARD_TYPES[sig["reward_function"]], obs_type=obs_type, action_space=act,
              round_robin=int(bool(sig["round_robin"])), visibility=vis, yellow_time=int(sig["yellow_time"]),
              obs_dim=obs_dim, state_dim=state_dim, n_actions=(P if act == 0 else 2),

@@ -65,6 +65,34 @@ CASES = {
 }
 
 
+# controller case -> (scenario, kwargs, controller name, controller kwargs, env-steps)
+# Recorded from the reference's own controller classes (pytsc/controllers/controllers.py) run the way
+# controllers/evaluate.py:112-137 runs them: action space forced to phase_selection, one controller object
+# per signal fed the simulator's step measurements.
+CONTROLLER_CASES = {
+    "ctl_sotl__hangzhou_4_4": ("hangzhou_4_4", dict(signal=dict(observation_space="lane_features",
+                               reward_function="queue_length", action_space="phase_selection", round_robin=False)),
+                               "sotl", dict(theta=3, mu=4, phi_min=5), 144),
+    "ctl_greedy__hangzhou_4_4": ("hangzhou_4_4", dict(signal=dict(observation_space="lane_features",
+                                 reward_function="queue_length", action_space="phase_selection", round_robin=False)),
+                                 "greedy", {}, 144),
+    "ctl_max_pressure__jinan_3_4": ("jinan_3_4", dict(signal=dict(observation_space="lane_features",
+                                    reward_function="max_pressure", action_space="phase_selection", round_robin=False)),
+                                    "max_pressure", {}, 120),
+    "ctl_max_pressure_rr__syn_1x1": ("syn_1x1", dict(
+        cityflow=dict(flow_rate_type="constant", flow_file="syn_1x1__gaussian_700_flows.json"),
+        signal=dict(observation_space="lane_features", reward_function="max_pressure",
+                    action_space="phase_selection", round_robin=True)), "max_pressure", {}, 160),
+    "ctl_random__syn_1x1": ("syn_1x1", dict(
+        cityflow=dict(flow_rate_type="constant", flow_file="syn_1x1__gaussian_600_flows.json"),
+        signal=dict(observation_space="lane_features", reward_function="queue_length",
+                    action_space="phase_selection", round_robin=False)), "random", {}, 100),
+    "ctl_fixed_time__jinan_3_4": ("jinan_3_4", dict(signal=dict(observation_space="lane_features",
+                                  reward_function="queue_length", action_space="phase_selection", round_robin=False)),
+                                  "fixed_time", dict(green_time=25), 100),
+}
+
+
 def setup_reference(ref):
     from pytsc_b200 import compat
     from oracle.engine import Engine
@@ -141,13 +169,81 @@ def record_case(name, scenario, kwargs, T, seed=0):
     return out
 
 
+def record_controller_case(name, scenario, kwargs, controller, ckw, T, seed=0):
+    """The reference's rule-based controller in closed loop.  Per step: the mask each controller saw,
+    the score the controller computes for every phase index (its own helper methods), the action it
+    returned, then the outputs of ``network.step(actions)``."""
+    from pytsc import TrafficSignalNetwork
+    from pytsc.controllers import CONTROLLERS
+    np.random.seed(seed)
+    net = TrafficSignalNetwork(scenario, "cityflow", **kwargs)
+    eng = net.simulator.engine
+    lane_ids = eng.lane_ids
+    ts = list(net.traffic_signals.values())
+    ctl = [CONTROLLERS[controller](t, **ckw) for t in ts]
+    P = max(t.controller.n_phases for t in ts)
+    rec = {k: [] for k in ("mask", "scores", "actions", "cur", "time_on_phase", "obs", "reward_global", "lane_count",
+                           "lane_queued", "sim")}
+    snaps = {}
+    MASKED = -2 ** 31
+    for t in range(T):
+        inp = net.simulator.step_measurements
+        masks, scores, acts, cur, top = [], [], [], [], []
+        for sig, c in zip(ts, ctl):
+            m = [int(x) for x in sig.controller.get_allowable_phase_switches()]
+            m += [0] * (P - len(m))
+            sc = [0] * P
+            green = sig.controller.current_phase_index in sig.controller.green_phase_indices
+            if controller in ("greedy", "max_pressure"):
+                f = c._compute_queue_for_phase if controller == "greedy" else c._compute_pressure_for_phase
+                sc = [int(f(inp, p)) if (green and p < sig.controller.n_phases and m[p]) else MASKED for p in range(P)]
+            elif controller == "sotl" and m[sig.controller.current_phase_index]:
+                sc[0] = int(c._compute_flow_for_phase(inp, sig.controller.current_phase_index))
+                sc[1] = int(c._compute_flow_for_phase(inp, sig.controller.next_green_phase_index))
+            cur.append(sig.controller.current_phase_index)
+            top.append(sig.controller.time_on_phase)
+            masks.append(m)
+            scores.append(sc)
+            acts.append(int(c.get_action(inp)))
+        r_glob, done, info = net.step(acts)
+        rec["mask"].append(masks); rec["scores"].append(scores); rec["actions"].append(acts)
+        rec["cur"].append(cur); rec["time_on_phase"].append(top)
+        rec["obs"].append(np.asarray(net.get_observations(), np.float64))
+        rec["reward_global"].append(float(r_glob))
+        lm = net.simulator.step_measurements["lane"]
+        rec["lane_count"].append([lm[l]["n_vehicles"] for l in lane_ids])
+        rec["lane_queued"].append([lm[l]["n_queued"] for l in lane_ids])
+        sm = net.simulator.step_measurements["sim"]
+        rec["sim"].append([sm["n_vehicles"], sm["average_travel_time"], sm["time_step"], eng.get_finished_vehicle_count()])
+        if t == T - 1:
+            s = eng.snapshot()
+            for k in ("uid", "drivable", "distance", "speed"):
+                snaps[f"snap{t}_{k}"] = s[k]
+    return dict(mask=np.asarray(rec["mask"], np.uint8), scores=np.asarray(rec["scores"], np.int64),
+                actions=np.asarray(rec["actions"], np.int32), cur=np.asarray(rec["cur"], np.int32),
+                time_on_phase=np.asarray(rec["time_on_phase"], np.int32), obs=np.asarray(rec["obs"]),
+                reward_global=np.asarray(rec["reward_global"]), lane_count=np.asarray(rec["lane_count"], np.int32),
+                lane_queued=np.asarray(rec["lane_queued"], np.int32), sim=np.asarray(rec["sim"], np.float64),
+                lane_ids=np.asarray(lane_ids), signal_ids=np.asarray([s.id for s in ts]),
+                scenario=np.asarray(scenario), kwargs=np.asarray(repr(kwargs)), controller=np.asarray(controller),
+                controller_kwargs=np.asarray(repr(ckw)), n_steps=np.asarray(T), snap_steps=np.asarray([T - 1]), **snaps)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("cases", nargs="*")
     args = ap.parse_args()
     setup_reference(args.ref)
-    for name in (args.cases or CASES):
+    for name in (args.cases or list(CASES) + list(CONTROLLER_CASES)):
+        if name in CONTROLLER_CASES:
+            scenario, kwargs, controller, ckw, T = CONTROLLER_CASES[name]
+            out = record_controller_case(name, scenario, kwargs, controller, ckw, T)
+            path = os.path.join(HERE, name + ".npz")
+            np.savez_compressed(path, **out)
+            print(f"{name}: T={T} A={out['actions'].shape[1]} veh(end)={int(out['sim'][-1, 0])} "
+                  f"switches={int((out['actions'] != out['cur']).sum())} -> {os.path.getsize(path) / 1024:.0f} KB")
+            continue
         scenario, kwargs, T = CASES[name]
         out = record_case(name, scenario, kwargs, T)
         path = os.path.join(HERE, name + ".npz")

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     assert set(names) == set(binding.SYMBOLS)
     for n in names:
         assert getattr(cuda_lib, n) is not None
-    assert cuda_lib.tsc_abi_version() == 1
+    assert cuda_lib.tsc_abi_version() == 2
 
 
 def test_library_is_sm100a_sass(cuda_lib):
@@ -39,14 +39,14 @@ def test_struct_layout_matches_header(tmp_path):
     from pytsc_b200.binding import tsc_outputs_t
     from pytsc_b200.scenario import tsc_scenario_t
     src = tmp_path / "layout.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tsc_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tsc_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(tsc_scenario_t), offsetof(tsc_scenario_t, tmpl), offsetof(tsc_scenario_t, interval),'
-                   'sizeof(tsc_outputs_t), offsetof(tsc_outputs_t, metrics), offsetof(tsc_scenario_t, reward_type));return 0;}')
+                   'sizeof(tsc_outputs_t), offsetof(tsc_outputs_t, metrics), offsetof(tsc_scenario_t, reward_type), offsetof(tsc_scenario_t, ctl_off));return 0;}')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     exp = [C.sizeof(tsc_scenario_t), tsc_scenario_t.tmpl.offset, tsc_scenario_t.interval.offset,
-           C.sizeof(tsc_outputs_t), tsc_outputs_t.metrics.offset, tsc_scenario_t.reward_type.offset]
+           C.sizeof(tsc_outputs_t), tsc_outputs_t.metrics.offset, tsc_scenario_t.reward_type.offset, tsc_scenario_t.ctl_off.offset]
     assert got == exp
 
 
