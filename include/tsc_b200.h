@@ -50,7 +50,7 @@ enum {
     TSC_OK = 0,
     TSC_EINVAL = -1,      /* bad argument / scenario table */
     TSC_ECUDA = -2,       /* CUDA runtime error (message has the detail) */
-    TSC_ENOMEM = -3,      /* replica state does not fit in shared memory on this device */
+    TSC_ENOMEM = -3,      /* out of device memory for the replica state */
     TSC_EOVERFLOW = -4,   /* a replica exceeded vehicle_capacity (sticky flag, see tsc_check) */
     TSC_EORDER = -5       /* a vehicle left its drivable out of FIFO order (sticky flag) */
 };
@@ -272,6 +272,12 @@ int  tsc_debug_timing(tsc_handle h, int32_t enable, uint64_t *cycles_out, int32_
 
 /* Name, bytes of dynamic shared memory, threads per block and grid of the step kernel. */
 int  tsc_kernel_info(tsc_handle h, int32_t *smem_bytes, int32_t *threads, int32_t *grid, int32_t *regs);
+
+/* Which variant of the step kernel the handle runs: staged = 1 when the per-tick re-pack stages the
+ * identity columns in registers (large replicas that only fit shared memory that way);
+ * global_workspace = 1 when the replica's working set does not fit shared memory at all and lives in a
+ * global-memory (L2-resident) workspace; blocks_per_sm = launch-bounds variant. */
+int  tsc_kernel_variant(tsc_handle h, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm);
 
 #ifdef __cplusplus
 }

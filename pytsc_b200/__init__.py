@@ -40,7 +40,7 @@ def register(install_import_stubs: bool = True):
 
 
 def __getattr__(name):
-    if name == "BatchedTrafficSignalNetwork":
-        from .env import BatchedTrafficSignalNetwork
-        return BatchedTrafficSignalNetwork
+    if name in ("BatchedTrafficSignalNetwork", "BatchedEPyMARLTrafficSignalNetwork"):
+        from . import env
+        return getattr(env, name)
     raise AttributeError(name)

@@ -22,7 +22,7 @@ ERRORS = {-1: "TSC_EINVAL", -2: "TSC_ECUDA", -3: "TSC_ENOMEM", -4: "TSC_EOVERFLO
 SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "tsc_get_dims", "tsc_reset",
            "tsc_set_phase", "tsc_init_program", "tsc_step", "tsc_retrieve", "tsc_env_step", "tsc_env_step_host",
            "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
-           "tsc_debug_timing", "tsc_controller_act")
+           "tsc_debug_timing", "tsc_controller_act", "tsc_kernel_variant")
 
 # tsc_env_step / tsc_controller_act controller codes (include/tsc_b200.h)
 CONTROLLERS = {"external": 0, "fixed_time": 1, "phase_index": 2, "greedy": 3, "max_pressure": 4, "sotl": 5, "random": 6}
@@ -79,6 +79,7 @@ def load_library(path=None):
     L.tsc_kernel_info.argtypes = [vp, pi32, pi32, pi32, pi32]
     L.tsc_debug_timing.argtypes = [vp, i32, vp, i32]
     L.tsc_controller_act.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.tsc_kernel_variant.argtypes = [vp, pi32, pi32, pi32]
     for n in SYMBOLS:
         getattr(L, n)
     if path == LIB_PATH:
@@ -263,4 +264,7 @@ class Engine:
     def kernel_info(self):
         v = [C.c_int32() for _ in range(4)]
         self._check(self.lib.tsc_kernel_info(self.h, *[C.byref(x) for x in v]))
-        return dict(zip(("smem_bytes", "threads", "grid", "regs"), [x.value for x in v]))
+        w = [C.c_int32() for _ in range(3)]
+        self._check(self.lib.tsc_kernel_variant(self.h, *[C.byref(x) for x in w]))
+        return dict(zip(("smem_bytes", "threads", "grid", "regs", "staged", "global_workspace", "blocks_per_sm"),
+                        [x.value for x in v + w]))

@@ -126,6 +126,7 @@ struct StepArgs {
     const int *actions;    // [B][A]
     const int *raw_phase;  // [B][A]
     unsigned long long *phase_cycles;   // debug: per-phase clock64 sums (thread 0 of every block), or NULL
+    unsigned char *workspace;           // GMEM variant: one working set of Y.smem_bytes (256-byte aligned stride) per block
     tsc_outputs_t out;
 };
 
@@ -143,7 +144,7 @@ __device__ __forceinline__ int trunc_int_x86(double x) {
 }
 
 #define SMEM_TEMPLATES 4
-#define SCATTER_PER 4    // vehicles per thread the register-staged re-pack can hold   // vehicle templates cached in shared memory (more: read from global)
+#define SCATTER_PER 8    // vehicles per thread the register-staged re-pack can hold   // vehicle templates cached in shared memory (more: read from global)
 
 struct Ctx {
     RepHeader *h;
@@ -1237,10 +1238,13 @@ __device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, in
 
 // CTL: the rule-based controllers are compiled in (kept out of the plain variant: their code costs the
 // hot path 2-3 % through register allocation alone).  STAGED: register-staged re-pack (see engine_tick).
-template <int NT, int MINB, bool CTL, bool STAGED>
+// GMEM: the replica's working set does not fit an SM's shared memory (a 16 x 16 grid needs ~1 MB): the
+// block works out of a global-memory workspace instead -- same layout, same code, L2-resident.
+template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM>
 __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
                                                       const u8 *is_spawn_lane, const StepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem_block[];
+    unsigned char *const smem = GMEM ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes + 255) & ~255) : smem_block;
     const int tid = threadIdx.x;
     Ctx c;
     c.h = (RepHeader *) smem;
@@ -1375,12 +1379,14 @@ static int fail(int code, const char *fmt, ...) {
 
 // Kernel variants.  256 threads per replica block while at least two replicas fit an SM's shared memory
 // (launch bounds 3 -> 80 registers, 2 -> 128); one 512-thread block per SM for replicas larger than
-// that, register-staged when even one copy of the identity columns is too much.
+// that, register-staged when even one copy of the identity columns is too much; one 1024-thread block
+// per SM over a global-memory workspace for replicas that do not fit shared memory at all.
 typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
 static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged) {
-    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true> : tsc_step_kernel<512, 1, true, false>;
-    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false> : tsc_step_kernel<256, 2, true, false>;
-    return minb >= 3 ? tsc_step_kernel<256, 3, false, false> : tsc_step_kernel<256, 2, false, false>;
+    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true>;
+    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true, false> : tsc_step_kernel<512, 1, true, false, false>;
+    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false> : tsc_step_kernel<256, 2, true, false, false>;
+    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false> : tsc_step_kernel<256, 2, false, false, false>;
 }
 
 #define MAX_HOST_CHUNKS 16
@@ -1402,6 +1408,8 @@ struct tsc_engine {
     step_kernel_t kern = nullptr, kern_ctl = nullptr;   // plain variant / with the rule-based controllers
     int64_t launches = 0;
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
+    unsigned char *workspace = nullptr;             // GMEM variant: grid working sets in global memory
+    bool gmem = false;
     cudaStream_t host_compute = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
     cudaEvent_t host_ev[1 + MAX_HOST_CHUNKS] = {};
     int host_chunks = MAX_HOST_CHUNKS;   // upper bound on chunks per host step (TSC_B200_HOST_CHUNKS)
@@ -1430,7 +1438,7 @@ static int align16(int x) { return (x + 15) & ~15; }
 static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.Vcap = Vcap;
     Y.staged = staged;
-    Y.ent_cap = Vcap / 2 < 64 ? 64 : (Vcap / 2 > 2048 ? 2048 : Vcap / 2);   // vehicles changing drivable in one tick
+    Y.ent_cap = Vcap / 2 < 64 ? 64 : (Vcap / 2 > 8192 ? 8192 : Vcap / 2);   // vehicles changing drivable in one tick
     int o = sizeof(RepHeader);
     Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
     Y.o_wq = o; o = align16(o + 2 * (S.n_spawn_lanes + 1));
@@ -1585,7 +1593,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
 
     int Vcap = vehicle_capacity > 0 ? vehicle_capacity : 1024;
     Vcap = (Vcap + E->n_spawn_lanes + 31) & ~31;
-    if (Vcap > 65000) { tsc_destroy(E); return fail(TSC_EINVAL, "vehicle_capacity too large for one replica block"); }
+    if (Vcap > 32767) { tsc_destroy(E); return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     // Pick the variant from what fits: 256-thread blocks (ping-pong re-pack) while >= 2 replicas fit an
@@ -1599,11 +1607,11 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     if (E->nt == 512 && (size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin && Vcap <= SCATTER_PER * 512) staged = 1;
     if (const char *env = getenv("TSC_B200_STAGED")) { int v = atoi(env); if (v == 0 || (v == 1 && E->nt == 512 && Vcap <= SCATTER_PER * 512)) staged = v; }
     if (staged) build_layout(E->Y, S, Vcap, 1);
-    if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) {
-        int need = E->Y.smem_bytes;
-        tsc_destroy(E);
-        return fail(TSC_ENOMEM, "replica working set %d B exceeds %zu B of shared memory per block; lower vehicle_capacity",
-                    need, (size_t) prop.sharedMemPerBlockOptin);
+    if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) E->gmem = true;
+    if (const char *env = getenv("TSC_B200_GMEM")) E->gmem = atoi(env) != 0 || E->gmem;
+    if (E->gmem) {      // global-memory working sets: ping-pong layout, 1024 threads, one block per SM
+        E->nt = 1024;
+        build_layout(E->Y, S, Vcap, 0);
     }
     // blocks per SM the shared-memory footprint allows decides the register budget (launch bounds variant);
     // measured on B200 (Hangzhou, B = 4096): 4 blocks x 64 registers loses to 3 blocks x 80 (1.41 vs 1.34 ms)
@@ -1613,11 +1621,12 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
     E->kern = kernel_for(E->nt, E->minb, false, staged != 0);
     E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0);
+    const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;
     for (int k = 0; k < 2; ++k) {
         step_kernel_t kern = k ? E->kern_ctl : E->kern;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E->Y.smem_bytes));
+        if (dyn_smem) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
         int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E->nt, E->Y.smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E->nt, dyn_smem));
         if (per_sm < 1) per_sm = 1;
         int grid = prop.multiProcessorCount * per_sm;
         if (grid > n_replicas) grid = n_replicas;
@@ -1627,6 +1636,10 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     CUDA_TRY(cudaFuncGetAttributes(&fa, E->kern));
     E->regs = fa.numRegs;
 
+    if (E->gmem) {
+        const int g = E->grid > E->grid_ctl ? E->grid : E->grid_ctl;
+        CUDA_TRY(cudaMalloc((void **) &E->workspace, (size_t) g * (size_t) ((E->Y.smem_bytes + 255) & ~255)));
+    }
     CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) n_replicas * E->Y.img_bytes));
     // tick-0 image: empty network, one spare slot per spawn lane
     E->init_image.assign(E->Y.img_bytes, 0);
@@ -1666,6 +1679,7 @@ void tsc_destroy(tsc_handle E) {
     cudaSetDevice(E->device);
     for (void *p : E->dev_allocs) cudaFree(p);
     cudaFree(E->d_phase_cycles);
+    cudaFree(E->workspace);
     if (E->host_compute) cudaStreamDestroy(E->host_compute);
     if (E->host_copy) cudaStreamDestroy(E->host_copy);
     for (auto &ev : E->host_ev) if (ev) cudaEventDestroy(ev);
@@ -1711,7 +1725,7 @@ static int launch(tsc_handle E, const StepArgs &a, void *stream) {
     int grid = ctl ? E->grid_ctl : E->grid;
     if (grid > a.B - a.b0) grid = a.B - a.b0;
     if (grid <= 0) return 0;
-    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->gmem ? 0 : E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
     E->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1722,6 +1736,7 @@ static StepArgs blank_args(tsc_handle E) {
     memset(&a, 0, sizeof a);
     a.b0 = 0; a.B = E->B; a.init_program = -1;
     a.phase_cycles = E->d_phase_cycles;
+    a.workspace = E->workspace;
     return a;
 }
 
@@ -2004,6 +2019,14 @@ int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t
     if (threads) *threads = E->nt;
     if (grid) *grid = E->grid;
     if (regs) *regs = E->regs;
+    return 0;
+}
+
+int tsc_kernel_variant(tsc_handle E, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    if (staged) *staged = E->Y.staged;
+    if (global_workspace) *global_workspace = E->gmem ? 1 : 0;
+    if (blocks_per_sm) *blocks_per_sm = E->minb;
     return 0;
 }
 

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 from .backend.config import Config
 from .backend.network_parser import NetworkParser
-from .binding import Engine
+from .binding import CONTROLLERS, Engine, sotl_arg
 from .scenario import compile_scenario
 
 def shard_replicas(total_replicas: int, world_size: int, rank: int):
@@ -124,18 +124,29 @@ class BatchedTrafficSignalNetwork:
         self.engine.close()
 
     # ---- the step (pytsc/__init__.py:178-182) ---------------------------------------------
-    def step(self, actions=None, controller=None, green_time=25):
-        """``actions``: int32 [B, A] device tensor in the configured action space; or
-        ``controller="fixed_time"`` to let the in-kernel FixedTimeController act."""
-        if controller == "fixed_time":
-            self.engine.env_step(None, self.out, n_ticks=self.delta_time, controller=1, controller_arg=green_time)
-        else:
+    def step(self, actions=None, controller=None, green_time=25, seed=0, theta=3, mu=4, phi_min=5):
+        """``actions``: int32 [B, A] device tensor in the configured action space; or ``controller`` =
+        one of pytsc's rule-based controllers (``pytsc/controllers/controllers.py``) evaluated inside
+        the launch: ``"fixed_time"`` (green_time), ``"greedy"`` / ``"max_pressure"`` / ``"random"``
+        (``seed`` of the tie-break stream), ``"sotl"`` (theta, mu, phi_min)."""
+        if controller is None or controller == "external":
             self.engine.env_step(actions, self.out, n_ticks=self.delta_time, controller=0)
+        elif controller == "phase_index":
+            self.engine.env_step(actions, self.out, n_ticks=self.delta_time, controller=CONTROLLERS["phase_index"])
+        else:
+            arg = {"fixed_time": green_time, "sotl": sotl_arg(theta, mu, phi_min)}.get(controller, seed)
+            self.engine.env_step(None, self.out, n_ticks=self.delta_time, controller=CONTROLLERS[controller], controller_arg=arg)
         self._tick += self.delta_time
         self._acc[0] += self.out["reward_global"].sum()
         self._acc[1] += self.out["metrics"][:, 0].sum()
         self._acc[2] += self.n_replicas
         return self.out["reward_global"], self.episode_over, self.get_env_info()
+
+    def controller_actions(self, controller, scores=False, **kw):
+        """The phase indices ``controller`` would choose in the current state (``tsc_controller_act``)."""
+        arg = {"fixed_time": kw.get("green_time", 25),
+               "sotl": sotl_arg(kw.get("theta", 3), kw.get("mu", 4), kw.get("phi_min", 5))}.get(controller, kw.get("seed", 0))
+        return self.engine.controller_act(controller, arg, scores=scores)
 
     # getters return the tensors the last launch wrote (no copies, no syncs)
     def get_observations(self):
@@ -174,3 +185,81 @@ class BatchedTrafficSignalNetwork:
                            self._acc[0], self._acc[1], self._acc[2],
                            torch.tensor(float(self.n_replicas), dtype=torch.float64, device=self.device)])
         return reduce_episode_metrics(vec, group)
+
+
+class BatchedEPyMARLTrafficSignalNetwork:
+    """``EPyMARLTrafficSignalNetwork`` (``pytsc/wrappers/epymarl.py:11-111``) with a leading replica
+    dimension: the smac-style API MARL trainers drive (``reset`` -> ``obs, state``; ``step(actions)``
+    -> ``obs, reward, episode_over, truncated, info``; ``get_avail_actions``), every array a device
+    tensor of shape ``[B, ...]``.  ``common_reward`` + ``reward_scalarization="mean"`` give the
+    global reward divided by the number of agents (epymarl.py:103-110), otherwise the local rewards."""
+
+    def __init__(self, map_name="hangzhou_4_4", simulator_backend="gpu", n_replicas=None, device=None, **kwargs):
+        if simulator_backend != "gpu":
+            raise ValueError("BatchedEPyMARLTrafficSignalNetwork drives the gpu backend only")
+        kwargs.pop("scenario", None)
+        self.common_reward = kwargs.pop("common_reward", True)
+        self.reward_scalarization = kwargs.pop("reward_scalarization", "mean")
+        self.tsc_env = BatchedTrafficSignalNetwork(map_name, n_replicas=n_replicas, device=device, **kwargs)
+        self.episode_limit = self.tsc_env.episode_limit
+
+    def get_avail_actions(self):
+        return self.tsc_env.get_action_mask()
+
+    def get_obs(self):
+        return self.tsc_env.get_observations()
+
+    def get_obs_size(self):
+        return self.tsc_env.get_observation_size()
+
+    def get_state(self):
+        return self.tsc_env.get_state()
+
+    def get_state_size(self):
+        return self.tsc_env.get_state_size()
+
+    def get_local_rewards(self):
+        return self.tsc_env.get_rewards()
+
+    def get_total_actions(self):
+        return self.tsc_env.get_action_size()
+
+    def get_network_flow(self):
+        return self.tsc_env.out["metrics"][:, 5]
+
+    def get_stats(self):
+        return self.tsc_env.get_env_info()
+
+    def get_env_info(self):
+        env = self.tsc_env
+        return {"agents": list(env.parsed_network.traffic_signals.keys()), "episode_limit": self.episode_limit,
+                "n_actions": self.get_total_actions(), "adjacency_matrix": env.parsed_network.adjacency_matrix,
+                "n_agents": env.n_agents, "obs_shape": self.get_obs_size(), "state_shape": self.get_state_size(),
+                "n_replicas": env.n_replicas}
+
+    def is_terminated(self):
+        return self.tsc_env.is_terminated
+
+    def sim_step(self):
+        return self.tsc_env.sim_step
+
+    def reset(self):
+        """epymarl.py:96-101: count the episode, hand out the current observations, restart the
+        simulation once its horizon is reached."""
+        self.tsc_env.episode_count += 1
+        obs, state = self.get_obs(), self.get_state()
+        if self.tsc_env.episode_over:
+            self.tsc_env.restart()
+        return obs, state
+
+    def step(self, actions):
+        reward, episode_over, env_info = self.tsc_env.step(actions)
+        if self.common_reward:
+            if self.reward_scalarization == "mean":
+                reward = reward / self.tsc_env.n_agents
+        else:
+            reward = self.get_local_rewards()
+        return self.get_obs(), reward, episode_over, False, env_info
+
+    def close(self):
+        self.tsc_env.close()

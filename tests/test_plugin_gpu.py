@@ -96,3 +96,57 @@ def test_reference_facade_on_device(cuda_lib, case):
         if done:
             net.restart()
     net.simulator.close_simulator()
+
+
+def test_batched_epymarl_wrapper_replays_reference(cuda_lib):
+    """BASELINE config 3 shape: Jinan 3x4, queue reward, the smac-style API
+    (epymarl.py:96-111) with a replica dimension -- common reward = global / n_agents."""
+    import torch
+    from pytsc_b200 import BatchedEPyMARLTrafficSignalNetwork
+    g = load_golden("jinan_3_4__lf_queue_select")
+    kw = {k: dict(v) for k, v in g["kwargs"].items()}
+    B = 6
+    env = BatchedEPyMARLTrafficSignalNetwork(map_name=g["scenario"], simulator_backend="gpu", n_replicas=B, **kw)
+    info = env.get_env_info()
+    assert info["n_agents"] == 12 and info["n_actions"] == g["mask"].shape[-1] and info["obs_shape"] == g["obs"].shape[-1]
+    assert info["agents"] == [str(x) for x in g["signal_ids"]]
+    obs, state = env.reset()
+    assert np.array_equal(env.get_avail_actions()[0].cpu().numpy(), g["mask0"])
+    for t in range(int(g["n_steps"])):
+        act = torch.from_numpy(np.repeat(g["actions"][t][None], B, 0).astype(np.int32)).cuda()
+        obs, reward, over, truncated, _ = env.step(act)
+        assert not truncated and over == ((t + 1) % env.episode_limit == 0)
+        assert np.array_equal(obs[B - 1].cpu().numpy().astype(np.float64), g["obs"][t])
+        assert np.array_equal(env.get_state()[1].cpu().numpy().astype(np.float64), g["state"][t])
+        assert np.array_equal(env.get_avail_actions()[2].cpu().numpy(), g["mask"][t])
+        np.testing.assert_allclose(reward.cpu().numpy(), np.full(B, g["reward_global"][t] / 12), rtol=REL_TOL)
+        np.testing.assert_allclose(env.get_local_rewards()[3].cpu().numpy(), g["reward"][t], rtol=REL_TOL)
+        if over:
+            env.reset()
+    env.tsc_env.check()
+    loc = BatchedEPyMARLTrafficSignalNetwork(map_name=g["scenario"], n_replicas=2, common_reward=False, **kw)
+    act = torch.from_numpy(np.repeat(g["actions"][0][None], 2, 0).astype(np.int32)).cuda()
+    _, reward, _, _, _ = loc.step(act)
+    np.testing.assert_allclose(reward[0].cpu().numpy(), g["reward"][0], rtol=REL_TOL)
+    env.close(); loc.close()
+
+
+def test_batched_env_rule_based_controllers(cuda_lib):
+    """env.step(controller=...) for every in-kernel controller == asking tsc_controller_act first and
+    feeding its phase indices back as external actions."""
+    import torch
+    from pytsc_b200 import BatchedTrafficSignalNetwork
+    kw = dict(signal=dict(observation_space="lane_features", reward_function="queue_length",
+                          action_space="phase_selection", round_robin=False))
+    for name, ckw in (("sotl", dict(theta=2, mu=3, phi_min=10)), ("greedy", dict(seed=5)), ("max_pressure", dict(seed=5)),
+                      ("random", dict(seed=9))):
+        a = BatchedTrafficSignalNetwork("jinan_3_4", n_replicas=3, **kw)
+        b = BatchedTrafficSignalNetwork("jinan_3_4", n_replicas=3, **kw)
+        for t in range(50):
+            acts = b.controller_actions(name, **ckw)
+            a.step(controller=name, **ckw)
+            b.step(acts, controller="phase_index")
+            assert torch.equal(a.get_observations(), b.get_observations()), (name, t)
+            assert torch.equal(a.get_action_mask(), b.get_action_mask()), (name, t)
+        a.check(); b.check()
+        a.close(); b.close()
