@@ -159,6 +159,45 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------
+class HostFixedTimePolicy:
+    """FixedTimeController.get_action (controllers/controllers.py:39-54) for all B x A signals on the
+    host, with its own copy of the programs' state (current phase index, time on phase): the e2e
+    leg's stand-in for a user's policy.  numpy, preallocated temporaries, table look-ups."""
+
+    def __init__(self, sig_phase_green, sig_n_phases, B, A, green_time, n_ticks):
+        import numpy as np
+        self.np = np
+        green = np.ascontiguousarray(sig_phase_green).reshape(A, -1).astype(np.uint8)
+        P = green.shape[1]
+        nph = np.asarray(sig_n_phases, np.int64).reshape(A, 1)
+        self.green_flat = green.ravel()
+        self.next_flat = ((np.arange(P, dtype=np.int64)[None, :] + 1) % nph).astype(np.uint8).ravel()
+        self.base = (np.arange(A, dtype=np.intp) * P)[None, :]
+        self.green_time, self.n_ticks = green_time, n_ticks
+        self.cur = np.zeros((B, A), np.uint8)
+        self.top = np.zeros((B, A), np.int32)
+        self.idx = np.empty((B, A), np.intp)
+        self.nxt = np.empty((B, A), np.uint8)
+        self.flag = np.empty((B, A), bool)
+
+    def reset(self):
+        self.cur.fill(0)
+        self.top.fill(0)
+
+    def act(self, out):
+        np = self.np
+        np.add(self.base, self.cur, out=self.idx)
+        stay = self.green_flat[self.idx]                       # on a green phase ...
+        np.less(self.top, self.green_time, out=self.flag)     # ... for less than green_time
+        np.logical_and(stay, self.flag, out=self.flag)
+        np.take(self.next_flat, self.idx, out=self.nxt, mode="clip")
+        np.copyto(self.nxt, self.cur, where=self.flag)
+        # BaseTSProgram.update_current_phase (common/traffic_signal.py:94-109)
+        np.add(self.top, self.n_ticks, out=self.top)
+        np.not_equal(self.nxt, self.cur, out=self.flag)
+        np.copyto(self.top, self.n_ticks, where=self.flag)
+        self.cur[...] = self.nxt
+        out[...] = self.nxt
 def algorithmic_bytes_per_env_step(V, L, K, A, obs_dim, P, n_ticks=5):
     """per tick 40 B per vehicle + 8 B per drivable + 4 B per signal; per env-step
     16 B per lane + per agent (4 obs_dim + reward 4 + mask P + action 4)."""
@@ -255,29 +294,25 @@ def run_gpu_arm(args):
     h_rew = torch.empty((B, A), dtype=torch.float32, **pin)
     h_mask = torch.empty((B, A, eng.dims["n_actions"]), dtype=torch.uint8, **pin)
     h_rg = torch.empty((B,), dtype=torch.float32, **pin)
-    green = torch.from_numpy(np.ascontiguousarray(cs.sig_phase_green.reshape(A, -1)).astype(bool))
-    nph = torch.from_numpy(np.asarray(cs.sig_n_phases, np.int64))
-    cur = torch.zeros((B, A), dtype=torch.int64)
-    top = torch.zeros((B, A), dtype=torch.int64)
-    ar = torch.arange(A)
+    policy = HostFixedTimePolicy(cs.sig_phase_green, cs.sig_n_phases, B, A, GREEN_TIME, n_ticks)
+    act_np = h_act.numpy()
 
     def host_policy():
-        """FixedTimeController on the host (controllers/controllers.py:39-54) for all B x A signals."""
-        stay = green[ar[None, :], cur] & (top < GREEN_TIME)
-        nxt = torch.where(stay, cur, (cur + 1) % nph[None, :])
-        top.copy_(torch.where(nxt == cur, top + n_ticks, torch.full_like(top, n_ticks)))
-        cur.copy_(nxt)
-        h_act.copy_(nxt.to(torch.int32))
+        policy.act(act_np)
 
     def e2e_restart():
         restart()
-        cur.zero_(); top.zero_()
+        policy.reset()
         torch.cuda.synchronize()
+
+    policy_s = [0.0]
 
     def e2e_step():
         if state["step"] == sim_len_steps:
             e2e_restart()
+        t_p = time.perf_counter()
         host_policy()
+        policy_s[0] += time.perf_counter() - t_p
         eng.env_step_host(h_act.numpy(), obs=h_obs.numpy(), reward=h_rew.numpy(), mask=h_mask.numpy(),
                           reward_global=h_rg.numpy(), n_ticks=n_ticks)
         state["step"] += 1
@@ -287,6 +322,7 @@ def run_gpu_arm(args):
         e2e_step()
     sync_all()
     l0 = eng.launch_count()
+    policy_s[0] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -348,7 +384,10 @@ def run_gpu_arm(args):
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": alg, "units_per_launch": B},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "mean_global_reward_last_step": e2e_reward},
+                "ms_per_step": 1e3 * e2e_s / args.steps, "mean_global_reward_last_step": e2e_reward,
+                "host_policy_ms_per_step": 1e3 * policy_s[0] / args.steps,
+                "note": "host fixed-time policy (numpy, inside the timed region) -> actions H2D -> chunked launches, "
+                        "observation rows D2H while the next chunk is stepped -> rewards / masks D2H"},
         "gpu_launches": int(launches),
         "e2e_gpu_launches": int(e2e_launches),
         "clocks": clk,

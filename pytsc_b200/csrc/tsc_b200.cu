@@ -16,10 +16,12 @@
 #include <cuda_runtime.h>
 
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -57,6 +59,7 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     int n_in_total, n_out_total, n_spawn_lanes;
     const double *drv_length, *drv_max_speed;
     const int *lane_ll_off, *lane_ll, *lane_spawn_off, *lane_spawn_vid, *spawn_lane;
+    const short *lane_spawn_idx;     // [L] index into the spawn-lane list, -1 for lanes nothing spawns on
     const int *ll_start_lane, *ll_end_lane, *ll_signal, *ll_roadlink, *ll_type, *ll_cross_off;
     const double *xr_dist, *xr_foe_dist;
     const int *xr_foe_ll;
@@ -66,13 +69,15 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     const int *created_cnt;          // [horizon+2] vehicles created before tick t
     const long long *created_enter;  // [horizon+2] sum of their creation ticks
     // pytsc tables
-    const double *lane_pytsc_length, *lane_feat;
+    const double *lane_pytsc_length, *lane_feat, *lane_cells;
     const int *sig_in_off, *sig_in_lane, *sig_out_off, *sig_out_lane;
     const int *sig_n_phases, *sig_phase_raw, *sig_min_time, *sig_max_time;
     const u8 *sig_phase_green;
     const int *nbr_off, *nbr_idx;
     const double *nbr_weight;
     const int *ctl_off, *ctl_in_lane, *ctl_out_lane;   // rule-based controllers: lanes served by every pytsc phase
+    const u32 *obs_code;      // [A * state_dim] lane-feature row recipe: 0 = static, else kind | truncate << 3 | argument << 4
+    const float *obs_static;  // [A * state_dim] the static values (lane features as the reference stores them, -1 padding)
     int reward_type, obs_type, action_space, round_robin, visibility, yellow_time;
     int obs_dim, state_dim, n_actions, reference_exact, max_lanes_per_signal, max_obs_phases;
     double v_size, flick, interval;
@@ -89,7 +94,8 @@ struct RepHeader {   // 64 bytes, first thing in every replica image
     int n_ent;            // scratch: movers this tick
     int n_x;              // scratch: vehicles deferred to the cross phase this tick
     int n_h, n_a;         // scratch: head vehicles / vehicles in an intersection zone this tick
-    int pad[3];
+    int n_pairs;          // scratch: (deferred vehicle, cross) pairs this tick
+    int pad[2];
 };
 static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 
@@ -99,6 +105,8 @@ static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 
 struct Layout {
     int Vcap, ent_cap;
+    int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
+    int pair_cap;          // (vehicle, cross) pairs the flat cross phase can list (0: warp-per-vehicle phase only)
     int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
     // persistent part: identical byte offsets in the HBM image and in shared memory
     int o_cnt, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
@@ -179,15 +187,25 @@ enum { TD_A = TSC_T_STRIDE,      // 0.5 / maxNegAcc            ("a" of the no-co
 // x * DT and x / DT are exact identities and fold away.
 #define DT 1.0
 
+// ONE_T: the scenario has a single vehicle template (every shipped flow file): the row is the
+// shared-memory copy at a fixed address, and the vehicle-id loads that only selected it disappear.
+template <bool ONE_T>
 __device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, int vid) {
-    return c.tmpl + (S.T == 1 ? 0 : TD_STRIDE * __ldg(S.veh_tmpl + vid));
+    if (ONE_T) return c.tmpl;
+    return c.tmpl + TD_STRIDE * __ldg(S.veh_tmpl + vid);
 }
 
 // ---- A.4 car following -------------------------------------------------------
 // a = 0.5 / dF and 0.5 / a come from the follower's template row.
+// x / y for y > 0 finite: a zero numerator gives that zero back.  The division's exponent-range
+// check sends zero numerators to its out-of-line slow path (~60 instructions); standing vehicles
+// and empty lanes make them the common case.
+__device__ __forceinline__ double div_pos(double x, double y) { return x == 0.0 ? x : x / y; }
+
+// dL > 0 (a deceleration the caller knows to be positive: a template's maxNegAcc, or v - vL > 0)
 __device__ __forceinline__ double no_collision_speed(double vL, double dL, double vF, double a, double half_over_a, double gap,
                                                      double target) {
-    double c = vF * DT / 2 + target - 0.5 * vL * vL / dL - gap;
+    double c = vF * DT / 2 + target - div_pos(0.5 * vL * vL, dL) - gap;
     double b = 0.5 * DT;
     if (b * b < 4 * a * c) return -100;
     double v1 = half_over_a * (sqrt(b * b - 4 * a * c) - b);
@@ -197,9 +215,18 @@ __device__ __forceinline__ double no_collision_speed(double vL, double dL, doubl
 
 __device__ __forceinline__ double car_follow_speed(const double *T, double v, double gap, double vL, double leaderMaxNegAcc) {
     double s = no_collision_speed(vL, leaderMaxNegAcc, v, T[TD_A], T[TD_HALF_OVER_A], gap, 0);
-    double assumeDecel = 0;
-    if (v > vL) assumeDecel = v - vL;
-    s = min2(s, no_collision_speed(vL, assumeDecel, v, T[TD_A], T[TD_HALF_OVER_A], gap, T[TSC_T_MIN_GAP]));
+    double assumeDecel = 0, s2;
+    if (v > vL) {
+        assumeDecel = v - vL;
+        s2 = no_collision_speed(vL, assumeDecel, v, T[TD_A], T[TD_HALF_OVER_A], gap, T[TSC_T_MIN_GAP]);
+    } else {
+        // assumeDecel == 0: CityFlow's formula divides by it.  0.5 vL^2 / 0 is +inf (or NaN for vL^2 == 0), so c is
+        // -inf (NaN), the discriminant test is false, v1 = half_over_a * (sqrt(+inf | NaN) - b) is +inf (NaN) because
+        // a, half_over_a > 0 (checked by tsc_create), and min2(v1, v2) = (v1 < v2 ? v1 : v2) returns v2 either way:
+        // the same bits without the division, the square root and their slow paths.
+        s2 = 2 * vL - 0.0 * DT + 2 * (gap - T[TSC_T_MIN_GAP]) / DT;
+    }
+    s = min2(s, s2);
     s = min2(s, (gap + (vL + assumeDecel / 2) * DT - v * DT / 2) / T[TD_HEADWAY_DEN]);
     return s;
 }
@@ -242,6 +269,7 @@ __device__ __forceinline__ bool ll_available(const Ctx &c, int ll) { return (c.a
 // scan)?  Returns the slot or -1; *d2 = its signed distance to
 // the cross.  Conditions are ordered so that shared memory decides first and
 // the route table (global) is read only when everything else already holds.
+template <bool ONE_T>
 __device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X, double *d2) {
     const int f = X.foe_ll, fl = S.L + f;
     const double dc = X.foe_dist;
@@ -249,7 +277,7 @@ __device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X
     if (n > 0) {   // the vehicle that has just moved onto the end lane
         int t = c.off[X.foe_end_lane] + n - 1;
         double crossDistance = X.foe_len - dc;
-        double vehDistance = c.pos[t] - tmpl_of(S, c, c.vid[t])[TSC_T_LEN];
+        double vehDistance = c.pos[t] - tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN];
         if (crossDistance + vehDistance < 0.0 && !c.pj[t] && __ldg(S.route_seq + c.rpos[t] - 1) == fl) {
             *d2 = -(c.pos[t] + crossDistance);
             return t;
@@ -261,7 +289,7 @@ __device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X
         int v = base + k;
         double vd = c.pos[v];
         if (vd > dc) {
-            if (vd - dc - tmpl_of(S, c, c.vid[v])[TSC_T_LEN] <= 0.0) { *d2 = dc - vd; return v; }
+            if (vd - dc - tmpl_of<ONE_T>(S, c, c.vid[v])[TSC_T_LEN] <= 0.0) { *d2 = dc - vd; return v; }
         } else { *d2 = dc - vd; return v; }
     }
     if (c.cnt[X.foe_start_lane] > 0 && ll_available(c, f)) {   // first vehicle of the incoming lane, heading here on green
@@ -276,17 +304,18 @@ __device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X
 
 // Cross::canPass (A.5) for vehicle `me` on / approaching a lane-link of type t1,
 // at the cross `X`.  *foe_out = announced vehicle on the other link.
+template <bool ONE_T>
 __device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T, int t1, const CrossEntry &X, double dts,
                          int *foe_out) {
     double d2;
-    int foe = cross_claimant(S, c, X, &d2);
+    int foe = cross_claimant<ONE_T>(S, c, X, &d2);
     *foe_out = foe;
     if (foe < 0) return true;
     int t2 = X.foe_type;
     double d1 = X.dist - dts;
     double v = c.spd[me];
     if (!can_yield(T, v, d1)) return true;
-    const double *TF = tmpl_of(S, c, c.vid[foe]);
+    const double *TF = tmpl_of<ONE_T>(S, c, c.vid[foe]);
     double vf = c.spd[foe];
     int yield = 0;
     if (!can_yield(TF, vf, d2)) yield = 1;
@@ -328,11 +357,15 @@ __device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T,
 
 // ---- block-wide exclusive scan of u16 counts into u16 offsets -------------------
 // in[i] (+ extra[i] if given) for i < n; out[n] = total.  All threads call.
+// With `cnt` / `leave` given, in[i] is first set to cnt[i] - leave[i] + in[i] (a tick's new per-drivable counts).
 template <int NT>
-__device__ void block_scan_counts(const u16 *in, const u8 *extra_lane, int n_lane, u16 *out, int n, int *scratch) {
+__device__ void block_scan_counts(u16 *in, const u8 *extra_lane, int n_lane, u16 *out, int n, int *scratch,
+                                  const u16 *cnt = nullptr, const u16 *leave = nullptr) {
     const int per = (n + NT - 1) / NT;
     int lo = threadIdx.x * per, hi = min(lo + per, n);
     int s = 0;
+    if (cnt)
+        for (int i = lo; i < hi; ++i) in[i] = (u16) (cnt[i] - leave[i] + in[i]);
     for (int i = lo; i < hi; ++i) s += in[i] + ((extra_lane && i < n_lane) ? extra_lane[i] : 0);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int incl = s;
@@ -403,7 +436,7 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
 // ----------------------------------------------------------------------------
 // One engine tick for the replica held in shared memory (A.2)
 // ----------------------------------------------------------------------------
-template <int NT, bool STAGED>
+template <int NT, bool STAGED, bool ONE_T>
 __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *is_spawn_lane) {
     const int tid = threadIdx.x;
     const int tick = c.h->tick;
@@ -417,48 +450,11 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         return;
     }
 
-    // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer.  The head of every
-    //      buffer (lane, vehicle, creation tick) is cached in shared memory, so a tick without an
-    //      arrival costs one compare per spawn lane. ----
-    for (int s = tid; s < S.n_spawn_lanes; s += NT) {
-        const int l = c.sp_lane[s];
-        u8 fr = 0;
-        if (c.sp_tick[s] <= tick) {
-            const int v = c.sp_vid[s];
-            int n = c.cnt[l];
-            bool ok = true;
-            if (n > 0) {
-                int t = c.off[l] + n - 1;
-                ok = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of(S, c, v)[TSC_T_MIN_GAP];
-            }
-            if (ok) {
-                int slot = c.off[l] + n;
-                int rp0 = __ldg(S.veh_seq_start + v);
-                c.pos[slot] = 0.0; c.spd[slot] = 0.0;
-                c.rpos[slot] = rp0;
-                c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
-                c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
-                c.pj[slot] = 0;
-                c.cnt[l] = (u16) (n + 1);
-                const int hd = c.wq[s] + 1;
-                c.wq[s] = (u16) hd;
-                const int at = __ldg(S.lane_spawn_off + l) + hd;
-                if (at < __ldg(S.lane_spawn_off + l + 1)) {
-                    const int nv = __ldg(S.lane_spawn_vid + at);
-                    c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
-                } else c.sp_tick[s] = INT_MAX;
-                fr = 1;
-                atomicAdd(&c.h->n_running, 1);
-            }
-        }
-        c.fresh[l] = fr;
-    }
-    for (int d = tid; d < D; d += NT) { c.leave[d] = 0; c.ent[d] = 0; }
-    if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; }
-    __syncthreads();
-    pt_mark(c, PT_SPAWN);
-
-    // ---- getAction is split so that every sub-phase runs the same code in all its lanes:
+    // ---- one pass over the drivables: handleWaiting (at most one vehicle per lane leaves its waiting
+    //      buffer; the head of every buffer -- lane, vehicle, creation tick -- is cached in shared memory,
+    //      so a tick without an arrival costs one compare per spawn lane), the move counters are reset,
+    //      and the non-empty drivables are listed for sub-phase 1a.
+    //      getAction is split so that every sub-phase runs the same code in all its lanes:
     //      1a  head vehicles (one per non-empty drivable): look-ahead leader + gap
     //      1b  every vehicle: car following; vehicles in an intersection zone go on a list
     //      1c  listed vehicles: red light / blocked exit / turn speed; those that must examine
@@ -466,16 +462,52 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     //      2   one warp per vehicle of the second list, one lane per cross ----
     u16 *hlist = c.xlist;      // dead before 1c fills xlist
     u16 *alist = c.newslot;    // dead before the new slots are computed
-    for (int d = tid; d < D; d += NT)
-        if (c.cnt[d] > 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) d;
+    for (int l = tid; l < D; l += NT) {
+        c.leave[l] = 0; c.ent[l] = 0;
+        int n = c.cnt[l];
+        const int s = l < L ? (int) __ldg(S.lane_spawn_idx + l) : -1;
+        if (s >= 0) {
+            u8 fr = 0;
+            if (c.sp_tick[s] <= tick) {
+                const int v = c.sp_vid[s];
+                bool ok = true;
+                if (n > 0) {
+                    int t = c.off[l] + n - 1;
+                    ok = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, v)[TSC_T_MIN_GAP];
+                }
+                if (ok) {
+                    int slot = c.off[l] + n;
+                    int rp0 = __ldg(S.veh_seq_start + v);
+                    c.pos[slot] = 0.0; c.spd[slot] = 0.0;
+                    c.rpos[slot] = rp0;
+                    c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
+                    c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
+                    c.pj[slot] = 0;
+                    c.cnt[l] = (u16) (++n);
+                    const int hd = c.wq[s] + 1;
+                    c.wq[s] = (u16) hd;
+                    const int at = __ldg(S.lane_spawn_off + l) + hd;
+                    if (at < __ldg(S.lane_spawn_off + l + 1)) {
+                        const int nv = __ldg(S.lane_spawn_vid + at);
+                        c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
+                    } else c.sp_tick[s] = INT_MAX;
+                    fr = 1;
+                    atomicAdd(&c.h->n_running, 1);
+                }
+            }
+            c.fresh[l] = fr;
+        }
+        if (n > 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) l;
+    }
     __syncthreads();
+    pt_mark(c, PT_SPAWN);
 
     // 1a: leader and gap of head vehicles as of the end of the previous tick (A.7): vehicles that
     // entered from the waiting buffer this tick are not yet visible to others
     for (int e = tid, n_h = c.h->n_h; e < n_h; e += NT) {
         const int d = hlist[e];
         const int i = c.off[d];
-        const double *T = tmpl_of(S, c, c.vid[i]);
+        const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
         const u32 dnv = c.dn[i];
         const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
         const int rp = c.rpos[i];
@@ -487,14 +519,14 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
             if (nd < 0) break;
             if (nd >= L) {
-                int sl = __ldg(&S.llinfo[nd - L].start_lane);
+                const int sl = (j == 1 && d < L) ? d : __ldg(&S.llinfo[nd - L].start_lane);   // the link after lane d starts at d
                 int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
                 for (int q = e0; q < e1; ++q) {
                     int dl = L + __ldg(S.lane_ll + q);
                     int n = c.cnt[dl];
                     if (n > 0) {
                         int cand = c.off[dl] + n - 1;
-                        double cg = dist + c.pos[cand] - tmpl_of(S, c, c.vid[cand])[TSC_T_LEN];
+                        double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
                         if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
                     }
                 }
@@ -503,7 +535,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 int n = c.cnt[nd] - c.fresh[nd];
                 if (n > 0) {
                     leader = c.off[nd] + n - 1;
-                    gap = dist + c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN];
+                    gap = dist + c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN];
                     break;
                 }
             }
@@ -519,7 +551,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     for (int i = tid; i < n_slots; i += NT) {
         int vid = c.vid[i];
         if (vid < 0) { c.nflag[i] = 0; continue; }
-        const double *T = tmpl_of(S, c, vid);
+        const double *T = tmpl_of<ONE_T>(S, c, vid);
         const u32 dnv = c.dn[i];
         const int d = dnv & 0xFFFF;
         const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
@@ -529,13 +561,13 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         double gap;
         if (i > c.off[d]) {
             leader = i - 1;
-            gap = c.pos[leader] - tmpl_of(S, c, c.vid[leader])[TSC_T_LEN] - x;
+            gap = c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN] - x;
         } else { leader = c.nblk[i]; gap = c.npos[i]; }
         double ns = T[TSC_T_MAX_SPEED];
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
         ns = min2(ns, __ldg(S.drv_max_speed + d));
         double cf = T[TSC_T_MAX_SPEED];
-        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
+        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
         ns = min2(ns, cf);
         if (d >= L || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {   // intersection related speed applies (A.5)
             c.nspd[i] = ns;
@@ -550,7 +582,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     // 1c: intersection related speed, part (i)-(ii) of A.5
     for (int e = tid, n_a = c.h->n_a; e < n_a; e += NT) {
         const int i = alist[e];
-        const double *T = tmpl_of(S, c, c.vid[i]);
+        const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
         const u32 dnv = c.dn[i];
         const int d = dnv & 0xFFFF;
         const double x = c.pos[i], v = c.spd[i];
@@ -565,7 +597,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             int n = c.cnt[el];
             if (n > 0) {
                 int t = c.off[el] + n - 1;
-                enter = c.pos[t] > tmpl_of(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
+                enter = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
             }
             if (!ll_available(c, ll) || !enter) {
                 if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
@@ -577,9 +609,20 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             }
             if (!done && __ldg(&S.llinfo[ll].type) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
         }
-        if (!done) {   // phase 2 walks the crosses with a whole warp
+        if (!done) {   // phase 2 examines the crosses of the lane-link
             c.npos[i] = vi;
-            c.xlist[atomicAdd(&c.h->n_x, 1)] = (u16) i;
+            const int e = atomicAdd(&c.h->n_x, 1);
+            c.xlist[e] = (u16) i;
+            if (!STAGED && Y.pair_cap > 0) {     // one (vehicle, cross) pair per cross of the link
+                const int ll = d >= L ? d - L : (int) (dnv >> 16) - L;
+                const int2 cr = __ldg((const int2 *) &S.llinfo[ll].cross_off);
+                const int nc = cr.y - cr.x;
+                u32 *pairs = c.dn2;
+                ((u32 *) c.ellt2)[e] = 0xFFFFFFFFu;
+                const int p0 = atomicAdd(&c.h->n_pairs, nc);
+                if (p0 + nc <= Y.pair_cap)
+                    for (int k = 0; k < nc; ++k) pairs[p0 + k] = ((u32) e << 8) | (u32) k;
+            }
             continue;
         }
         ns = min2(ns, vi);
@@ -589,15 +632,65 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); atomicAdd(c.pt + PT_NH, (unsigned long long) c.h->n_h); }
     pt_mark(c, PT_PHASE1C);
 
-    // ---- getAction, phase 2: one warp per deferred vehicle, one lane per cross.  canPass has no
-    //      side effects, so evaluating every cross ahead at once and taking the first refusal in
-    //      link order is the sequential scan of A.5(iii). ----
-    {
-        const int n_x = c.h->n_x;
+    // ---- getAction, phase 2: Cross::canPass for every cross ahead of every deferred vehicle.  canPass
+    //      has no side effects, so all crosses are evaluated at once and the first refusal in link order
+    //      is the sequential scan of A.5(iii).
+    //      Flat form: one thread per (vehicle, cross) pair listed by 1c, the first refusal found by an
+    //      atomicMin on (cross position in the link << 16 | announced vehicle), then one thread per
+    //      vehicle commits.  Fallback (register-staged variant, or more pairs than the list holds):
+    //      one warp per vehicle, one lane per cross. ----
+    const int n_x = c.h->n_x;
+    if (!STAGED && Y.pair_cap > 0 && c.h->n_pairs <= Y.pair_cap) {
+        const int n_pairs = c.h->n_pairs;
+        const u32 *pairs = c.dn2;
+        u32 *first_refusal = (u32 *) c.ellt2;
+        for (int p = tid; p < n_pairs; p += NT) {
+            const u32 pr = pairs[p];
+            const int e = (int) (pr >> 8), k = (int) (pr & 0xFFu);
+            const int i = c.xlist[e];
+            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
+            const u32 dnv = c.dn[i];
+            const int d = dnv & 0xFFFF;
+            const bool on_ll = d >= L;
+            const int ll = on_ll ? d - L : (int) (dnv >> 16) - L;
+            const double dts = on_ll ? c.pos[i] : -(__ldg(S.drv_length + d) - c.pos[i]);
+            const int4 head = __ldg((const int4 *) &S.llinfo[ll]);   // start_lane, end_lane, cross_off, cross_end
+            const int t1 = __ldg(&S.llinfo[ll].type);
+            CrossEntry X;
+            const int4 *src = (const int4 *) &S.cross[head.z + k];
+            int4 *dst = (int4 *) &X;
+            dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+            int foe = -1;
+            if (!(X.dist < dts) && !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe))
+                atomicMin(first_refusal + e, ((u32) k << 16) | (u32) foe);
+        }
+        __syncthreads();
+        for (int e = tid; e < n_x; e += NT) {
+            const int i = c.xlist[e];
+            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
+            const u32 dnv = c.dn[i];
+            const int d = dnv & 0xFFFF;
+            const bool on_ll = d >= L;
+            const int ll = on_ll ? d - L : (int) (dnv >> 16) - L;
+            const double x = c.pos[i], v = c.spd[i];
+            const double dlen = __ldg(S.drv_length + d);
+            const double dts = on_ll ? x : -(dlen - x);
+            double vi = c.npos[i], ns = c.nspd[i];
+            int blocker = -1;
+            const u32 fr = first_refusal[e];
+            if (fr != 0xFFFFFFFFu) {
+                const double dOn = __ldg(&S.cross[__ldg(&S.llinfo[ll].cross_off) + (int) (fr >> 16)].dist);
+                vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST]));
+                blocker = (int) (fr & 0xFFFFu);
+            }
+            ns = min2(ns, vi);
+            finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
+        }
+    } else {
         const int lane = tid & 31;
         for (int e = tid >> 5; e < n_x; e += NT / 32) {
             const int i = c.xlist[e];
-            const double *T = tmpl_of(S, c, c.vid[i]);
+            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
             const u32 dnv = c.dn[i];
             const int d = dnv & 0xFFFF;
             const bool on_ll = d >= L;
@@ -620,7 +713,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                     int4 *dst = (int4 *) &X;
                     dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
                     dOn = X.dist;
-                    if (!(dOn < dts)) refuse = !can_pass(S, c, i, T, t1, X, dts, &foe);
+                    if (!(dOn < dts)) refuse = !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, refuse);
                 if (m) {
@@ -641,10 +734,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
 
     // ---- updateLocation: new per-drivable counts, then a stable re-pack ----
     // leave[] = number of leavers, new count = cnt - leave + ent (kept in ent[])
-    for (int d = tid; d < D; d += NT) c.ent[d] = (u16) (c.cnt[d] - c.leave[d] + c.ent[d]);
-    __syncthreads();
     u16 *noff = (u16 *) (c.scan + 64);
-    block_scan_counts<NT>(c.ent, is_spawn_lane, L, noff, D, c.scan);
+    block_scan_counts<NT>(c.ent, is_spawn_lane, L, noff, D, c.scan, c.cnt, c.leave);
     const int n_ent = min(c.h->n_ent, Y.ent_cap);
     if (tid == 0) {
         if (c.h->n_ent > Y.ent_cap) c.h->err |= ERR_ENT_OVERFLOW;
@@ -774,7 +865,10 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
     }
     for (int d = tid; d < D; d += NT) { c.cnt[d] = c.ent[d]; c.off[d] = noff[d]; }
-    if (tid == 0) { c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1; }
+    if (tid == 0) {
+        c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1;
+        c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_pairs = 0;      // scratch counters of the next tick
+    }
     __syncthreads();
     pt_mark(c, PT_SCATTER);
 }
@@ -1014,6 +1108,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     // scratch aliases (the n* arrays are free between ticks)
     double *l_occ = c.npos;              // [L]
     double *l_ms = c.npos + L;           // [L]
+    double *l_nms = c.npos + 2 * L;      // [L] mean speed / lane speed limit (metrics.py:113-135, traffic_signal.py:118)
     int *l_q = (int *) (smem + Y.o_lane_q);   // [L]
     double *s_loc = c.nspd;              // [A] local reward term
     double *s_prs = c.nspd + A;          // [A] pressure
@@ -1028,10 +1123,10 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             tot += v;
             q += v < 0.1;
         }
-        double ms = n ? tot / n : 0.0;
-        double lane_length = __ldg(S.lane_pytsc_length + l) / S.v_size;
-        double occ = n / lane_length;
+        double ms = n ? div_pos(tot, (double) n) : 0.0;
+        double occ = div_pos((double) n, __ldg(S.lane_cells + l));      // lane_cells = pytsc lane length / veh_size_min_gap
         l_occ[l] = occ; l_ms[l] = ms; l_q[l] = q;
+        l_nms[l] = div_pos(ms, __ldg(S.drv_max_speed + l));
         size_t o = (size_t) b * L + l;
         if (O.lane_count) O.lane_count[o] = n;
         if (O.lane_queued) O.lane_queued[o] = q;
@@ -1073,7 +1168,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             nq += l_q[l];
             occ += l_occ[l];
             ms += l_ms[l];
-            md += 1 - l_ms[l] / __ldg(S.drv_max_speed + l);
+            md += 1 - l_nms[l];
         }
         int nin = i1 - i0, nout = o1 - o0;
         occ /= nin; ms /= nin; md /= nin;
@@ -1149,7 +1244,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             qsum += l_q[l]; vsum += n;
             wspeed += l_ms[l] * n;
             occs += l_occ[l];
-            nms += l_ms[l] / __ldg(S.drv_max_speed + l);
+            nms += l_nms[l];
         }
         int chg = 0;
         for (int s = ln; s < A; s += 32) chg += c.schg[s];
@@ -1169,7 +1264,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             double density = occs / L, norm_ms = nms / L;
             if (O.metrics) {
                 double *m = O.metrics + (size_t) b * 8;
-                m[0] = qsum; m[1] = vsum ? wspeed / vsum : 0.0; m[2] = 1 - norm_ms; m[3] = density;
+                m[0] = qsum; m[1] = vsum ? div_pos(wspeed, (double) vsum) : 0.0; m[2] = 1 - norm_ms; m[3] = density;
                 m[4] = psum; m[5] = density * norm_ms; m[6] = flicker; m[7] = norm_ms;
             }
             if (O.reward_global) {
@@ -1192,33 +1287,42 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     }
 
     // --- lane-feature observation / state rows (observations.py:305-329, 352-374): one element per
-    //     thread, rows are contiguous so the stores coalesce ---
+    //     thread, rows are contiguous so the stores coalesce.  What each element is was worked out once
+    //     on the host (build_obs_recipe): a static value (lane features, padding) or a code naming the
+    //     dynamic quantity to read ---
     {
-        const int per = 12, ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
-        const int row = ML * per + MP;                 // == obs_dim (lane features) == state_dim
-        const bool ex = S.reference_exact != 0;
-        float *obs = (O.obs && S.obs_type == TSC_OBS_LANE_FEATURES) ? O.obs + (size_t) b * A * row : nullptr;
-        float *state = O.state ? O.state + (size_t) b * A * row : nullptr;
+        const int n_el = A * S.state_dim;
+        float *obs = (O.obs && S.obs_type == TSC_OBS_LANE_FEATURES) ? O.obs + (size_t) b * n_el : nullptr;
+        float *state = O.state ? O.state + (size_t) b * n_el : nullptr;
         if (obs || state) {
-            for (int idx = tid; idx < A * row; idx += NT) {
-                const int s = idx / row, k = idx - s * row;
-                const int i0 = __ldg(S.sig_in_off + s), nin = __ldg(S.sig_in_off + s + 1) - i0;
-                float val;
-                if (k < ML * per) {
-                    const int e = k / per, f = k - e * per;
-                    if (e < nin) {
-                        const bool tr = ex && nin < ML;      // pad_list only converts when it pads
-                        const int l = __ldg(S.sig_in_lane + i0 + e);
-                        if (f < 9) val = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
-                        else if (f == 9) val = (float) l_q[l];
-                        else val = ref_trunc(f == 10 ? l_occ[l] : l_ms[l], tr);
-                    } else val = -1.0f;
-                } else {
-                    const int ph = k - ML * per;
-                    val = (ph < __ldg(S.sig_n_phases + s) && ph == c.scur[s]) ? 1.0f : 0.0f;
+            auto element = [&](u32 code, float val) -> float {
+                if (code) {
+                    const int kind = code & 7, arg = (int) (code >> 4);
+                    const bool tr = (code & 8) != 0;          // pad_list only converts when it pads
+                    if (kind == 1) val = (float) l_q[arg];
+                    else if (kind == 2) val = ref_trunc(l_occ[arg], tr);
+                    else if (kind == 3) val = ref_trunc(l_ms[arg], tr);
+                    else val = (arg & 0xFF) == c.scur[arg >> 8] ? 1.0f : 0.0f;      // phase one-hot
                 }
-                if (obs) obs[idx] = val;
-                if (state) state[idx] = val;
+                return val;
+            };
+            const bool vec = (n_el & 3) == 0 && ((((size_t) obs) | ((size_t) state)) & 15) == 0;
+            if (vec) {      // four consecutive elements per thread: 16-byte loads of the recipe, 16-byte row stores
+                const uint4 *code4 = (const uint4 *) S.obs_code;
+                const float4 *stat4 = (const float4 *) S.obs_static;
+                for (int q = tid; q < n_el / 4; q += NT) {
+                    const uint4 cd = __ldg(code4 + q);
+                    float4 v = __ldg(stat4 + q);
+                    v.x = element(cd.x, v.x); v.y = element(cd.y, v.y); v.z = element(cd.z, v.z); v.w = element(cd.w, v.w);
+                    if (obs) ((float4 *) obs)[q] = v;
+                    if (state) ((float4 *) state)[q] = v;
+                }
+            } else {
+                for (int idx = tid; idx < n_el; idx += NT) {
+                    const float val = element(__ldg(S.obs_code + idx), __ldg(S.obs_static + idx));
+                    if (obs) obs[idx] = val;
+                    if (state) state[idx] = val;
+                }
             }
         }
     }
@@ -1240,7 +1344,7 @@ __device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, in
 // hot path 2-3 % through register allocation alone).  STAGED: register-staged re-pack (see engine_tick).
 // GMEM: the replica's working set does not fit an SM's shared memory (a 16 x 16 grid needs ~1 MB): the
 // block works out of a global-memory workspace instead -- same layout, same code, L2-resident.
-template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM>
+template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM, bool ONE_T>
 __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
                                                       const u8 *is_spawn_lane, const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_block[];
@@ -1261,7 +1365,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     c.avail = (u32 *) (smem + Y.o_avail);
     c.sp_lane = (int *) (smem + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
     for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
-    if (S.T <= SMEM_TEMPLATES) {
+    if (ONE_T || S.T <= SMEM_TEMPLATES) {
         double *ts = (double *) (smem + Y.o_tmpl);
         for (int k = tid; k < S.T * TD_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
@@ -1289,6 +1393,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
         }
         for (int l = tid; l < S.L; l += NT) c.fresh[l] = 0;
+        if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_pairs = 0; }
         for (int s = tid; s < S.n_spawn_lanes; s += NT) {
             const int l = __ldg(S.spawn_lane + s);
             const int at = __ldg(S.lane_spawn_off + l) + c.wq[s];
@@ -1305,6 +1410,13 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 u32 nd = 0xFFFFu;
                 if (c.vid[i] >= 0) nd = (u32) (__ldg(S.route_seq + c.rpos[i] + 1) & 0xFFFF);
                 c.dn[i] = (u32) drv16[i] | (nd << 16);
+            }
+        }
+        if (!GMEM && Y.prefetch_next) {   // this block's next replica: pull its image into L2 while this one is stepped
+            const int nb = b + gridDim.x;
+            if (nb < a.B) {
+                const unsigned char *nimg = images + (size_t) nb * Y.img_bytes;
+                for (int o = tid * 128; o < Y.img_bytes; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nimg + o));
             }
         }
         block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
@@ -1328,7 +1440,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         }
         __syncthreads();
         pt_mark(c, PT_PROLOGUE);
-        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT, STAGED>(S, Y, c, is_spawn_lane);
+        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT, STAGED, ONE_T>(S, Y, c, is_spawn_lane);
         if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
         pt_mark(c, PT_RETRIEVE);
 
@@ -1382,11 +1494,15 @@ static int fail(int code, const char *fmt, ...) {
 // that, register-staged when even one copy of the identity columns is too much; one 1024-thread block
 // per SM over a global-memory workspace for replicas that do not fit shared memory at all.
 typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
-static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged) {
-    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true>;
-    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true, false> : tsc_step_kernel<512, 1, true, false, false>;
-    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false> : tsc_step_kernel<256, 2, true, false, false>;
-    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false> : tsc_step_kernel<256, 2, false, false, false>;
+static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged, bool one_t) {
+    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true, false>;
+    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true, false, false> : tsc_step_kernel<512, 1, true, false, false, false>;
+    if (one_t) {
+        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true> : tsc_step_kernel<256, 2, true, false, false, true>;
+        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true> : tsc_step_kernel<256, 2, false, false, false, true>;
+    }
+    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, false> : tsc_step_kernel<256, 2, true, false, false, false>;
+    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, false> : tsc_step_kernel<256, 2, false, false, false, false>;
 }
 
 #define MAX_HOST_CHUNKS 16
@@ -1410,7 +1526,9 @@ struct tsc_engine {
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
     unsigned char *workspace = nullptr;             // GMEM variant: grid working sets in global memory
     bool gmem = false;
-    cudaStream_t host_compute = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
+    cudaStream_t host_compute = nullptr, host_compute2 = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
+    int host_streams = 1;               // compute streams the chunks alternate on (TSC_B200_HOST_STREAMS=2: measured slower, 1.58 vs 1.53 ms per B=4096 step)
+    cudaEvent_t host_ev_actions = nullptr;
     cudaEvent_t host_ev[1 + MAX_HOST_CHUNKS] = {};
     int host_chunks = MAX_HOST_CHUNKS;   // upper bound on chunks per host step (TSC_B200_HOST_CHUNKS)
     bool host_zero_copy = false;        // TSC_B200_HOST_ZERO_COPY=1: kernel stores straight into mapped page-locked buffers
@@ -1438,6 +1556,7 @@ static int align16(int x) { return (x + 15) & ~15; }
 static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.Vcap = Vcap;
     Y.staged = staged;
+    Y.pair_cap = staged ? 0 : Vcap;      // the list lives in the idle copy of the ping-pong identity columns
     Y.ent_cap = Vcap / 2 < 64 ? 64 : (Vcap / 2 > 8192 ? 8192 : Vcap / 2);   // vehicles changing drivable in one tick
     int o = sizeof(RepHeader);
     Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
@@ -1457,7 +1576,7 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.o_pj = o; o = align16(o + Vcap);
     Y.img_bytes = o;
     // shared-memory-only part; npos/nspd/nrpos double as retrieve scratch: make sure they are large enough
-    int need_np = 2 * S.L, need_ns = 2 * S.A + 160;
+    int need_np = 3 * S.L, need_ns = 2 * S.A + 160;
     int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
     Y.o_dn = o; o = align16(o + 4 * Vcap);
     const int V2 = Y.staged ? 0 : Vcap;    // second copy of the identity columns: only for the ping-pong re-pack
@@ -1528,16 +1647,55 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     UP(nbr_off, A + 1) UP(nbr_idx, s->n_nbr_total) UP(nbr_weight, s->n_nbr_total)
     UP(ctl_off, A * s->max_phases + 1) UP(ctl_in_lane, s->n_ctl_total) UP(ctl_out_lane, s->n_ctl_total)
 #undef UP
+    {   // pytsc's lane length in vehicle cells (retriever.py:73), the same IEEE division the kernel used to repeat per lane
+        std::vector<double> cells(L > 0 ? L : 1, 1.0);
+        for (int l = 0; l < L; ++l) {
+            cells[l] = s->lane_pytsc_length[l] / s->veh_size_min_gap;
+            if (!(cells[l] > 0.0)) { tsc_destroy(E); return fail(TSC_EINVAL, "lane %d: pytsc length / veh_size_min_gap must be positive", l); }
+        }
+        if ((rc = upload(E, cells.data(), (size_t) L, &S.lane_cells))) { tsc_destroy(E); return rc; }
+    }
+    for (int k = 0; k < D; ++k)
+        if (!(s->drv_max_speed[k] > 0.0)) { tsc_destroy(E); return fail(TSC_EINVAL, "drivable %d: max speed must be positive", k); }
     S.reward_type = s->reward_type; S.obs_type = s->obs_type; S.action_space = s->action_space; S.round_robin = s->round_robin;
     S.visibility = s->visibility; S.yellow_time = s->yellow_time; S.obs_dim = s->obs_dim; S.state_dim = s->state_dim;
     S.n_actions = s->n_actions; S.reference_exact = s->reference_exact; S.max_lanes_per_signal = s->max_lanes_per_signal;
     S.max_obs_phases = s->max_obs_phases; S.v_size = s->veh_size_min_gap; S.flick = s->flickering_coef; S.interval = s->interval;
+    {   // lane-feature rows (observations.py:305-329): per incoming lane [9 static, n_queued, occupancy, mean_speed],
+        // -1 padding up to max_lanes_per_signal lanes, then the phase one-hot over max_obs_phases entries
+        const int per = 12, ML = S.max_lanes_per_signal, MP = S.max_obs_phases, row = ML * per + MP;
+        if (row != S.state_dim) { tsc_destroy(E); return fail(TSC_EINVAL, "state_dim %d != %d * 12 + %d", S.state_dim, ML, MP); }
+        if (S.obs_type == TSC_OBS_LANE_FEATURES && S.obs_dim != row) { tsc_destroy(E); return fail(TSC_EINVAL, "obs_dim %d != state_dim %d", S.obs_dim, row); }
+        if (A > 0xFFFFF || MP > 256) { tsc_destroy(E); return fail(TSC_EINVAL, "too many signals / phases for the observation recipe"); }
+        std::vector<u32> code((size_t) A * row > 0 ? (size_t) A * row : 1, 0u);
+        std::vector<float> sval(code.size(), 0.0f);
+        for (int sg = 0; sg < A; ++sg) {
+            const int i0 = s->sig_in_off[sg], nin = s->sig_in_off[sg + 1] - i0;
+            const bool tr = S.reference_exact && nin < ML;
+            for (int k = 0; k < row; ++k) {
+                const size_t at = (size_t) sg * row + k;
+                if (k < ML * per) {
+                    const int e = k / per, f = k - e * per;
+                    if (e >= nin) { sval[at] = -1.0f; continue; }
+                    const int l = s->sig_in_lane[i0 + e];
+                    if (f < 9) { double x = s->lane_feat[(size_t) l * 9 + f]; sval[at] = (float) (tr ? trunc(x) : x); }
+                    else code[at] = (u32) (f - 8) | (tr ? 8u : 0u) | ((u32) l << 4);
+                } else {
+                    const int ph = k - ML * per;
+                    if (ph < s->sig_n_phases[sg]) code[at] = 4u | ((u32) (sg << 8 | ph) << 4);
+                }
+            }
+        }
+        if ((rc = upload(E, code.data(), code.size(), &S.obs_code))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, sval.data(), sval.size(), &S.obs_static))) { tsc_destroy(E); return rc; }
+    }
     {   // vehicle templates, extended with the per-template constants of the car-following law
         std::vector<double> td((size_t) s->n_templates * TD_STRIDE, 0.0);
         for (int t = 0; t < s->n_templates; ++t) {
             const double *src = s->tmpl + (size_t) t * TSC_T_STRIDE;
             double *dst = td.data() + (size_t) t * TD_STRIDE;
             for (int k = 0; k < TSC_T_STRIDE; ++k) dst[k] = src[k];
+            if (!(src[TSC_T_MAX_NEG_ACC] > 0.0) || !(src[TSC_T_MAX_NEG_ACC] < 1e300)) { tsc_destroy(E); return fail(TSC_EINVAL, "template %d: maxNegAcc must be positive and finite", t); }
             const double a = 0.5 / src[TSC_T_MAX_NEG_ACC];
             dst[TD_A] = a;
             dst[TD_HALF_OVER_A] = 0.5 / a;
@@ -1577,6 +1735,12 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     for (int l = 0; l < L; ++l) if (s->lane_spawn_off[l + 1] > s->lane_spawn_off[l]) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
     S.n_spawn_lanes = E->n_spawn_lanes = (int) E->h_spawn_lane.size();
     if ((rc = upload(E, E->h_spawn_lane.data(), E->h_spawn_lane.size(), &S.spawn_lane))) { tsc_destroy(E); return rc; }
+    {
+        if (E->n_spawn_lanes > 32767) { tsc_destroy(E); return fail(TSC_EINVAL, "more than 32767 spawn lanes"); }
+        std::vector<short> idx(L > 0 ? L : 1, (short) -1);
+        for (int k = 0; k < E->n_spawn_lanes; ++k) idx[E->h_spawn_lane[k]] = (short) k;
+        if ((rc = upload(E, idx.data(), (size_t) L, &S.lane_spawn_idx))) { tsc_destroy(E); return rc; }
+    }
     { const u8 *p; if ((rc = upload(E, E->h_is_spawn.data(), (size_t) L, &p))) { tsc_destroy(E); return rc; } E->d_is_spawn_lane = (u8 *) p; }
     std::vector<int> ccnt(S.horizon + 2, 0);
     std::vector<long long> cent(S.horizon + 2, 0);
@@ -1599,6 +1763,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     // Pick the variant from what fits: 256-thread blocks (ping-pong re-pack) while >= 2 replicas fit an
     // SM; else one 512-thread block per SM; register-staged (13 bytes less per vehicle slot) only when
     // that is what makes the replica fit.  TSC_B200_THREADS / TSC_B200_STAGED / TSC_B200_MIN_BLOCKS override.
+    // (Two 512-thread blocks at 64 registers were measured too: 1.36 ms against 1.13 ms for three 256-thread blocks at 80.)
     int staged = 0;
     build_layout(E->Y, S, Vcap, 0);
     E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
@@ -1613,14 +1778,24 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         E->nt = 1024;
         build_layout(E->Y, S, Vcap, 0);
     }
+    {   // the flat cross phase packs a cross's position in its link into 8 bits
+        int max_cross = 0;
+        for (int k = 0; k < K; ++k) max_cross = std::max(max_cross, s->ll_cross_off[k + 1] - s->ll_cross_off[k]);
+        if (max_cross > 255) E->Y.pair_cap = 0;
+        if (const char *env = getenv("TSC_B200_FLAT_CROSS")) { if (atoi(env) == 0) E->Y.pair_cap = 0; }
+        E->Y.prefetch_next = 1;
+        if (const char *env = getenv("TSC_B200_PREFETCH")) E->Y.prefetch_next = atoi(env) != 0;
+    }
     // blocks per SM the shared-memory footprint allows decides the register budget (launch bounds variant);
     // measured on B200 (Hangzhou, B = 4096): 4 blocks x 64 registers loses to 3 blocks x 80 (1.41 vs 1.34 ms)
     E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
     if (E->minb < 1) E->minb = 1;
     if (E->minb > 3) E->minb = 3;
     if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
-    E->kern = kernel_for(E->nt, E->minb, false, staged != 0);
-    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0);
+    bool one_t = S.T == 1;
+    if (const char *env = getenv("TSC_B200_ONE_TEMPLATE")) one_t = one_t && atoi(env) != 0;
+    E->kern = kernel_for(E->nt, E->minb, false, staged != 0, one_t);
+    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0, one_t);
     const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;
     for (int k = 0; k < 2; ++k) {
         step_kernel_t kern = k ? E->kern_ctl : E->kern;
@@ -1663,7 +1838,10 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     CUDA_TRY(cudaMallocHost((void **) &E->h_rg, (size_t) n_replicas * sizeof(float)));
     CUDA_TRY(cudaMallocHost((void **) &E->h_mask, io * S.n_actions));
     CUDA_TRY(cudaStreamCreateWithFlags(&E->host_compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&E->host_compute2, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&E->host_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&E->host_ev_actions, cudaEventDisableTiming));
+    if (const char *env = getenv("TSC_B200_HOST_STREAMS")) { int v = atoi(env); if (v == 1 || v == 2) E->host_streams = v; }
     for (auto &ev : E->host_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *env = getenv("TSC_B200_HOST_CHUNKS")) { int v = atoi(env); if (v >= 1 && v <= MAX_HOST_CHUNKS) E->host_chunks = v; }
     if (const char *env = getenv("TSC_B200_HOST_ZERO_COPY")) E->host_zero_copy = atoi(env) != 0;
@@ -1681,7 +1859,9 @@ void tsc_destroy(tsc_handle E) {
     cudaFree(E->d_phase_cycles);
     cudaFree(E->workspace);
     if (E->host_compute) cudaStreamDestroy(E->host_compute);
+    if (E->host_compute2) cudaStreamDestroy(E->host_compute2);
     if (E->host_copy) cudaStreamDestroy(E->host_copy);
+    if (E->host_ev_actions) cudaEventDestroy(E->host_ev_actions);
     for (auto &ev : E->host_ev) if (ev) cudaEventDestroy(ev);
     cudaFree(E->images); cudaFree(E->d_actions); cudaFree(E->d_obs); cudaFree(E->d_reward); cudaFree(E->d_rg); cudaFree(E->d_mask);
     cudaFreeHost(E->h_actions); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_reward); cudaFreeHost(E->h_rg); cudaFreeHost(E->h_mask);
@@ -1822,7 +2002,7 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     // Replicas are independent, so the batch is cut into chunks: while chunk k+1 is being stepped on
     // the compute stream, chunk k's observations / rewards / masks travel to the host on the copy
     // stream.  Both streams are ordered after whatever the caller queued on the default stream.
-    cudaStream_t sc = E->host_compute, sd = E->host_copy;
+    cudaStream_t sc = E->host_compute, sc2 = E->host_streams > 1 ? E->host_compute2 : E->host_compute, sd = E->host_copy;
     CUDA_TRY(cudaEventRecord(E->host_ev[0], 0));
     CUDA_TRY(cudaStreamWaitEvent(sc, E->host_ev[0], 0));
     // page-locked caller buffers are used in place; pageable ones go through the handle's pinned staging
@@ -1867,13 +2047,18 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     int wpc = E->host_chunks > 0 ? (total_waves + E->host_chunks - 1) / E->host_chunks : 1;
     if (wpc < 1) wpc = 1;
     const int chunk = wpc * E->grid;
+    if (sc2 != sc) {   // the second compute stream starts after the actions have arrived
+        CUDA_TRY(cudaEventRecord(E->host_ev_actions, sc));
+        CUDA_TRY(cudaStreamWaitEvent(sc2, E->host_ev_actions, 0));
+    }
     int k = 0;
     for (int b0 = 0; b0 < E->B; b0 += chunk, ++k) {
         a.b0 = b0;
         a.B = b0 + chunk < E->B ? b0 + chunk : E->B;
-        int rc = launch(E, a, sc);
+        cudaStream_t st = (k & 1) ? sc2 : sc;
+        int rc = launch(E, a, st);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(E->host_ev[1 + k], sc));
+        CUDA_TRY(cudaEventRecord(E->host_ev[1 + k], st));
         CUDA_TRY(cudaStreamWaitEvent(sd, E->host_ev[1 + k], 0));
         const bool last = a.B == E->B;
         for (int o = 0; o < 4; ++o) {
@@ -1888,6 +2073,7 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     }
     CUDA_TRY(cudaStreamSynchronize(sd));
     CUDA_TRY(cudaStreamSynchronize(sc));
+    if (sc2 != sc) CUDA_TRY(cudaStreamSynchronize(sc2));
     for (Out &x : outs) if (x.user && !x.direct) memcpy(x.user, x.stage, (size_t) E->B * x.row);
     return 0;
 }

@@ -80,7 +80,7 @@ def compare_snapshots(so, sg, tol=0.0):
 # ---- golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py) ----
 def golden_cases():
     """Step fixtures (random-over-mask actions); the closed-loop controller fixtures are ``controller_cases()``."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("ctl_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("ctl_", "trips_")))
 
 
 def controller_cases():

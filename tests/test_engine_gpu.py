@@ -83,3 +83,37 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
             assert compare_snapshots(e1.snapshot(0), e5.snapshot(1)) is None
     e1.check(); e5.check()
     e1.close(); e5.close()
+
+
+@pytest.mark.parametrize("env", [
+    {"TSC_B200_FLAT_CROSS": "0"},        # warp-per-vehicle cross phase (the fallback of the flat pair list)
+    {"TSC_B200_ONE_TEMPLATE": "0"},      # per-vehicle template look-up although the scenario has one template
+    {"TSC_B200_PREFETCH": "0"},
+])
+def test_kernel_variants_agree_with_oracle(cuda_lib, env, monkeypatch):
+    """The code paths an environment switch (or an unusual scenario) selects at tsc_create produce the
+    same trajectories: hangzhou_4_4 for 300 ticks in lock-step with the oracle, random light phases."""
+    import torch
+    from pytsc_b200.binding import Engine
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg, parser, cs = build_scenario("hangzhou_4_4")
+    orc = oracle_engine(cfg)
+    eng = Engine(cs, 2, 0, vehicle_capacity=1280)
+    inter = signal_inter_indices(parser)
+    rng = np.random.RandomState(7)
+    raw = np.ones((2, eng.A), np.int32)
+    for t in range(300):
+        if t % 5 == 0:
+            r = _phases("random", t, eng.A, cs.sig_n_raw_phases, rng)
+            raw[:] = r
+            eng.set_phase(torch.from_numpy(raw).cuda())
+            for a in range(eng.A):
+                orc.set_tl_phase_idx(inter[a], int(r[a]))
+        orc.next_step()
+        eng.step(1)
+        if t % 10 == 9:
+            msg = compare_snapshots(orc.snapshot(), eng.snapshot(1), POSITION_TOL_M)
+            assert msg is None, f"{env} tick {t}: {msg}"
+    eng.check()
+    eng.close()

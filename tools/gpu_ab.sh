@@ -10,7 +10,7 @@ for cfg in "$@"; do
 import json
 try:
     d=json.load(open("gpurun_out/ab$i.json"))
-    print("[$cfg]", "ms %.4f"%d["ms_per_step"], "e2e ms %.3f"%d["e2e"]["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["config"]["kernel"])
+    print("[$cfg]", "ms %.4f"%d["ms_per_step"], "e2e ms %.3f"%d["e2e"]["ms_per_step"], "policy ms %.3f"%d["e2e"].get("host_policy_ms_per_step",-1), "frac %.4f"%d["roofline"]["frac"], d["config"]["kernel"])
 except Exception as e:
     print("[$cfg] failed", e); print(open("gpurun_out/ab$i.err").read()[-1500:])
 PY
