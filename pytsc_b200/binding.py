@@ -51,7 +51,7 @@ def load_library(path=None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    path = path or LIB_PATH
+    path = path or os.environ.get("TSC_B200_LIB") or LIB_PATH      # TSC_B200_LIB: another build of the same ABI (A/B measurements)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: build it with `python -m pytsc_b200._build` "
                            "(the gpu backend has no CPU fallback)")

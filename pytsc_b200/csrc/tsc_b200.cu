@@ -115,7 +115,7 @@ struct Layout {
     int o_vid2, o_ellt2, o_pj2;
     int o_dn, o_dn2, o_xlist, o_avail, o_tmpl, o_spawn;
     int o_npos, o_nspd, o_nrpos, o_nblk, o_nflag, o_off, o_leave, o_ent, o_fresh, o_entlist,
-        o_entpos, o_entdrv, o_scan, o_lane_q, smem_bytes;
+        o_entpos, o_entdrv, o_scan, o_cold, o_img_cold, hybrid_smem_bytes, smem_bytes;
 };
 
 struct StepArgs {
@@ -241,7 +241,7 @@ __device__ double stop_before_speed(const double *T, double v, double distance) 
 }
 
 __device__ __forceinline__ bool can_yield(const double *T, double v, double dist) {
-    double minBrake = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC];
+    double minBrake = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC];      // (div_pos here was measured: 1 % slower)
     return (dist > 0 && minBrake < dist - T[TSC_T_YIELD_DIST]) || (dist < 0 && dist + T[TSC_T_LEN] < 0);
 }
 
@@ -618,7 +618,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 const int2 cr = __ldg((const int2 *) &S.llinfo[ll].cross_off);
                 const int nc = cr.y - cr.x;
                 u32 *pairs = c.dn2;
-                ((u32 *) c.ellt2)[e] = 0xFFFFFFFFu;
+                ((u32 *) c.vid2)[e] = 0xFFFFFFFFu;
                 const int p0 = atomicAdd(&c.h->n_pairs, nc);
                 if (p0 + nc <= Y.pair_cap)
                     for (int k = 0; k < nc; ++k) pairs[p0 + k] = ((u32) e << 8) | (u32) k;
@@ -643,7 +643,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     if (!STAGED && Y.pair_cap > 0 && c.h->n_pairs <= Y.pair_cap) {
         const int n_pairs = c.h->n_pairs;
         const u32 *pairs = c.dn2;
-        u32 *first_refusal = (u32 *) c.ellt2;
+        u32 *first_refusal = (u32 *) c.vid2;
         for (int p = tid; p < n_pairs; p += NT) {
             const u32 pr = pairs[p];
             const int e = (int) (pr >> 8), k = (int) (pr & 0xFFu);
@@ -1109,9 +1109,9 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     double *l_occ = c.npos;              // [L]
     double *l_ms = c.npos + L;           // [L]
     double *l_nms = c.npos + 2 * L;      // [L] mean speed / lane speed limit (metrics.py:113-135, traffic_signal.py:118)
-    int *l_q = (int *) (smem + Y.o_lane_q);   // [L]
     double *s_loc = c.nspd;              // [A] local reward term
     double *s_prs = c.nspd + A;          // [A] pressure
+    int *l_q = (int *) (c.nspd + 2 * A); // [L]
 
     // --- Retriever._compute_lane_measurements (retriever.py:54-85) ---
     for (int l = tid; l < L; l += NT) {
@@ -1344,11 +1344,15 @@ __device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, in
 // hot path 2-3 % through register allocation alone).  STAGED: register-staged re-pack (see engine_tick).
 // GMEM: the replica's working set does not fit an SM's shared memory (a 16 x 16 grid needs ~1 MB): the
 // block works out of a global-memory workspace instead -- same layout, same code, L2-resident.
-template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM, bool ONE_T>
+template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM, bool ONE_T, bool HYB>
 __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
                                                       const u8 *is_spawn_lane, const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_block[];
     unsigned char *const smem = GMEM ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes + 255) & ~255) : smem_block;
+    // HYB: the cold buffers (D) live in this block's global workspace, the cold image column (B) stays
+    // in the image, and the shared-memory-only hot arrays (C) move down over the room (B) would have taken
+    unsigned char *const hot = HYB ? smem - (Y.img_bytes - Y.o_img_cold) : smem;
+    unsigned char *const cold = HYB ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes - Y.o_cold + 255) & ~255) - Y.o_cold : smem;
     const int tid = threadIdx.x;
     Ctx c;
     c.h = (RepHeader *) smem;
@@ -1357,16 +1361,16 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd);
     c.rpos = (int *) (smem + Y.o_rpos); c.blk = (short *) (smem + Y.o_blk);
     c.newslot = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
-    c.npos = (double *) (smem + Y.o_npos); c.nspd = (double *) (smem + Y.o_nspd); c.nrpos = (int *) (smem + Y.o_nrpos);
-    c.nblk = (short *) (smem + Y.o_nblk); c.nflag = smem + Y.o_nflag; c.xlist = (u16 *) (smem + Y.o_xlist);
-    c.off = (u16 *) (smem + Y.o_off); c.leave = (u16 *) (smem + Y.o_leave); c.ent = (u16 *) (smem + Y.o_ent);
-    c.fresh = smem + Y.o_fresh; c.entlist = (u16 *) (smem + Y.o_entlist); c.entpos = (double *) (smem + Y.o_entpos);
-    c.entdrv = (u16 *) (smem + Y.o_entdrv); c.scan = (int *) (smem + Y.o_scan);
-    c.avail = (u32 *) (smem + Y.o_avail);
-    c.sp_lane = (int *) (smem + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
+    c.npos = (double *) (hot + Y.o_npos); c.nspd = (double *) (hot + Y.o_nspd); c.nrpos = (int *) (cold + Y.o_nrpos);
+    c.nblk = (short *) (hot + Y.o_nblk); c.nflag = hot + Y.o_nflag; c.xlist = (u16 *) (hot + Y.o_xlist);
+    c.off = (u16 *) (hot + Y.o_off); c.leave = (u16 *) (hot + Y.o_leave); c.ent = (u16 *) (hot + Y.o_ent);
+    c.fresh = hot + Y.o_fresh; c.entlist = (u16 *) (hot + Y.o_entlist); c.entpos = (double *) (hot + Y.o_entpos);
+    c.entdrv = (u16 *) (hot + Y.o_entdrv); c.scan = (int *) (hot + Y.o_scan);
+    c.avail = (u32 *) (hot + Y.o_avail);
+    c.sp_lane = (int *) (hot + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
     for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
     if (ONE_T || S.T <= SMEM_TEMPLATES) {
-        double *ts = (double *) (smem + Y.o_tmpl);
+        double *ts = (double *) (hot + Y.o_tmpl);
         for (int k = tid; k < S.T * TD_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
     } else c.tmpl = S.tmpl;
@@ -1376,8 +1380,9 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     for (int b = a.b0 + blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
         // the identity fields ping-pong between two buffers every tick: start from the primary ones
-        c.vid = (int *) (smem + Y.o_vid); c.ellt = (int *) (smem + Y.o_ellt); c.dn = (u32 *) (smem + Y.o_dn); c.pj = smem + Y.o_pj;
-        c.vid2 = (int *) (smem + Y.o_vid2); c.ellt2 = (int *) (smem + Y.o_ellt2); c.dn2 = (u32 *) (smem + Y.o_dn2); c.pj2 = smem + Y.o_pj2;
+        c.vid = (int *) (smem + Y.o_vid); c.dn = (u32 *) (hot + Y.o_dn); c.pj = smem + Y.o_pj;
+        c.vid2 = (int *) (hot + Y.o_vid2); c.dn2 = (u32 *) (hot + Y.o_dn2); c.pj2 = hot + Y.o_pj2;
+        c.ellt = (int *) ((HYB ? img : smem) + Y.o_ellt); c.ellt2 = (int *) (cold + Y.o_ellt2);
         // ---- stage the replica image into shared memory ----
         copy16(smem, img, Y.o_meta_end, tid, NT);
         __syncthreads();
@@ -1388,7 +1393,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             copy16(smem + Y.o_spd, img + Y.o_spd, n8, tid, NT);
             copy16(smem + Y.o_rpos, img + Y.o_rpos, n4, tid, NT);
             copy16(smem + Y.o_vid, img + Y.o_vid, n4, tid, NT);
-            copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
+            if (!HYB) copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
             copy16(smem + Y.o_blk, img + Y.o_blk, n2, tid, NT);
             copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
         }
@@ -1454,7 +1459,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 copy16(img + Y.o_spd, smem + Y.o_spd, n8, tid, NT);
                 copy16(img + Y.o_rpos, smem + Y.o_rpos, n4, tid, NT);
                 copy16(img + Y.o_vid, c.vid, n4, tid, NT);
-                copy16(img + Y.o_ellt, c.ellt, n4, tid, NT);
+                if ((unsigned char *) c.ellt != img + Y.o_ellt) copy16(img + Y.o_ellt, c.ellt, n4, tid, NT);
                 copy16(img + Y.o_blk, smem + Y.o_blk, n2, tid, NT);
                 copy16(img + Y.o_pj, c.pj, n1, tid, NT);
                 u32 *drv_pairs = (u32 *) (img + Y.o_drv);     // two u16 drivables per 32-bit store
@@ -1494,15 +1499,19 @@ static int fail(int code, const char *fmt, ...) {
 // that, register-staged when even one copy of the identity columns is too much; one 1024-thread block
 // per SM over a global-memory workspace for replicas that do not fit shared memory at all.
 typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
-static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged, bool one_t) {
-    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true, false>;
-    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true, false, false> : tsc_step_kernel<512, 1, true, false, false, false>;
+static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged, bool one_t, bool hybrid) {
+    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true, false, false>;
+    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true, false, false, false> : tsc_step_kernel<512, 1, true, false, false, false, false>;
+    if (nt == 192 && one_t && hybrid)   // four 192-thread blocks per SM (80 registers), cold buffers in the global workspace
+        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, true> : tsc_step_kernel<192, 4, false, false, false, true, true>;
+    if (nt == 192 && one_t)             // the same with everything in shared memory (working set below 56 KB)
+        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, false> : tsc_step_kernel<192, 4, false, false, false, true, false>;
     if (one_t) {
-        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true> : tsc_step_kernel<256, 2, true, false, false, true>;
-        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true> : tsc_step_kernel<256, 2, false, false, false, true>;
+        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true, false> : tsc_step_kernel<256, 2, true, false, false, true, false>;
+        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true, false> : tsc_step_kernel<256, 2, false, false, false, true, false>;
     }
-    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, false> : tsc_step_kernel<256, 2, true, false, false, false>;
-    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, false> : tsc_step_kernel<256, 2, false, false, false, false>;
+    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, false, false> : tsc_step_kernel<256, 2, true, false, false, false, false>;
+    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, false, false> : tsc_step_kernel<256, 2, false, false, false, false, false>;
 }
 
 #define MAX_HOST_CHUNKS 16
@@ -1525,7 +1534,8 @@ struct tsc_engine {
     int64_t launches = 0;
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
     unsigned char *workspace = nullptr;             // GMEM variant: grid working sets in global memory
-    bool gmem = false;
+    bool gmem = false, hybrid = false;
+    int dyn_smem = 0;                               // dynamic shared memory per block of the chosen variant
     cudaStream_t host_compute = nullptr, host_compute2 = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
     int host_streams = 1;               // compute streams the chunks alternate on (TSC_B200_HOST_STREAMS=2: measured slower, 1.58 vs 1.53 ms per B=4096 step)
     cudaEvent_t host_ev_actions = nullptr;
@@ -1557,7 +1567,11 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.Vcap = Vcap;
     Y.staged = staged;
     Y.pair_cap = staged ? 0 : Vcap;      // the list lives in the idle copy of the ping-pong identity columns
-    Y.ent_cap = Vcap / 2 < 64 ? 64 : (Vcap / 2 > 8192 ? 8192 : Vcap / 2);   // vehicles changing drivable in one tick
+    // vehicles changing drivable in one tick (a lane hands over at most one or two per tick; the shipped
+    // workloads stay far below a tenth of the running vehicles): a quarter of the slots, overflow is
+    // reported (ERR_ENT_OVERFLOW)
+    Y.ent_cap = Vcap / 4 < 64 ? 64 : (Vcap / 4 > 8192 ? 8192 : Vcap / 4);
+    // ---- (A) replica image, hot part: same byte offsets in HBM and in shared memory
     int o = sizeof(RepHeader);
     Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
     Y.o_wq = o; o = align16(o + 2 * (S.n_spawn_lanes + 1));
@@ -1570,26 +1584,21 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.o_spd = o; o = align16(o + 8 * Vcap);
     Y.o_rpos = o; o = align16(o + 4 * Vcap);
     Y.o_vid = o; o = align16(o + 4 * Vcap);
-    Y.o_ellt = o; o = align16(o + 4 * Vcap);
-    Y.o_blk = o; o = align16(o + 2 * Vcap);
     Y.o_drv = o; o = align16(o + 2 * Vcap);     // HBM: u16 drivable; shared memory: the newslot scratch
     Y.o_pj = o; o = align16(o + Vcap);
+    Y.o_blk = o; o = align16(o + 2 * Vcap);
+    // ---- (B) replica image, cold part (enterLaneLinkTime: read by canPass tie-breaks only): the hybrid
+    //      variant leaves this column in the image and works on it in place
+    Y.o_img_cold = o;
+    Y.o_ellt = o; o = align16(o + 4 * Vcap);
     Y.img_bytes = o;
-    // shared-memory-only part; npos/nspd/nrpos double as retrieve scratch: make sure they are large enough
-    int need_np = 3 * S.L, need_ns = 2 * S.A + 160;
-    int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
+    // ---- (C) shared-memory-only hot arrays (the hybrid variant places them right after (A))
     Y.o_dn = o; o = align16(o + 4 * Vcap);
     const int V2 = Y.staged ? 0 : Vcap;    // second copy of the identity columns: only for the ping-pong re-pack
     Y.o_dn2 = o; o = align16(o + 4 * V2);
     Y.o_vid2 = o; o = align16(o + 4 * V2);
-    Y.o_ellt2 = o; o = align16(o + 4 * V2);
     Y.o_pj2 = o; o = align16(o + V2);
-    Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
-    Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
-    Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
-    Y.o_nblk = o; o = align16(o + 2 * Vcap);
     Y.o_xlist = o; o = align16(o + 2 * Vcap);
-    Y.o_nflag = o; o = align16(o + Vcap);
     Y.o_off = o; o = align16(o + 2 * (S.D + 2));
     Y.o_leave = o; o = align16(o + 2 * (S.D + 2));
     Y.o_ent = o; o = align16(o + 2 * (S.D + 2));
@@ -1598,11 +1607,25 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     Y.o_entdrv = o; o = align16(o + 2 * Y.ent_cap);
     Y.o_entpos = o; o = align16(o + 8 * Y.ent_cap);
     Y.o_scan = o; o = align16(o + 4 * 64 + 2 * (S.D + 2));
-    Y.o_lane_q = o; o = align16(o + 4 * S.L);
     Y.o_avail = o; o = align16(o + 4 * ((S.K + 31) / 32 + 1));
-    Y.o_tmpl = o; o = align16(o + 8 * TD_STRIDE * SMEM_TEMPLATES);
+    Y.o_tmpl = o; o = align16(o + 8 * TD_STRIDE * (S.T < SMEM_TEMPLATES ? S.T : SMEM_TEMPLATES));
     Y.o_spawn = o; o = align16(o + 12 * (S.n_spawn_lanes + 1));
+    // the tick's decision buffers; npos / nspd / nrpos double as retrieve scratch: make sure they are large enough
+    int need_np = 3 * S.L, need_ns = 2 * S.A + (S.L + 1) / 2 + 2;
+    int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
+    Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
+    Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
+    Y.o_nblk = o; o = align16(o + 2 * Vcap);
+    Y.o_nflag = o; o = align16(o + Vcap);
+    // ---- (D) the new route cursors and the idle copy of the cold column: written once and read once per
+    //      vehicle per tick, in slot order.  The hybrid variant keeps them in a per-block global-memory
+    //      workspace (L2-resident) so that one more replica fits an SM's shared memory (12 bytes per slot
+    //      with (B); moving the other decision buffers out as well was measured: slower).
+    Y.o_cold = o;
+    Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
+    Y.o_ellt2 = o; o = align16(o + 4 * V2);
     Y.smem_bytes = o;
+    Y.hybrid_smem_bytes = Y.o_cold - (Y.img_bytes - Y.o_img_cold);      // (A) + (C)
 }
 
 extern "C" {
@@ -1756,7 +1779,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     E->h_veh_seq_start.assign(s->veh_seq_start, s->veh_seq_start + N);
 
     int Vcap = vehicle_capacity > 0 ? vehicle_capacity : 1024;
-    Vcap = (Vcap + E->n_spawn_lanes + 31) & ~31;
+    Vcap = (Vcap + E->n_spawn_lanes + 7) & ~7;
     if (Vcap > 32767) { tsc_destroy(E); return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1790,13 +1813,26 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     // measured on B200 (Hangzhou, B = 4096): 4 blocks x 64 registers loses to 3 blocks x 80 (1.41 vs 1.34 ms)
     E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
     if (E->minb < 1) E->minb = 1;
-    if (E->minb > 3) E->minb = 3;
-    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
     bool one_t = S.T == 1;
     if (const char *env = getenv("TSC_B200_ONE_TEMPLATE")) one_t = one_t && atoi(env) != 0;
-    E->kern = kernel_for(E->nt, E->minb, false, staged != 0, one_t);
-    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0, one_t);
-    const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;
+    // Four 192-thread blocks per SM beat three 256-thread ones (1.00 vs 1.14 ms on the bench workload): taken
+    // whenever the working set allows it -- all of it in shared memory if that fits four times, else with the
+    // cold buffers in a global workspace (hybrid).  TSC_B200_THREADS=256 / TSC_B200_HYBRID=0 opt out.
+    bool small = one_t && !E->gmem && !staged && E->nt == 256;
+    if (const char *env = getenv("TSC_B200_THREADS")) small = small && atoi(env) == 192;
+    const size_t per_sm = prop.sharedMemPerMultiprocessor;
+    const bool four_plain = small && per_sm / (size_t) (E->Y.smem_bytes + 1024) >= 4;
+    bool hybrid = small && !four_plain && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4;
+    if (const char *env = getenv("TSC_B200_HYBRID")) { int v = atoi(env); hybrid = v == 0 ? false : (small && (v == 2 || hybrid) && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4); }
+    const bool four_blocks = hybrid || four_plain;
+    if (E->minb > 3) E->minb = 3;
+    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
+    if (four_blocks) { E->nt = 192; E->minb = 4; }
+    E->hybrid = hybrid;
+    E->kern = kernel_for(E->nt, E->minb, false, staged != 0, one_t, hybrid);
+    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0, one_t, hybrid);
+    const int dyn_smem = E->gmem ? 0 : (hybrid ? E->Y.hybrid_smem_bytes : E->Y.smem_bytes);
+    E->dyn_smem = dyn_smem;
     for (int k = 0; k < 2; ++k) {
         step_kernel_t kern = k ? E->kern_ctl : E->kern;
         if (dyn_smem) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
@@ -1811,9 +1847,10 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     CUDA_TRY(cudaFuncGetAttributes(&fa, E->kern));
     E->regs = fa.numRegs;
 
-    if (E->gmem) {
+    if (E->gmem || E->hybrid) {
         const int g = E->grid > E->grid_ctl ? E->grid : E->grid_ctl;
-        CUDA_TRY(cudaMalloc((void **) &E->workspace, (size_t) g * (size_t) ((E->Y.smem_bytes + 255) & ~255)));
+        const size_t per_block = E->gmem ? (size_t) ((E->Y.smem_bytes + 255) & ~255) : (size_t) ((E->Y.smem_bytes - E->Y.o_cold + 255) & ~255);
+        CUDA_TRY(cudaMalloc((void **) &E->workspace, (size_t) g * per_block));
     }
     CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) n_replicas * E->Y.img_bytes));
     // tick-0 image: empty network, one spare slot per spawn lane
@@ -1905,7 +1942,7 @@ static int launch(tsc_handle E, const StepArgs &a, void *stream) {
     int grid = ctl ? E->grid_ctl : E->grid;
     if (grid > a.B - a.b0) grid = a.B - a.b0;
     if (grid <= 0) return 0;
-    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->gmem ? 0 : E->Y.smem_bytes, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->dyn_smem, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
     E->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -2201,7 +2238,7 @@ int tsc_debug_timing(tsc_handle E, int32_t enable, uint64_t *cycles_out, int32_t
 
 int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t *grid, int32_t *regs) {
     if (!E) return fail(TSC_EINVAL, "null handle");
-    if (smem_bytes) *smem_bytes = E->Y.smem_bytes;
+    if (smem_bytes) *smem_bytes = E->gmem ? E->Y.smem_bytes : E->dyn_smem;
     if (threads) *threads = E->nt;
     if (grid) *grid = E->grid;
     if (regs) *regs = E->regs;
@@ -2211,7 +2248,7 @@ int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t
 int tsc_kernel_variant(tsc_handle E, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm) {
     if (!E) return fail(TSC_EINVAL, "null handle");
     if (staged) *staged = E->Y.staged;
-    if (global_workspace) *global_workspace = E->gmem ? 1 : 0;
+    if (global_workspace) *global_workspace = E->gmem ? 1 : (E->hybrid ? 2 : 0);      // 2: decision buffers only
     if (blocks_per_sm) *blocks_per_sm = E->minb;
     return 0;
 }

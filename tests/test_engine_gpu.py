@@ -85,21 +85,28 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     e1.close(); e5.close()
 
 
-@pytest.mark.parametrize("env", [
-    {"TSC_B200_FLAT_CROSS": "0"},        # warp-per-vehicle cross phase (the fallback of the flat pair list)
-    {"TSC_B200_ONE_TEMPLATE": "0"},      # per-vehicle template look-up although the scenario has one template
-    {"TSC_B200_PREFETCH": "0"},
+@pytest.mark.parametrize("env,capacity,variant", [
+    ({}, 600, (192, 2)),                                 # default at this size: four blocks per SM, cold buffers in the global workspace
+    ({}, 520, (192, 0)),                                 # small enough for four blocks with everything in shared memory
+    ({"TSC_B200_HYBRID": "2"}, 520, (192, 2)),
+    ({"TSC_B200_THREADS": "256"}, 600, (256, 0)),        # three 256-thread blocks per SM
+    ({"TSC_B200_FLAT_CROSS": "0"}, 600, (192, 2)),       # warp-per-vehicle cross phase (the fallback of the flat pair list)
+    ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0)),     # per-vehicle template look-up although the scenario has one template
+    ({"TSC_B200_PREFETCH": "0"}, 600, (192, 2)),
+    ({"TSC_B200_HYBRID": "0"}, 600, (256, 0)),
 ])
-def test_kernel_variants_agree_with_oracle(cuda_lib, env, monkeypatch):
+def test_kernel_variants_agree_with_oracle(cuda_lib, env, capacity, variant, monkeypatch):
     """The code paths an environment switch (or an unusual scenario) selects at tsc_create produce the
     same trajectories: hangzhou_4_4 for 300 ticks in lock-step with the oracle, random light phases."""
     import torch
     from pytsc_b200.binding import Engine
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    cfg, parser, cs = build_scenario("hangzhou_4_4")
+    cfg, parser, cs = build_scenario("hangzhou_4_4", signal=dict(observation_space="lane_features"))
     orc = oracle_engine(cfg)
-    eng = Engine(cs, 2, 0, vehicle_capacity=1280)
+    eng = Engine(cs, 2, 0, vehicle_capacity=capacity)
+    info = eng.kernel_info()
+    assert (info["threads"], info["global_workspace"]) == variant, info
     inter = signal_inter_indices(parser)
     rng = np.random.RandomState(7)
     raw = np.ones((2, eng.A), np.int32)
