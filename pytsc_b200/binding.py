@@ -248,7 +248,7 @@ class Engine:
         return out
 
     PHASES = ("stage_in", "prologue", "spawn", "phase1a", "phase1b", "phase1c", "phase2", "count_scan", "newslot", "scatter",
-              "retrieve", "stage_out", "n_heads", "n_zone", "n_cross")
+              "retrieve", "stage_out", "n_heads", "n_zone", "n_cross", "n_pairs")
 
     def debug_timing(self, enable=True):
         """Read the per-phase cycle counters accumulated so far (dict), then enable / disable them."""

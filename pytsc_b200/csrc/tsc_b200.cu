@@ -106,6 +106,7 @@ static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 struct Layout {
     int Vcap, ent_cap;
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
+    int cross_group;       // lanes per vehicle in the per-vehicle cross phase: 32, 16 or 8
     int pair_cap;          // (vehicle, cross) pairs the flat cross phase can list (0: warp-per-vehicle phase only)
     int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
     // persistent part: identical byte offsets in the HBM image and in shared memory
@@ -172,7 +173,7 @@ struct Ctx {
 
 // phase ids of the debug timing
 enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1A, PT_PHASE1, PT_PHASE1C, PT_PHASE2, PT_COUNT_SCAN, PT_NEWSLOT, PT_SCATTER, PT_RETRIEVE,
-       PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_N };
+       PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_NPAIR, PT_N };
 __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
     if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
 }
@@ -450,54 +451,52 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         return;
     }
 
-    // ---- one pass over the drivables: handleWaiting (at most one vehicle per lane leaves its waiting
-    //      buffer; the head of every buffer -- lane, vehicle, creation tick -- is cached in shared memory,
-    //      so a tick without an arrival costs one compare per spawn lane), the move counters are reset,
-    //      and the non-empty drivables are listed for sub-phase 1a.
+    // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer.  The head of every
+    //      buffer (lane, vehicle, creation tick) is cached in shared memory, so a tick without an arrival
+    //      costs one compare per spawn lane.  The move counters were reset and the non-empty drivables
+    //      listed for sub-phase 1a when the previous tick (or the launch prologue) finished: a lane that
+    //      receives its only vehicle here adds itself.
     //      getAction is split so that every sub-phase runs the same code in all its lanes:
     //      1a  head vehicles (one per non-empty drivable): look-ahead leader + gap
     //      1b  every vehicle: car following; vehicles in an intersection zone go on a list
     //      1c  listed vehicles: red light / blocked exit / turn speed; those that must examine
     //          the crosses of a lane-link go on a second list
-    //      2   one warp per vehicle of the second list, one lane per cross ----
+    //      2   a group of lanes per vehicle of the second list, one lane per cross ----
     u16 *hlist = c.xlist;      // dead before 1c fills xlist
     u16 *alist = c.newslot;    // dead before the new slots are computed
-    for (int l = tid; l < D; l += NT) {
-        c.leave[l] = 0; c.ent[l] = 0;
-        int n = c.cnt[l];
-        const int s = l < L ? (int) __ldg(S.lane_spawn_idx + l) : -1;
-        if (s >= 0) {
-            u8 fr = 0;
-            if (c.sp_tick[s] <= tick) {
-                const int v = c.sp_vid[s];
-                bool ok = true;
-                if (n > 0) {
-                    int t = c.off[l] + n - 1;
-                    ok = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, v)[TSC_T_MIN_GAP];
-                }
-                if (ok) {
-                    int slot = c.off[l] + n;
-                    int rp0 = __ldg(S.veh_seq_start + v);
-                    c.pos[slot] = 0.0; c.spd[slot] = 0.0;
-                    c.rpos[slot] = rp0;
-                    c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
-                    c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
-                    c.pj[slot] = 0;
-                    c.cnt[l] = (u16) (++n);
-                    const int hd = c.wq[s] + 1;
-                    c.wq[s] = (u16) hd;
-                    const int at = __ldg(S.lane_spawn_off + l) + hd;
-                    if (at < __ldg(S.lane_spawn_off + l + 1)) {
-                        const int nv = __ldg(S.lane_spawn_vid + at);
-                        c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
-                    } else c.sp_tick[s] = INT_MAX;
-                    fr = 1;
-                    atomicAdd(&c.h->n_running, 1);
-                }
+    for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+        const int l = c.sp_lane[s];
+        u8 fr = 0;
+        if (c.sp_tick[s] <= tick) {
+            const int v = c.sp_vid[s];
+            const int n = c.cnt[l];
+            bool ok = true;
+            if (n > 0) {
+                int t = c.off[l] + n - 1;
+                ok = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, v)[TSC_T_MIN_GAP];
             }
-            c.fresh[l] = fr;
+            if (ok) {
+                int slot = c.off[l] + n;
+                int rp0 = __ldg(S.veh_seq_start + v);
+                c.pos[slot] = 0.0; c.spd[slot] = 0.0;
+                c.rpos[slot] = rp0;
+                c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
+                c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
+                c.pj[slot] = 0;
+                c.cnt[l] = (u16) (n + 1);
+                const int hd = c.wq[s] + 1;
+                c.wq[s] = (u16) hd;
+                const int at = __ldg(S.lane_spawn_off + l) + hd;
+                if (at < __ldg(S.lane_spawn_off + l + 1)) {
+                    const int nv = __ldg(S.lane_spawn_vid + at);
+                    c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
+                } else c.sp_tick[s] = INT_MAX;
+                fr = 1;
+                atomicAdd(&c.h->n_running, 1);
+                if (n == 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) l;
+            }
         }
-        if (n > 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) l;
+        c.fresh[l] = fr;
     }
     __syncthreads();
     pt_mark(c, PT_SPAWN);
@@ -545,6 +544,10 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         c.nblk[i] = (short) leader; c.npos[i] = gap;
     }
     __syncthreads();
+    if (tid == 0) {
+        if (c.pt) atomicAdd(c.pt + PT_NH, (unsigned long long) c.h->n_h);
+        c.h->n_h = 0;       // every thread has read it; the end of the tick lists the next tick's heads
+    }
     pt_mark(c, PT_PHASE1A);
 
     // 1b: next speed from acceleration, speed limits and the car-following law (A.4)
@@ -629,7 +632,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
     }
     __syncthreads();
-    if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); atomicAdd(c.pt + PT_NH, (unsigned long long) c.h->n_h); }
+    if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); atomicAdd(c.pt + PT_NPAIR, (unsigned long long) c.h->n_pairs); }
     pt_mark(c, PT_PHASE1C);
 
     // ---- getAction, phase 2: Cross::canPass for every cross ahead of every deferred vehicle.  canPass
@@ -687,8 +690,11 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
         }
     } else {
-        const int lane = tid & 31;
-        for (int e = tid >> 5; e < n_x; e += NT / 32) {
+        // a group of G lanes (a whole warp, or a half / quarter of one: links rarely have more than a dozen
+        // crosses) per vehicle, one lane per cross; groups of one warp work on different vehicles
+        const int G = Y.cross_group, lane = tid & 31, sl = lane & (G - 1);
+        const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
+        for (int e = tid / G; e < n_x; e += NT / G) {
             const int i = c.xlist[e];
             const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
             const u32 dnv = c.dn[i];
@@ -702,8 +708,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             const int t1 = __ldg(&S.llinfo[ll].type);
             double vi = c.npos[i], ns = c.nspd[i];
             int blocker = -1;
-            for (int base = head.z; base < head.w; base += 32) {
-                const int xi = base + lane;
+            for (int base = head.z; base < head.w; base += G) {
+                const int xi = base + sl;
                 bool refuse = false;
                 int foe = -1;
                 double dOn = 0.0;
@@ -715,18 +721,18 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                     dOn = X.dist;
                     if (!(dOn < dts)) refuse = !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe);
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, refuse);
+                const unsigned m = __ballot_sync(gm, refuse) & gm;
                 if (m) {
                     const int src_lane = __ffs(m) - 1;
-                    dOn = __shfl_sync(0xffffffffu, dOn, src_lane);
-                    foe = __shfl_sync(0xffffffffu, foe, src_lane);
+                    dOn = __shfl_sync(gm, dOn, src_lane);
+                    foe = __shfl_sync(gm, foe, src_lane);
                     vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST]));
                     blocker = foe;
                     break;
                 }
             }
             ns = min2(ns, vi);
-            if (lane == 0) finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
+            if (sl == 0) finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
         }
     }
     __syncthreads();
@@ -822,12 +828,12 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 r_dn[k] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
                 r_ellt[k] = dd >= L ? tick : INT_MAX;
                 r_pj[k] = (fl & 4) ? 1 : 0;
-            } else { r_dn[k] = c.dn[i]; r_ellt[k] = c.ellt[i]; r_pj[k] = c.pj[i]; }
+            } else { r_dn[k] = c.dn[i]; r_ellt[k] = (int) (r_dn[k] & 0xFFFF) >= L ? c.ellt[i] : INT_MAX; r_pj[k] = c.pj[i]; }
         }
         __syncthreads();
         for (int s = tid; s < S.n_spawn_lanes; s += NT) {
             int l = c.sp_lane[s];
-            c.vid[noff[l] + c.ent[l]] = -1;      // the lane's spare slot stays empty
+            c.vid[noff[l + 1] - 1] = -1;         // the lane's spare slot (the last of its range) stays empty
         }
 #pragma unroll
         for (int k = 0; k < SCATTER_PER; ++k) {
@@ -838,7 +844,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     } else {
         for (int s = tid; s < S.n_spawn_lanes; s += NT) {
             int l = c.sp_lane[s];
-            c.vid2[noff[l] + c.ent[l]] = -1;      // the lane's spare slot stays empty
+            c.vid2[noff[l + 1] - 1] = -1;        // the lane's spare slot (the last of its range) stays empty
         }
         for (int i = tid; i < n_slots; i += NT) {
             u16 dst = c.newslot[i];
@@ -856,7 +862,9 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 c.ellt2[dst] = dd >= L ? tick : INT_MAX;
                 c.pj2[dst] = (fl & 4) ? 1 : 0;
             } else {
-                c.dn2[dst] = c.dn[i]; c.ellt2[dst] = c.ellt[i]; c.pj2[dst] = c.pj[i];
+                // enterLaneLinkTime is INT_MAX on every lane: only vehicles staying on a lane-link read the (cold) column
+                const u32 dnv = c.dn[i];
+                c.dn2[dst] = dnv; c.ellt2[dst] = (int) (dnv & 0xFFFF) >= L ? c.ellt[i] : INT_MAX; c.pj2[dst] = c.pj[i];
             }
         }
         { int *t = c.vid; c.vid = c.vid2; c.vid2 = t; }
@@ -864,10 +872,16 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         { u32 *t = c.dn; c.dn = c.dn2; c.dn2 = t; }
         { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
     }
-    for (int d = tid; d < D; d += NT) { c.cnt[d] = c.ent[d]; c.off[d] = noff[d]; }
+    // new counts and offsets; move counters reset and non-empty drivables listed for the next tick
+    for (int d = tid; d < D; d += NT) {
+        const int n = c.ent[d];
+        c.cnt[d] = (u16) n; c.off[d] = noff[d];
+        c.leave[d] = 0; c.ent[d] = 0;
+        if (n > 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) d;
+    }
     if (tid == 0) {
         c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1;
-        c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_pairs = 0;      // scratch counters of the next tick
+        c.h->n_ent = 0; c.h->n_x = 0; c.h->n_a = 0; c.h->n_pairs = 0;      // scratch counters of the next tick
     }
     __syncthreads();
     pt_mark(c, PT_SCATTER);
@@ -1361,7 +1375,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd);
     c.rpos = (int *) (smem + Y.o_rpos); c.blk = (short *) (smem + Y.o_blk);
     c.newslot = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
-    c.npos = (double *) (hot + Y.o_npos); c.nspd = (double *) (hot + Y.o_nspd); c.nrpos = (int *) (cold + Y.o_nrpos);
+    c.npos = (double *) (hot + Y.o_npos); c.nspd = (double *) (hot + Y.o_nspd); c.nrpos = (int *) (hot + Y.o_nrpos);
     c.nblk = (short *) (hot + Y.o_nblk); c.nflag = hot + Y.o_nflag; c.xlist = (u16 *) (hot + Y.o_xlist);
     c.off = (u16 *) (hot + Y.o_off); c.leave = (u16 *) (hot + Y.o_leave); c.ent = (u16 *) (hot + Y.o_ent);
     c.fresh = hot + Y.o_fresh; c.entlist = (u16 *) (hot + Y.o_entlist); c.entpos = (double *) (hot + Y.o_entpos);
@@ -1425,6 +1439,10 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             }
         }
         block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
+        for (int d = tid; d < S.D; d += NT) {      // what the end of a tick leaves for the next one
+            c.leave[d] = 0; c.ent[d] = 0;
+            if (c.cnt[d] > 0) c.xlist[atomicAdd(&c.h->n_h, 1)] = (u16) d;
+        }
         pt_mark(c, PT_STAGE_IN);
 
         int *decided = (int *) c.nspd;       // free between ticks
@@ -1615,14 +1633,14 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
     Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
     Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
+    Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
     Y.o_nblk = o; o = align16(o + 2 * Vcap);
     Y.o_nflag = o; o = align16(o + Vcap);
-    // ---- (D) the new route cursors and the idle copy of the cold column: written once and read once per
-    //      vehicle per tick, in slot order.  The hybrid variant keeps them in a per-block global-memory
-    //      workspace (L2-resident) so that one more replica fits an SM's shared memory (12 bytes per slot
-    //      with (B); moving the other decision buffers out as well was measured: slower).
+    // ---- (D) the idle copy of the cold column.  The hybrid variant keeps it in a per-block global-memory
+    //      workspace (L2-resident) so that one more replica fits an SM's shared memory (8 bytes per slot
+    //      with (B)).  Moving decision buffers out as well was measured: the new route cursors cost 4 %,
+    //      all of them 20 %.
     Y.o_cold = o;
-    Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
     Y.o_ellt2 = o; o = align16(o + 4 * V2);
     Y.smem_bytes = o;
     Y.hybrid_smem_bytes = Y.o_cold - (Y.img_bytes - Y.o_img_cold);      // (A) + (C)
@@ -1805,7 +1823,12 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         int max_cross = 0;
         for (int k = 0; k < K; ++k) max_cross = std::max(max_cross, s->ll_cross_off[k + 1] - s->ll_cross_off[k]);
         if (max_cross > 255) E->Y.pair_cap = 0;
-        if (const char *env = getenv("TSC_B200_FLAT_CROSS")) { if (atoi(env) == 0) E->Y.pair_cap = 0; }
+        // measured on the bench workload (192 x 4): flat pair list 1.010 ms, groups of 32 / 16 / 8 lanes per
+        // vehicle 1.059 / 1.000 / 0.971 ms -> groups of 8 by default, TSC_B200_FLAT_CROSS=1 selects the pair list
+        const char *flat = getenv("TSC_B200_FLAT_CROSS");
+        if (!flat || atoi(flat) == 0) E->Y.pair_cap = 0;
+        E->Y.cross_group = 8;
+        if (const char *env = getenv("TSC_B200_CROSS_GROUP")) { int v = atoi(env); if (v == 4 || v == 8 || v == 16 || v == 32) E->Y.cross_group = v; }
         E->Y.prefetch_next = 1;
         if (const char *env = getenv("TSC_B200_PREFETCH")) E->Y.prefetch_next = atoi(env) != 0;
     }

@@ -90,7 +90,10 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({}, 520, (192, 0)),                                 # small enough for four blocks with everything in shared memory
     ({"TSC_B200_HYBRID": "2"}, 520, (192, 2)),
     ({"TSC_B200_THREADS": "256"}, 600, (256, 0)),        # three 256-thread blocks per SM
-    ({"TSC_B200_FLAT_CROSS": "0"}, 600, (192, 2)),       # warp-per-vehicle cross phase (the fallback of the flat pair list)
+    ({"TSC_B200_FLAT_CROSS": "1"}, 600, (192, 2)),       # flat (vehicle, cross) pair list instead of lane groups per vehicle
+    ({"TSC_B200_CROSS_GROUP": "32"}, 600, (192, 2)),     # a whole warp per vehicle in the cross phase
+    ({"TSC_B200_CROSS_GROUP": "16"}, 600, (192, 2)),
+    ({"TSC_B200_CROSS_GROUP": "4"}, 600, (192, 2)),
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0)),     # per-vehicle template look-up although the scenario has one template
     ({"TSC_B200_PREFETCH": "0"}, 600, (192, 2)),
     ({"TSC_B200_HYBRID": "0"}, 600, (256, 0)),
