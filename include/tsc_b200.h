@@ -202,6 +202,22 @@ int  tsc_get_dims(tsc_handle h, int32_t *n_replicas, int32_t *n_lanes, int32_t *
 /* All replicas back to tick 0, empty network, light phase 0, program state cleared. */
 int  tsc_reset(tsc_handle h, void *stream);
 
+/* Selected replicas back to tick 0 (as tsc_reset does for all of them), e.g. the replicas whose
+ * episode has ended while the others run on.  replicas: host int32 [n], indices in [0, B).  The
+ * caller re-applies tsc_init_program / phases as after tsc_reset.  Ordered on `stream`. */
+int  tsc_reset_replicas(tsc_handle h, const int32_t *replicas, int32_t n, void *stream);
+
+/* Engine state snapshot / restore -- the batched counterpart of CityFlow's engine.snapshot() /
+ * engine.load(archive) (cityflow.Engine API; pytsc's save_replay / mid-episode restarts).
+ * tsc_state_bytes: size of the opaque blob holding all B replicas (vehicles, waiting-buffer cursors,
+ * signal programs, travel-time sums, tick).  tsc_save_state / tsc_load_state copy it to / from `buf`,
+ * host or device memory of at least that size; ordered on `stream`, which is synchronised before
+ * returning.  A blob is valid for handles created from the same scenario with the same
+ * n_replicas and vehicle_capacity; tsc_load_state checks the header it wrote. */
+int64_t tsc_state_bytes(tsc_handle h);
+int  tsc_save_state(tsc_handle h, void *buf, int64_t buf_bytes, void *stream);
+int  tsc_load_state(tsc_handle h, const void *buf, int64_t buf_bytes, void *stream);
+
 /* raw_phase: device int32 [B][A] raw CityFlow light-phase index per signal. */
 int  tsc_set_phase(tsc_handle h, const int32_t *raw_phase, void *stream);
 
@@ -267,7 +283,7 @@ int64_t tsc_launch_count(tsc_handle h);
 /* Debug: per-phase clock64() sums seen by thread 0 of every block since timing was (re)enabled.
  * Copies up to n counters into cycles_out (may be NULL), then enables (zeroing) or disables the
  * instrumentation; returns the number of counters (stage-in, prologue, spawn, getAction 1a / 1b / 1c / 2,
- * count+scan, new slots, scatter, retrieve, stage-out, then three list-length sums).  Syncs.  Off by default (no overhead). */
+ * count+scan, new slots, scatter, retrieve, stage-out, then four list-length sums).  Syncs.  Off by default (no overhead). */
 int  tsc_debug_timing(tsc_handle h, int32_t enable, uint64_t *cycles_out, int32_t n);
 
 /* Name, bytes of dynamic shared memory, threads per block and grid of the step kernel. */
@@ -276,7 +292,8 @@ int  tsc_kernel_info(tsc_handle h, int32_t *smem_bytes, int32_t *threads, int32_
 /* Which variant of the step kernel the handle runs: staged = 1 when the per-tick re-pack stages the
  * identity columns in registers (large replicas that only fit shared memory that way);
  * global_workspace = 1 when the replica's working set does not fit shared memory at all and lives in a
- * global-memory (L2-resident) workspace; blocks_per_sm = launch-bounds variant. */
+ * global-memory (L2-resident) workspace, 2 when only the cold enterLaneLinkTime column does (hybrid:
+ * four replica blocks per SM); blocks_per_sm = launch-bounds variant. */
 int  tsc_kernel_variant(tsc_handle h, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm);
 
 #ifdef __cplusplus

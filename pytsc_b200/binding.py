@@ -22,7 +22,8 @@ ERRORS = {-1: "TSC_EINVAL", -2: "TSC_ECUDA", -3: "TSC_ENOMEM", -4: "TSC_EOVERFLO
 SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "tsc_get_dims", "tsc_reset",
            "tsc_set_phase", "tsc_init_program", "tsc_step", "tsc_retrieve", "tsc_env_step", "tsc_env_step_host",
            "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
-           "tsc_debug_timing", "tsc_controller_act", "tsc_kernel_variant")
+           "tsc_debug_timing", "tsc_controller_act", "tsc_kernel_variant", "tsc_reset_replicas", "tsc_state_bytes",
+           "tsc_save_state", "tsc_load_state")
 
 # tsc_env_step / tsc_controller_act controller codes (include/tsc_b200.h)
 CONTROLLERS = {"external": 0, "fixed_time": 1, "phase_index": 2, "greedy": 3, "max_pressure": 4, "sotl": 5, "random": 6}
@@ -64,6 +65,11 @@ def load_library(path=None):
     L.tsc_destroy.restype = None
     L.tsc_get_dims.argtypes = [vp] + [pi32] * 9
     L.tsc_reset.argtypes = [vp, vp]
+    L.tsc_reset_replicas.argtypes = [vp, vp, i32, vp]
+    L.tsc_state_bytes.argtypes = [vp]
+    L.tsc_state_bytes.restype = C.c_int64
+    L.tsc_save_state.argtypes = [vp, vp, C.c_int64, vp]
+    L.tsc_load_state.argtypes = [vp, vp, C.c_int64, vp]
     L.tsc_set_phase.argtypes = [vp, vp, vp]
     L.tsc_init_program.argtypes = [vp, i32, vp]
     L.tsc_step.argtypes = [vp, i32, vp]
@@ -175,6 +181,24 @@ class Engine:
     # ---- engine-level calls --------------------------------------------------------------
     def reset(self):
         self._check(self.lib.tsc_reset(self.h, self._stream()))
+
+    def reset_replicas(self, replicas):
+        """Selected replicas back to tick 0 (host list / array of replica indices)."""
+        idx = np.ascontiguousarray(np.asarray(replicas, np.int32).reshape(-1))
+        self._check(self.lib.tsc_reset_replicas(self.h, _np_ptr(idx), len(idx), self._stream()))
+
+    def save_state(self, device=False):
+        """Snapshot of all replicas (CityFlow's engine.snapshot()): a uint8 tensor, pinned host or device."""
+        n = int(self.lib.tsc_state_bytes(self.h))
+        buf = (self.torch.empty(n, dtype=self.torch.uint8, device="cuda") if device
+               else self.torch.empty(n, dtype=self.torch.uint8, pin_memory=True))
+        self._check(self.lib.tsc_save_state(self.h, _ptr(buf), n, self._stream()))
+        return buf
+
+    def load_state(self, blob):
+        """Restore a snapshot taken by ``save_state`` (CityFlow's engine.load(archive))."""
+        assert blob.dtype == self.torch.uint8 and blob.is_contiguous()
+        self._check(self.lib.tsc_load_state(self.h, _ptr(blob), blob.numel(), self._stream()))
 
     def set_phase(self, raw_phase):
         assert raw_phase.dtype == self.torch.int32 and tuple(raw_phase.shape) == (self.B, self.A)

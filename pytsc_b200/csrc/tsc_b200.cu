@@ -198,10 +198,16 @@ __device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, 
 
 // ---- A.4 car following -------------------------------------------------------
 // a = 0.5 / dF and 0.5 / a come from the follower's template row.
-// x / y for y > 0 finite: a zero numerator gives that zero back.  The division's exponent-range
-// check sends zero numerators to its out-of-line slow path (~60 instructions); standing vehicles
-// and empty lanes make them the common case.
-__device__ __forceinline__ double div_pos(double x, double y) { return x == 0.0 ? x : x / y; }
+// x / y for y > 0 finite, x >= 0.  The division's exponent-range check sends zero numerators to its
+// out-of-line slow path (~60 instructions), and standing vehicles / empty lanes make them the common
+// case.  A plain `x == 0 ? x : x / y` is if-converted by the compiler (the division, slow path
+// included, runs anyway and a select picks the result), so the zero is replaced by 1.0 before the
+// division and put back after it: the quotient of a zero numerator is that zero, bit for bit.
+__device__ __forceinline__ double div_pos(double x, double y) {
+    const bool zero = x == 0.0;
+    const double q = (zero ? 1.0 : x) / y;
+    return zero ? x : q;
+}
 
 // dL > 0 (a deceleration the caller knows to be positive: a template's maxNegAcc, or v - vL > 0)
 __device__ __forceinline__ double no_collision_speed(double vL, double dL, double vF, double a, double half_over_a, double gap,
@@ -242,7 +248,7 @@ __device__ double stop_before_speed(const double *T, double v, double distance) 
 }
 
 __device__ __forceinline__ bool can_yield(const double *T, double v, double dist) {
-    double minBrake = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC];      // (div_pos here was measured: 1 % slower)
+    double minBrake = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC];
     return (dist > 0 && minBrake < dist - T[TSC_T_YIELD_DIST]) || (dist < 0 && dist + T[TSC_T_LEN] < 0);
 }
 
@@ -1875,7 +1881,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         const size_t per_block = E->gmem ? (size_t) ((E->Y.smem_bytes + 255) & ~255) : (size_t) ((E->Y.smem_bytes - E->Y.o_cold + 255) & ~255);
         CUDA_TRY(cudaMalloc((void **) &E->workspace, (size_t) g * per_block));
     }
-    CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) n_replicas * E->Y.img_bytes));
+    CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) (n_replicas + 1) * E->Y.img_bytes));      // + the tick-0 image (tsc_reset_replicas)
     // tick-0 image: empty network, one spare slot per spawn lane
     E->init_image.assign(E->Y.img_bytes, 0);
     {
@@ -1948,6 +1954,7 @@ int tsc_reset(tsc_handle E, void *stream) {
     CUDA_TRY(cudaSetDevice(E->device));
     cudaStream_t st = (cudaStream_t) stream;
     // the initial image is tiny compared with B of them: upload once, then replicate on the device
+    CUDA_TRY(cudaMemcpyAsync(E->images + (size_t) E->B * E->Y.img_bytes, E->init_image.data(), E->Y.img_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(E->images, E->init_image.data(), E->Y.img_bytes, cudaMemcpyHostToDevice, st));
     size_t done = 1;
     while (done < (size_t) E->B) {
@@ -1955,6 +1962,57 @@ int tsc_reset(tsc_handle E, void *stream) {
         CUDA_TRY(cudaMemcpyAsync(E->images + done * E->Y.img_bytes, E->images, n * E->Y.img_bytes, cudaMemcpyDeviceToDevice, st));
         done += n;
     }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int tsc_reset_replicas(tsc_handle E, const int32_t *replicas, int32_t n, void *stream) {
+    if (!E || n < 0 || (n && !replicas)) return fail(TSC_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(E->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    for (int k = 0; k < n; ++k)
+        if (replicas[k] < 0 || replicas[k] >= E->B) return fail(TSC_EINVAL, "replica index %d out of range", replicas[k]);
+    // the tick-0 image is kept on the device right behind the B replica images
+    for (int k = 0; k < n; ++k)
+        CUDA_TRY(cudaMemcpyAsync(E->images + (size_t) replicas[k] * E->Y.img_bytes, E->images + (size_t) E->B * E->Y.img_bytes,
+                                 E->Y.img_bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// blob = StateHeader + B replica images
+struct StateHeader { char magic[8]; int32_t abi, B, img_bytes, Vcap, D, A, N, pad; };
+static void fill_state_header(tsc_handle E, StateHeader &h) {
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "TSCB200S", 8);
+    h.abi = TSC_ABI_VERSION; h.B = E->B; h.img_bytes = E->Y.img_bytes; h.Vcap = E->Y.Vcap; h.D = E->S.D; h.A = E->S.A; h.N = E->S.N;
+}
+
+int64_t tsc_state_bytes(tsc_handle E) { return E ? (int64_t) sizeof(StateHeader) + (int64_t) E->B * E->Y.img_bytes : 0; }
+
+int tsc_save_state(tsc_handle E, void *buf, int64_t buf_bytes, void *stream) {
+    if (!E || !buf) return fail(TSC_EINVAL, "null argument");
+    if (buf_bytes < tsc_state_bytes(E)) return fail(TSC_EINVAL, "state buffer too small: %lld < %lld", (long long) buf_bytes, (long long) tsc_state_bytes(E));
+    CUDA_TRY(cudaSetDevice(E->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    StateHeader h;
+    fill_state_header(E, h);
+    CUDA_TRY(cudaMemcpyAsync(buf, &h, sizeof h, cudaMemcpyDefault, st));
+    CUDA_TRY(cudaMemcpyAsync((char *) buf + sizeof h, E->images, (size_t) E->B * E->Y.img_bytes, cudaMemcpyDefault, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int tsc_load_state(tsc_handle E, const void *buf, int64_t buf_bytes, void *stream) {
+    if (!E || !buf) return fail(TSC_EINVAL, "null argument");
+    if (buf_bytes < tsc_state_bytes(E)) return fail(TSC_EINVAL, "state buffer too small");
+    CUDA_TRY(cudaSetDevice(E->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    StateHeader h, want;
+    CUDA_TRY(cudaMemcpyAsync(&h, buf, sizeof h, cudaMemcpyDefault, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    fill_state_header(E, want);
+    if (memcmp(&h, &want, sizeof h) != 0) return fail(TSC_EINVAL, "state blob was saved by a different scenario / batch size / capacity");
+    CUDA_TRY(cudaMemcpyAsync(E->images, (const char *) buf + sizeof h, (size_t) E->B * E->Y.img_bytes, cudaMemcpyDefault, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
