@@ -126,34 +126,44 @@ def run_reference_arm(args):
 # clocks
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the GPU is under the bench load.
+    Started before the warm-up steps so that short runs still get samples; the samples that fall inside
+    the timed region are the ones reported whenever there are at least three of them."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_timed = index, [], None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def mark_timed_region(self):
+        self.t_timed = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        timed = [r for t, r in self.rows if self.t_timed is not None and t >= self.t_timed]
+        window = "timed region"
+        if len(timed) < 3:
+            timed, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than three samples)"
+        sm = sorted(int(r[0]) for r in timed if r and r[0].isdigit())
+        mx = [int(r[1]) for r in timed if len(r) > 1 and r[1].isdigit()]
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in timed)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------
@@ -261,16 +271,17 @@ def run_gpu_arm(args):
 
     # ---- device-resident leg ----------------------------------------------------------
     restart()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         one_step()
         flush.zero_()
     sync_all()
     launches0 = eng.launch_count()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
+    clocks.mark_timed_region()
     t_wall = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                      # evict the replica images and last step's outputs from L2
