@@ -108,6 +108,7 @@ struct Layout {
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
     int cross_group;       // lanes per vehicle in the per-vehicle cross phase: 32, 16 or 8
     int pair_cap;          // (vehicle, cross) pairs the flat cross phase can list (0: warp-per-vehicle phase only)
+    int cold_level;        // 2: the decision buffers are laid out in the cold region (D)
     int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
     // persistent part: identical byte offsets in the HBM image and in shared memory
     int o_cnt, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
@@ -1364,13 +1365,14 @@ __device__ __forceinline__ void copy16(void *dst, const void *src, int bytes, in
 // hot path 2-3 % through register allocation alone).  STAGED: register-staged re-pack (see engine_tick).
 // GMEM: the replica's working set does not fit an SM's shared memory (a 16 x 16 grid needs ~1 MB): the
 // block works out of a global-memory workspace instead -- same layout, same code, L2-resident.
-template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM, bool ONE_T, bool HYB>
+template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM, bool ONE_T, int HYB>
 __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
                                                       const u8 *is_spawn_lane, const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_block[];
     unsigned char *const smem = GMEM ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes + 255) & ~255) : smem_block;
-    // HYB: the cold buffers (D) live in this block's global workspace, the cold image column (B) stays
-    // in the image, and the shared-memory-only hot arrays (C) move down over the room (B) would have taken
+    // HYB >= 1: the cold buffers (D) live in this block's global workspace, the cold image column (B) stays
+    // in the image, and the shared-memory-only hot arrays (C) move down over the room (B) would have taken.
+    // HYB == 2 (replicas too large for three blocks per SM otherwise): the tick's decision buffers are in (D) too.
     unsigned char *const hot = HYB ? smem - (Y.img_bytes - Y.o_img_cold) : smem;
     unsigned char *const cold = HYB ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes - Y.o_cold + 255) & ~255) - Y.o_cold : smem;
     const int tid = threadIdx.x;
@@ -1381,8 +1383,9 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd);
     c.rpos = (int *) (smem + Y.o_rpos); c.blk = (short *) (smem + Y.o_blk);
     c.newslot = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
-    c.npos = (double *) (hot + Y.o_npos); c.nspd = (double *) (hot + Y.o_nspd); c.nrpos = (int *) (hot + Y.o_nrpos);
-    c.nblk = (short *) (hot + Y.o_nblk); c.nflag = hot + Y.o_nflag; c.xlist = (u16 *) (hot + Y.o_xlist);
+    unsigned char *const dec = HYB >= 2 ? cold : hot;      // decision buffers
+    c.npos = (double *) (dec + Y.o_npos); c.nspd = (double *) (dec + Y.o_nspd); c.nrpos = (int *) (dec + Y.o_nrpos);
+    c.nblk = (short *) (dec + Y.o_nblk); c.nflag = dec + Y.o_nflag; c.xlist = (u16 *) (hot + Y.o_xlist);
     c.off = (u16 *) (hot + Y.o_off); c.leave = (u16 *) (hot + Y.o_leave); c.ent = (u16 *) (hot + Y.o_ent);
     c.fresh = hot + Y.o_fresh; c.entlist = (u16 *) (hot + Y.o_entlist); c.entpos = (double *) (hot + Y.o_entpos);
     c.entdrv = (u16 *) (hot + Y.o_entdrv); c.scan = (int *) (hot + Y.o_scan);
@@ -1413,7 +1416,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             copy16(smem + Y.o_spd, img + Y.o_spd, n8, tid, NT);
             copy16(smem + Y.o_rpos, img + Y.o_rpos, n4, tid, NT);
             copy16(smem + Y.o_vid, img + Y.o_vid, n4, tid, NT);
-            if (!HYB) copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
+            if (HYB == 0) copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
             copy16(smem + Y.o_blk, img + Y.o_blk, n2, tid, NT);
             copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
         }
@@ -1523,19 +1526,25 @@ static int fail(int code, const char *fmt, ...) {
 // that, register-staged when even one copy of the identity columns is too much; one 1024-thread block
 // per SM over a global-memory workspace for replicas that do not fit shared memory at all.
 typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
-static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged, bool one_t, bool hybrid) {
-    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true, false, false>;
-    if (nt == 512) return staged ? tsc_step_kernel<512, 1, true, true, false, false, false> : tsc_step_kernel<512, 1, true, false, false, false, false>;
-    if (nt == 192 && one_t && hybrid)   // four 192-thread blocks per SM (80 registers), cold buffers in the global workspace
-        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, true> : tsc_step_kernel<192, 4, false, false, false, true, true>;
-    if (nt == 192 && one_t)             // the same with everything in shared memory (working set below 56 KB)
-        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, false> : tsc_step_kernel<192, 4, false, false, false, true, false>;
-    if (one_t) {
-        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true, false> : tsc_step_kernel<256, 2, true, false, false, true, false>;
-        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true, false> : tsc_step_kernel<256, 2, false, false, false, true, false>;
+static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged, bool one_t, int hybrid, bool gmem) {
+    if (nt == 1024 && gmem) return tsc_step_kernel<1024, 1, true, false, true, false, 0>;
+    if (nt == 1024 && !staged && one_t) return tsc_step_kernel<1024, 1, true, false, false, true, 0>;    // shared memory, 32 warps, 64 registers
+    if (nt == 512 && !staged && one_t) return tsc_step_kernel<512, 1, true, false, false, true, 0>;
+    if (nt == 512 || nt == 1024) return staged ? tsc_step_kernel<512, 1, true, true, false, false, 0> : tsc_step_kernel<512, 1, true, false, false, false, 0>;
+    if (nt == 256 && one_t && hybrid == 2) {    // large replicas: decision buffers in the global workspace buy a block per SM
+        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true, 2> : tsc_step_kernel<256, 2, true, false, false, true, 2>;
+        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true, 2> : tsc_step_kernel<256, 2, false, false, false, true, 2>;
     }
-    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, false, false> : tsc_step_kernel<256, 2, true, false, false, false, false>;
-    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, false, false> : tsc_step_kernel<256, 2, false, false, false, false, false>;
+    if (nt == 192 && one_t && hybrid)   // four 192-thread blocks per SM (80 registers), cold buffers in the global workspace
+        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, 1> : tsc_step_kernel<192, 4, false, false, false, true, 1>;
+    if (nt == 192 && one_t)             // the same with everything in shared memory (working set below 56 KB)
+        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, 0> : tsc_step_kernel<192, 4, false, false, false, true, 0>;
+    if (one_t) {
+        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true, 0> : tsc_step_kernel<256, 2, true, false, false, true, 0>;
+        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true, 0> : tsc_step_kernel<256, 2, false, false, false, true, 0>;
+    }
+    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, false, 0> : tsc_step_kernel<256, 2, true, false, false, false, 0>;
+    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, false, 0> : tsc_step_kernel<256, 2, false, false, false, false, 0>;
 }
 
 #define MAX_HOST_CHUNKS 16
@@ -1558,7 +1567,8 @@ struct tsc_engine {
     int64_t launches = 0;
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
     unsigned char *workspace = nullptr;             // GMEM variant: grid working sets in global memory
-    bool gmem = false, hybrid = false;
+    bool gmem = false;
+    int hybrid = 0;                                 // 0: everything in shared memory; 1: cold column in the global workspace; 2: decision buffers too
     int dyn_smem = 0;                               // dynamic shared memory per block of the chosen variant
     cudaStream_t host_compute = nullptr, host_compute2 = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
     int host_streams = 1;               // compute streams the chunks alternate on (TSC_B200_HOST_STREAMS=2: measured slower, 1.58 vs 1.53 ms per B=4096 step)
@@ -1587,9 +1597,10 @@ static int upload(tsc_engine *E, const Tp *host, size_t n, const Tp **dev) {
 
 static int align16(int x) { return (x + 15) & ~15; }
 
-static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
+static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged, int cold_level = 0) {
     Y.Vcap = Vcap;
     Y.staged = staged;
+    Y.cold_level = cold_level;
     Y.pair_cap = staged ? 0 : Vcap;      // the list lives in the idle copy of the ping-pong identity columns
     // vehicles changing drivable in one tick (a lane hands over at most one or two per tick; the shipped
     // workloads stay far below a tenth of the running vehicles): a quarter of the slots, overflow is
@@ -1637,16 +1648,21 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged) {
     // the tick's decision buffers; npos / nspd / nrpos double as retrieve scratch: make sure they are large enough
     int need_np = 3 * S.L, need_ns = 2 * S.A + (S.L + 1) / 2 + 2;
     int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
-    Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
-    Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
-    Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
-    Y.o_nblk = o; o = align16(o + 2 * Vcap);
-    Y.o_nflag = o; o = align16(o + Vcap);
-    // ---- (D) the idle copy of the cold column.  The hybrid variant keeps it in a per-block global-memory
-    //      workspace (L2-resident) so that one more replica fits an SM's shared memory (8 bytes per slot
-    //      with (B)).  Moving decision buffers out as well was measured: the new route cursors cost 4 %,
-    //      all of them 20 %.
+    auto decision_buffers = [&]() {
+        Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
+        Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
+        Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
+        Y.o_nblk = o; o = align16(o + 2 * Vcap);
+        Y.o_nflag = o; o = align16(o + Vcap);
+    };
+    if (cold_level < 2) decision_buffers();
+    // ---- (D) cold region: written once and read once per vehicle per tick, in slot order.  The hybrid
+    //      variants keep it in a per-block global-memory workspace (L2-resident) so that more replicas fit
+    //      an SM's shared memory.  Level 1: the idle copy of the cold column (8 bytes per slot with (B)) --
+    //      what lets the bench workload run four blocks per SM.  Level 2: the decision buffers as well
+    //      (29 more bytes per slot; costs ~20 % per block, taken only when it buys a block per SM).
     Y.o_cold = o;
+    if (cold_level >= 2) decision_buffers();
     Y.o_ellt2 = o; o = align16(o + 4 * V2);
     Y.smem_bytes = o;
     Y.hybrid_smem_bytes = Y.o_cold - (Y.img_bytes - Y.o_img_cold);      // (A) + (C)
@@ -1851,15 +1867,36 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     if (const char *env = getenv("TSC_B200_THREADS")) small = small && atoi(env) == 192;      // (224 threads x 4 at 72 registers: 0.984 vs 0.970 ms)
     const size_t per_sm = prop.sharedMemPerMultiprocessor;
     const bool four_plain = small && per_sm / (size_t) (E->Y.smem_bytes + 1024) >= 4;
-    bool hybrid = small && !four_plain && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4;
-    if (const char *env = getenv("TSC_B200_HYBRID")) { int v = atoi(env); hybrid = v == 0 ? false : (small && (v == 2 || hybrid) && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4); }
-    const bool four_blocks = hybrid || four_plain;
+    int hybrid = (small && !four_plain && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4) ? 1 : 0;
+    int hyb_env = 1;
+    if (const char *env = getenv("TSC_B200_HYBRID")) hyb_env = atoi(env);
+    if (hyb_env == 0) hybrid = 0;
+    if (hyb_env == 2 && small && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4) hybrid = 1;      // forced although everything would fit
+    const bool four_blocks = hybrid == 1 || four_plain;
     if (E->minb > 3) E->minb = 3;
     if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
     if (four_blocks) { E->nt = 192; E->minb = 4; }
+    if (!four_blocks && one_t && hyb_env != 0 && !getenv("TSC_B200_THREADS") && !getenv("TSC_B200_STAGED") && !getenv("TSC_B200_GMEM") &&
+        !getenv("TSC_B200_MIN_BLOCKS")) {
+        // larger replicas: does moving the decision buffers out as well buy a block per SM (up to three)?
+        const int plain_blocks = E->gmem ? 0 : (int) (per_sm / (size_t) (E->Y.smem_bytes + 1024));
+        Layout Y2 = E->Y;
+        build_layout(Y2, S, Vcap, 0, 2);
+        int b2 = (int) (per_sm / (size_t) (Y2.hybrid_smem_bytes + 1024));
+        if (b2 > 3) b2 = 3;
+        if (b2 >= 2 && b2 > plain_blocks && plain_blocks < 3) {
+            const int pc = E->Y.pair_cap, cg = E->Y.cross_group, pf = E->Y.prefetch_next;
+            E->Y = Y2;
+            E->Y.pair_cap = pc ? Y2.pair_cap : 0; E->Y.cross_group = cg; E->Y.prefetch_next = pf;
+            E->gmem = false; staged = 0;
+            E->nt = 256; E->minb = b2; hybrid = 2;
+        }
+    }
     E->hybrid = hybrid;
-    E->kern = kernel_for(E->nt, E->minb, false, staged != 0, one_t, hybrid);
-    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0, one_t, hybrid);
+    if (E->nt == 512 && !E->gmem && !staged && one_t)      // one block per SM: TSC_B200_THREADS=1024 runs it with 32 warps at 64 registers
+        if (const char *env = getenv("TSC_B200_THREADS")) { if (atoi(env) == 1024) E->nt = 1024; }
+    E->kern = kernel_for(E->nt, E->minb, false, staged != 0, one_t, hybrid, E->gmem);
+    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0, one_t, hybrid, E->gmem);
     const int dyn_smem = E->gmem ? 0 : (hybrid ? E->Y.hybrid_smem_bytes : E->Y.smem_bytes);
     E->dyn_smem = dyn_smem;
     for (int k = 0; k < 2; ++k) {
@@ -2329,7 +2366,7 @@ int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t
 int tsc_kernel_variant(tsc_handle E, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm) {
     if (!E) return fail(TSC_EINVAL, "null handle");
     if (staged) *staged = E->Y.staged;
-    if (global_workspace) *global_workspace = E->gmem ? 1 : (E->hybrid ? 2 : 0);      // 2: decision buffers only
+    if (global_workspace) *global_workspace = E->gmem ? 1 : (E->hybrid ? 1 + E->hybrid : 0);      // 2: cold column only, 3: decision buffers too
     if (blocks_per_sm) *blocks_per_sm = E->minb;
     return 0;
 }

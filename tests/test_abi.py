@@ -64,3 +64,38 @@ def test_create_fails_loudly_without_gpu(cuda_lib):
     h = C.c_void_p()
     rc = cuda_lib.tsc_create(C.byref(s), 1, 0, 0, C.byref(h))
     assert rc < 0 and cuda_lib.tsc_last_error()
+
+
+def test_null_and_bad_arguments_return_einval(cuda_lib):
+    """Error behaviour of the ABI without touching a device: every entry point rejects a null handle
+    (or a null required pointer) with TSC_EINVAL and leaves a message; nothing crashes."""
+    L = cuda_lib
+    EINVAL = -1
+    null = C.c_void_p()
+    out = C.c_void_p()
+    i = C.c_int32()
+    assert L.tsc_create(None, 1, 0, 0, C.byref(out)) == EINVAL and b"null" in L.tsc_last_error()
+    cfg, parser, cs = build_scenario("syn_1x1")
+    s = cs.to_struct()
+    assert L.tsc_create(C.byref(s), 0, 0, 0, C.byref(out)) == EINVAL and b"n_replicas" in L.tsc_last_error()
+    s.abi_version = 1
+    assert L.tsc_create(C.byref(s), 1, 0, 0, C.byref(out)) == EINVAL and b"abi_version" in L.tsc_last_error()
+    s = cs.to_struct()
+    s.interval = 0.5
+    assert L.tsc_create(C.byref(s), 1, 0, 0, C.byref(out)) == EINVAL and b"interval" in L.tsc_last_error()
+    for call in (lambda: L.tsc_reset(null, None), lambda: L.tsc_step(null, 1, None), lambda: L.tsc_set_phase(null, None, None),
+                 lambda: L.tsc_init_program(null, 0, None), lambda: L.tsc_retrieve(null, None, None),
+                 lambda: L.tsc_env_step(null, None, 0, 0, 5, None, None),
+                 lambda: L.tsc_env_step_host(null, None, 0, 0, 5, None, None, None, None),
+                 lambda: L.tsc_snapshot(null, 0, 0, None, None, None, None, None, None),
+                 lambda: L.tsc_load_snapshot(null, 0, 0, None, None, None, None, None),
+                 lambda: L.tsc_check(null, C.byref(i)), lambda: L.tsc_counters(null, None, None, None, None),
+                 lambda: L.tsc_kernel_info(null, None, None, None, None), lambda: L.tsc_kernel_variant(null, None, None, None),
+                 lambda: L.tsc_debug_timing(null, 0, None, 0), lambda: L.tsc_controller_act(null, 3, 0, None, None, None),
+                 lambda: L.tsc_reset_replicas(null, None, 0, None), lambda: L.tsc_save_state(null, None, 0, None),
+                 lambda: L.tsc_load_state(null, None, 0, None),
+                 lambda: L.tsc_get_dims(null, None, None, None, None, None, None, None, None, None)):
+        assert call() == EINVAL
+        assert L.tsc_last_error()
+    assert L.tsc_launch_count(null) == 0 and L.tsc_state_bytes(null) == 0
+    L.tsc_destroy(null)      # no-op

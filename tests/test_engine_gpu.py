@@ -97,6 +97,9 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0)),     # per-vehicle template look-up although the scenario has one template
     ({"TSC_B200_PREFETCH": "0"}, 600, (192, 2)),
     ({"TSC_B200_HYBRID": "0"}, 600, (256, 0)),
+    ({}, 2000, (256, 3)),                                # large replica: decision buffers in the global workspace buy a second block per SM
+    ({"TSC_B200_THREADS": "512"}, 2000, (512, 0)),       # one block per SM, everything in shared memory
+    ({"TSC_B200_THREADS": "1024"}, 2000, (1024, 0)),     # the same with 32 warps at 64 registers
 ])
 def test_kernel_variants_agree_with_oracle(cuda_lib, env, capacity, variant, monkeypatch):
     """The code paths an environment switch (or an unusual scenario) selects at tsc_create produce the
