@@ -171,43 +171,46 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 class HostFixedTimePolicy:
     """FixedTimeController.get_action (controllers/controllers.py:39-54) for all B x A signals on the
-    host, with its own copy of the programs' state (current phase index, time on phase): the e2e
-    leg's stand-in for a user's policy.  numpy, preallocated temporaries, table look-ups."""
+    host, with its own copy of the programs' state: the e2e leg's stand-in for a user's policy.
+
+    The controller is a finite-state machine per signal -- state = (current phase index, time on phase in
+    units of delta_time, saturating) -- so the whole B x A batch advances with two table look-ups per
+    step (action, next state).  tests/test_port.py checks it against the rule written out."""
+    T = 64      # time-on-phase slots per phase (saturating: beyond green_time nothing changes)
 
     def __init__(self, sig_phase_green, sig_n_phases, B, A, green_time, n_ticks):
         import numpy as np
         self.np = np
-        green = np.ascontiguousarray(sig_phase_green).reshape(A, -1).astype(np.uint8)
-        P = green.shape[1]
-        nph = np.asarray(sig_n_phases, np.int64).reshape(A, 1)
-        self.green_flat = green.ravel()
-        self.next_flat = ((np.arange(P, dtype=np.int64)[None, :] + 1) % nph).astype(np.uint8).ravel()
-        self.base = (np.arange(A, dtype=np.intp) * P)[None, :]
-        self.green_time, self.n_ticks = green_time, n_ticks
-        self.cur = np.zeros((B, A), np.uint8)
-        self.top = np.zeros((B, A), np.int32)
+        green = np.ascontiguousarray(sig_phase_green).reshape(A, -1).astype(bool)
+        P, T = green.shape[1], self.T
+        assert green_time < (T - 1) * n_ticks
+        nph = np.asarray(sig_n_phases, np.int64).reshape(A)
+        nxt_state = np.zeros((A, P * T), np.uint16)
+        action = np.zeros((A, P * T), np.int32)
+        for a in range(A):
+            for c in range(int(nph[a])):
+                for t in range(T):
+                    stay = bool(green[a, c]) and t * n_ticks < green_time       # on green for less than green_time
+                    n = c if stay else (c + 1) % int(nph[a])
+                    # BaseTSProgram.update_current_phase (common/traffic_signal.py:94-109): += delta_time or = delta_time
+                    nt = min(t + 1, T - 1) if n == c else 1
+                    nxt_state[a, c * T + t] = n * T + nt
+                    action[a, c * T + t] = n
+        self.nxt_state, self.action = nxt_state.ravel(), action.ravel()
+        self.base = (np.arange(A, dtype=np.intp) * (P * T))[None, :]
+        self.state = np.zeros((B, A), np.uint16)
         self.idx = np.empty((B, A), np.intp)
-        self.nxt = np.empty((B, A), np.uint8)
-        self.flag = np.empty((B, A), bool)
 
     def reset(self):
-        self.cur.fill(0)
-        self.top.fill(0)
+        self.state.fill(0)
 
     def act(self, out):
         np = self.np
-        np.add(self.base, self.cur, out=self.idx)
-        stay = self.green_flat[self.idx]                       # on a green phase ...
-        np.less(self.top, self.green_time, out=self.flag)     # ... for less than green_time
-        np.logical_and(stay, self.flag, out=self.flag)
-        np.take(self.next_flat, self.idx, out=self.nxt, mode="clip")
-        np.copyto(self.nxt, self.cur, where=self.flag)
-        # BaseTSProgram.update_current_phase (common/traffic_signal.py:94-109)
-        np.add(self.top, self.n_ticks, out=self.top)
-        np.not_equal(self.nxt, self.cur, out=self.flag)
-        np.copyto(self.top, self.n_ticks, where=self.flag)
-        self.cur[...] = self.nxt
-        out[...] = self.nxt
+        np.add(self.base, self.state, out=self.idx)
+        np.take(self.action, self.idx, out=out, mode="clip")
+        np.take(self.nxt_state, self.idx, out=self.state, mode="clip")
+
+
 def algorithmic_bytes_per_env_step(V, L, K, A, obs_dim, P, n_ticks=5):
     """per tick 40 B per vehicle + 8 B per drivable + 4 B per signal; per env-step
     16 B per lane + per agent (4 obs_dim + reward 4 + mask P + action 4)."""

@@ -63,3 +63,32 @@ def test_fixed_time_controller_cycle():
         env.step(a)
         seq.append(a[0])
     assert seq == [0, 0, 0, 0, 0, 1, 2, 2, 2, 2, 2, 3, 4, 4]
+
+
+def test_bench_host_policy_is_the_fixed_time_rule():
+    """bench.py's table-driven host policy == FixedTimeController.get_action + update_current_phase
+    written out (controllers/controllers.py:39-54, common/traffic_signal.py:94-109), 800 steps."""
+    import numpy as np
+    import bench
+    from helpers import build_scenario
+    cfg, parser, cs = build_scenario(bench.SCENARIO, **bench.SCENARIO_KW)
+    A, B, G, dt = cs.n_signals, 7, bench.GREEN_TIME, 5
+    green = np.ascontiguousarray(cs.sig_phase_green).reshape(A, -1).astype(bool)
+    nph = np.asarray(cs.sig_n_phases, np.int64)
+    pol = bench.HostFixedTimePolicy(cs.sig_phase_green, cs.sig_n_phases, B, A, G, dt)
+    cur = np.zeros((B, A), np.int64)
+    top = np.zeros((B, A), np.int64)
+    out = np.zeros((B, A), np.int32)
+    for step in range(800):
+        want = np.empty((B, A), np.int64)
+        for b in range(B):
+            for a in range(A):
+                stay = green[a, cur[b, a]] and top[b, a] < G
+                want[b, a] = cur[b, a] if stay else (cur[b, a] + 1) % nph[a]
+        top = np.where(want == cur, top + dt, dt)
+        cur = want
+        pol.act(out)
+        assert np.array_equal(out, want), step
+    pol.reset()
+    pol.act(out)
+    assert (out == 0).all() or (out[0] == out[-1]).all()
