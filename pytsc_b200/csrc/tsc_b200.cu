@@ -58,8 +58,10 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     int L, K, D, A, N, T, horizon, max_raw, P;
     int n_in_total, n_out_total, n_spawn_lanes;
     const double *drv_length, *drv_max_speed;
+    const double2 *drv_lm;      // [D] (length, max speed) packed for the per-vehicle pass
     const int *lane_ll_off, *lane_ll, *lane_spawn_off, *lane_spawn_vid, *spawn_lane;
     const short *lane_spawn_idx;     // [L] index into the spawn-lane list, -1 for lanes nothing spawns on
+    const int4 *lane_sib;            // [L] {n, d0, d1, d2}: the (up to three) lane-links leaving the lane as drivable indices; n = -1: more, use lane_ll
     const int *ll_start_lane, *ll_end_lane, *ll_signal, *ll_roadlink, *ll_type, *ll_cross_off;
     const double *xr_dist, *xr_foe_dist;
     const int *xr_foe_ll;
@@ -526,15 +528,23 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             if (nd < 0) break;
             if (nd >= L) {
                 const int sl = (j == 1 && d < L) ? d : __ldg(&S.llinfo[nd - L].start_lane);   // the link after lane d starts at d
-                int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
-                for (int q = e0; q < e1; ++q) {
-                    int dl = L + __ldg(S.lane_ll + q);
+                // all lane-links leaving that lane, in roadnet order: one packed load for up to three of them
+                const int4 sib = __ldg(S.lane_sib + sl);
+                auto consider = [&](int dl) {
                     int n = c.cnt[dl];
                     if (n > 0) {
                         int cand = c.off[dl] + n - 1;
                         double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
                         if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
                     }
+                };
+                if (sib.x >= 0) {
+                    if (sib.x > 0) consider(sib.y);
+                    if (sib.x > 1) consider(sib.z);
+                    if (sib.x > 2) consider(sib.w);
+                } else {
+                    int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
+                    for (int q = e0; q < e1; ++q) consider(L + __ldg(S.lane_ll + q));
                 }
                 if (leader >= 0) break;
             } else {
@@ -566,7 +576,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         const int d = dnv & 0xFFFF;
         const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
         const double x = c.pos[i], v = c.spd[i];
-        const double dlen = __ldg(S.drv_length + d);
+        const double2 lm = __ldg(S.drv_lm + d);       // length, speed limit: one 16-byte load
+        const double dlen = lm.x;
         int leader;
         double gap;
         if (i > c.off[d]) {
@@ -575,7 +586,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         } else { leader = c.nblk[i]; gap = c.npos[i]; }
         double ns = T[TSC_T_MAX_SPEED];
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
-        ns = min2(ns, __ldg(S.drv_max_speed + d));
+        ns = min2(ns, lm.y);
         double cf = T[TSC_T_MAX_SPEED];
         if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
         ns = min2(ns, cf);
@@ -1139,7 +1150,13 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         int n = c.cnt[l], base = c.off[l];
         int q = 0;
         double tot = 0.0;
-        for (int k = 0; k < n; ++k) {
+        int k = 0;
+        for (; k + 4 <= n; k += 4) {      // four loads in flight; the sum keeps the reference's front-to-back order
+            const double v0 = c.spd[base + k], v1 = c.spd[base + k + 1], v2 = c.spd[base + k + 2], v3 = c.spd[base + k + 3];
+            tot += v0; tot += v1; tot += v2; tot += v3;
+            q += (v0 < 0.1) + (v1 < 0.1) + (v2 < 0.1) + (v3 < 0.1);
+        }
+        for (; k < n; ++k) {
             double v = c.spd[base + k];
             tot += v;
             q += v < 0.1;
@@ -1793,6 +1810,23 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         if ((rc = upload(E, li.data(), li.size(), &S.llinfo))) { tsc_destroy(E); return rc; }
         if ((rc = upload(E, ce.data(), ce.size(), &S.cross))) { tsc_destroy(E); return rc; }
     }
+    {
+        std::vector<double2> lm(D > 0 ? D : 1);
+        for (int k = 0; k < D; ++k) lm[k] = make_double2(s->drv_length[k], s->drv_max_speed[k]);
+        if ((rc = upload(E, lm.data(), lm.size(), &S.drv_lm))) { tsc_destroy(E); return rc; }
+    }
+    {   // packed sibling lists for the head look-ahead
+        std::vector<int4> sib(L > 0 ? L : 1);
+        for (int l = 0; l < L; ++l) {
+            const int e0 = s->lane_ll_off[l], n = s->lane_ll_off[l + 1] - e0;
+            int4 v = make_int4(n <= 3 ? n : -1, 0, 0, 0);
+            if (n > 0 && n <= 3) v.y = L + s->lane_ll[e0];
+            if (n > 1 && n <= 3) v.z = L + s->lane_ll[e0 + 1];
+            if (n > 2 && n <= 3) v.w = L + s->lane_ll[e0 + 2];
+            sib[l] = v;
+        }
+        if ((rc = upload(E, sib.data(), sib.size(), &S.lane_sib))) { tsc_destroy(E); return rc; }
+    }
     // spawn lanes and creation prefix tables
     E->h_is_spawn.assign(L, 0);
     for (int l = 0; l < L; ++l) if (s->lane_spawn_off[l + 1] > s->lane_spawn_off[l]) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
@@ -2157,7 +2191,8 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     // Replicas are independent, so the batch is cut into chunks: while chunk k+1 is being stepped on
     // the compute stream, chunk k's observations / rewards / masks travel to the host on the copy
     // stream.  Both streams are ordered after whatever the caller queued on the default stream.
-    cudaStream_t sc = E->host_compute, sc2 = E->host_streams > 1 ? E->host_compute2 : E->host_compute, sd = E->host_copy;
+    // (two compute streams only without a per-block global workspace: concurrent launches would share it)
+    cudaStream_t sc = E->host_compute, sc2 = (E->host_streams > 1 && !E->workspace) ? E->host_compute2 : E->host_compute, sd = E->host_copy;
     CUDA_TRY(cudaEventRecord(E->host_ev[0], 0));
     CUDA_TRY(cudaStreamWaitEvent(sc, E->host_ev[0], 0));
     // page-locked caller buffers are used in place; pageable ones go through the handle's pinned staging
