@@ -1592,6 +1592,7 @@ struct tsc_engine {
     cudaEvent_t host_ev_actions = nullptr;
     cudaEvent_t host_ev[1 + MAX_HOST_CHUNKS] = {};
     int host_chunks = MAX_HOST_CHUNKS;   // upper bound on chunks per host step (TSC_B200_HOST_CHUNKS)
+    int host_lead = 0;                  // TSC_B200_HOST_LEAD=1 / =N: a short first chunk (one replica per SM / N replicas) so that the copies start early -- measured slower (1.58 vs 1.39-1.50 ms)
     bool host_zero_copy = false;        // TSC_B200_HOST_ZERO_COPY=1: kernel stores straight into mapped page-locked buffers
     std::vector<unsigned char> init_image;   // host copy of the tick-0 image
     // host copies needed by snapshot/load
@@ -1982,6 +1983,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     for (auto &ev : E->host_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *env = getenv("TSC_B200_HOST_CHUNKS")) { int v = atoi(env); if (v >= 1 && v <= MAX_HOST_CHUNKS) E->host_chunks = v; }
     if (const char *env = getenv("TSC_B200_HOST_ZERO_COPY")) E->host_zero_copy = atoi(env) != 0;
+    if (const char *env = getenv("TSC_B200_HOST_LEAD")) E->host_lead = atoi(env) > 0 ? atoi(env) : 0;
     *out = E;
     int r = tsc_reset(E, nullptr);
     if (r) { tsc_destroy(E); *out = nullptr; return r; }
@@ -2233,8 +2235,13 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     }
     // chunk = a whole number of waves of the persistent grid, so that no launch ends on a partly
     // filled wave; at most MAX_HOST_CHUNKS chunks
-    const int total_waves = (E->B + E->grid - 1) / E->grid;
-    int wpc = E->host_chunks > 0 ? (total_waves + E->host_chunks - 1) / E->host_chunks : 1;
+    // The copies are the longer leg (57 MB per step on the bench workload against < 1 ms of kernel); an optional
+    // short lead chunk lets the first copy start earlier (off by default: it cost more than it gave).
+    int lead = E->host_lead > 1 ? E->host_lead : ((E->host_lead && E->minb > 1) ? E->grid / E->minb : 0);      // > 1: explicit size
+    if (lead >= E->B) lead = 0;
+    const int total_waves = (E->B - lead + E->grid - 1) / E->grid;
+    const int max_chunks = E->host_chunks - (lead ? 1 : 0) > 0 ? E->host_chunks - (lead ? 1 : 0) : 1;
+    int wpc = (total_waves + max_chunks - 1) / max_chunks;
     if (wpc < 1) wpc = 1;
     const int chunk = wpc * E->grid;
     if (sc2 != sc) {   // the second compute stream starts after the actions have arrived
@@ -2242,9 +2249,11 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
         CUDA_TRY(cudaStreamWaitEvent(sc2, E->host_ev_actions, 0));
     }
     int k = 0;
-    for (int b0 = 0; b0 < E->B; b0 += chunk, ++k) {
+    for (int b0 = 0; b0 < E->B; ++k) {
+        const int len = (k == 0 && lead) ? lead : chunk;
         a.b0 = b0;
-        a.B = b0 + chunk < E->B ? b0 + chunk : E->B;
+        a.B = b0 + len < E->B ? b0 + len : E->B;
+        b0 = a.B;
         cudaStream_t st = (k & 1) ? sc2 : sc;
         int rc = launch(E, a, st);
         if (rc) return rc;
