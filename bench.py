@@ -169,6 +169,32 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and the pinned buffers it is about to allocate) to the CPUs of the GPU's NUMA
+    node, as a multi-socket deployment would per rank: host <-> device copies then stay on the local PCIe
+    root.  Returns (description, previous affinity); silent no-op where the topology is not exposed."""
+    try:
+        if os.environ.get("BENCH_NO_AFFINITY"):
+            return "unchanged (BENCH_NO_AFFINITY)", None
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if node < 0 or not cpus or cpus == prev:
+            return f"unchanged (numa node {node})", None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} of GPU {bdf}: {len(cpus)} of {len(prev)} cpus", prev
+    except Exception as e:      # no sysfs, no permission, old torch ...
+        return f"unchanged ({type(e).__name__})", None
+
+
 class HostFixedTimePolicy:
     """FixedTimeController.get_action (controllers/controllers.py:39-54) for all B x A signals on the
     host, with its own copy of the programs' state: the e2e leg's stand-in for a user's policy.
@@ -233,6 +259,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the gpu backend has no CPU fallback)")
     torch.cuda.set_device(local)
+    affinity, prev_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
@@ -393,7 +420,8 @@ def run_gpu_arm(args):
                    "replicas_per_gpu": B, "replicas_total": total_B, "parallelism": f"replica-sharded x{world}, no step-path collective",
                    "l2": "256 MiB flush write between timed launches", "mean_running_vehicles": vbar,
                    "final_tick": final_tick, "env_steps_per_s": value / A, "engine_ticks_per_s": value / A * n_ticks,
-                   "kernel": {"name": "tsc_step_kernel", **info}, "wall_s_timed_region": t_wall},
+                   "kernel": {"name": "tsc_step_kernel", **info}, "wall_s_timed_region": t_wall,
+                   "host_cpu_affinity": affinity},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": alg, "units_per_launch": B},
@@ -408,6 +436,8 @@ def run_gpu_arm(args):
         "episode": {"mean_average_travel_time_s": float(epi[0] / epi[3]), "finished_vehicles_per_replica": float(epi[1] / epi[3])},
     }
     if world == 1 and not args.no_cpu_baseline:
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)      # the CPU baseline gets every host core back
         line["cpu_baseline"] = cpu_baseline_block(args.cpu_steps)
     print(json.dumps(line), flush=True)
 
