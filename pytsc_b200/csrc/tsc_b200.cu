@@ -108,7 +108,7 @@ static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 struct Layout {
     int Vcap, ent_cap;
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
-    int cross_group;       // lanes per vehicle in the per-vehicle cross phase: 32, 16 or 8
+    int cross_group;       // lanes per vehicle in the per-vehicle cross phase: 32, 16, 8, 4, 2, or 0 = chosen per tick from the list length
     int pair_cap;          // (vehicle, cross) pairs the flat cross phase can list (0: warp-per-vehicle phase only)
     int cold_level;        // 2: the decision buffers are laid out in the cold region (D)
     int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
@@ -710,7 +710,11 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     } else {
         // a group of G lanes (a whole warp, or a half / quarter of one: links rarely have more than a dozen
         // crosses) per vehicle, one lane per cross; groups of one warp work on different vehicles
-        const int G = Y.cross_group, lane = tid & 31, sl = lane & (G - 1);
+        // cross_group = 0 (default): the widest group that still gives every listed vehicle its own group in
+        // one round -- 16 lanes for up to NT/16 vehicles, 8, 4, then 2
+        int G = Y.cross_group;
+        if (G == 0) G = n_x * 16 <= NT ? 16 : (n_x * 8 <= NT ? 8 : (n_x * 4 <= NT ? 4 : 2));
+        const int lane = tid & 31, sl = lane & (G - 1);
         const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
         for (int e = tid / G; e < n_x; e += NT / G) {
             const int i = c.xlist[e];
@@ -1884,8 +1888,8 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         // vehicle 1.059 / 1.000 / 0.971 ms -> groups of 8 by default, TSC_B200_FLAT_CROSS=1 selects the pair list
         const char *flat = getenv("TSC_B200_FLAT_CROSS");
         if (!flat || atoi(flat) == 0) E->Y.pair_cap = 0;
-        E->Y.cross_group = 8;
-        if (const char *env = getenv("TSC_B200_CROSS_GROUP")) { int v = atoi(env); if (v == 4 || v == 8 || v == 16 || v == 32) E->Y.cross_group = v; }
+        E->Y.cross_group = 0;      // adaptive
+        if (const char *env = getenv("TSC_B200_CROSS_GROUP")) { int v = atoi(env); if (v == 0 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) E->Y.cross_group = v; }
         E->Y.prefetch_next = 1;
         if (const char *env = getenv("TSC_B200_PREFETCH")) E->Y.prefetch_next = atoi(env) != 0;
     }

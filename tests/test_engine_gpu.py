@@ -93,7 +93,8 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({"TSC_B200_FLAT_CROSS": "1"}, 600, (192, 2)),       # flat (vehicle, cross) pair list instead of lane groups per vehicle
     ({"TSC_B200_CROSS_GROUP": "32"}, 600, (192, 2)),     # a whole warp per vehicle in the cross phase
     ({"TSC_B200_CROSS_GROUP": "16"}, 600, (192, 2)),
-    ({"TSC_B200_CROSS_GROUP": "4"}, 600, (192, 2)),
+    ({"TSC_B200_CROSS_GROUP": "8"}, 600, (192, 2)),
+    ({"TSC_B200_CROSS_GROUP": "2"}, 600, (192, 2)),
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0)),     # per-vehicle template look-up although the scenario has one template
     ({"TSC_B200_PREFETCH": "0"}, 600, (192, 2)),
     ({"TSC_B200_HYBRID": "0"}, 600, (256, 0)),
