@@ -97,6 +97,7 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({"TSC_B200_CROSS_GROUP": "2"}, 600, (192, 2)),
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0)),     # per-vehicle template look-up although the scenario has one template
     ({"TSC_B200_PREFETCH": "0"}, 600, (192, 2)),
+    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (192, 2)),      # plain vector copies instead of cp.async for staging
     ({"TSC_B200_HYBRID": "0"}, 600, (256, 0)),
     ({}, 2000, (256, 3)),                                # large replica: decision buffers in the global workspace buy a second block per SM
     ({"TSC_B200_THREADS": "512"}, 2000, (512, 0)),       # one block per SM, everything in shared memory
