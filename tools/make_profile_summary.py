@@ -72,7 +72,7 @@ json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "source": f"profiles/{tag
           open(os.path.join(P, "traffic.json"), "w"))
 alg = bench["roofline"]["algorithmic_bytes_per_env_step"] * bench["roofline"]["units_per_launch"]
 with open(os.path.join(P, f"{tag}_ncu_step_kernel.md"), "w") as f:
-    f.write(f"# ncu --set full, tsc_step_kernel, launches 450-451 of `bench.py --steps 500 --warmup 5` "
+    f.write(f"# ncu --set full, tsc_step_kernel, launch(es) from step 450 of `bench.py --steps 452..500 --warmup 5 --no-cpu-baseline` "
             f"(Hangzhou 4x4, B=4096, kernel {bench['config']['kernel']})\n\n"
             "Cold-cache, serialised replays: use shares and ratios, not absolute times.\n\n" + "\n".join(lines) + "\n\n"
             f"DRAM traffic per launch: {', '.join(f'{t / 1e6:.1f} MB' for t in tr)} (= {sum(tr) / len(tr) / 4096 / 1e3:.1f} KB per replica); "
