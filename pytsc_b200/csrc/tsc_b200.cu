@@ -110,7 +110,7 @@ struct Layout {
     int async_stage;       // 1: cp.async staging of the image columns (TSC_B200_ASYNC_STAGE)
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
     int cross_group;       // lanes per vehicle in the per-vehicle cross phase: 32, 16, 8, 4, 2, or 0 = chosen per tick from the list length
-    int pair_cap;          // (vehicle, cross) pairs the flat cross phase can list (0: warp-per-vehicle phase only)
+    int pair_cap;          // (vehicle, cross) pairs the optional flat cross phase can list (0, the default: lane groups per vehicle)
     int cold_level;        // 2: the decision buffers are laid out in the cold region (D)
     int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
     // persistent part: identical byte offsets in the HBM image and in shared memory
@@ -657,10 +657,10 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     // ---- getAction, phase 2: Cross::canPass for every cross ahead of every deferred vehicle.  canPass
     //      has no side effects, so all crosses are evaluated at once and the first refusal in link order
     //      is the sequential scan of A.5(iii).
-    //      Flat form: one thread per (vehicle, cross) pair listed by 1c, the first refusal found by an
-    //      atomicMin on (cross position in the link << 16 | announced vehicle), then one thread per
-    //      vehicle commits.  Fallback (register-staged variant, or more pairs than the list holds):
-    //      one warp per vehicle, one lane per cross. ----
+    //      Optional flat form (TSC_B200_FLAT_CROSS=1): one thread per (vehicle, cross) pair listed by 1c, the
+    //      first refusal found by an atomicMin on (cross position in the link << 16 | announced vehicle),
+    //      then one thread per vehicle commits.  Default (and the flat form's fallback when the list
+    //      overflows): a group of lanes per vehicle, one lane per cross, group width chosen per tick. ----
     const int n_x = c.h->n_x;
     if (!STAGED && Y.pair_cap > 0 && c.h->n_pairs <= Y.pair_cap) {
         const int n_pairs = c.h->n_pairs;
@@ -1906,8 +1906,8 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         int max_cross = 0;
         for (int k = 0; k < K; ++k) max_cross = std::max(max_cross, s->ll_cross_off[k + 1] - s->ll_cross_off[k]);
         if (max_cross > 255) E->Y.pair_cap = 0;
-        // measured on the bench workload (192 x 4): flat pair list 1.010 ms, groups of 32 / 16 / 8 lanes per
-        // vehicle 1.059 / 1.000 / 0.971 ms -> groups of 8 by default, TSC_B200_FLAT_CROSS=1 selects the pair list
+        // measured on the bench workload (192 x 4): flat pair list 1.010 ms, groups of 32 / 16 / 8 lanes per vehicle
+        // 1.059 / 1.000 / 0.971 ms, width chosen per tick 0.923 ms (default); TSC_B200_FLAT_CROSS=1 selects the pair list
         const char *flat = getenv("TSC_B200_FLAT_CROSS");
         if (!flat || atoi(flat) == 0) E->Y.pair_cap = 0;
         E->Y.cross_group = 0;      // adaptive
