@@ -209,9 +209,24 @@ __device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, 
 // division and put back after it: the quotient of a zero numerator is that zero, bit for bit.
 __device__ __forceinline__ double div_pos(double x, double y) {
     const bool zero = x == 0.0;
+#ifdef TSC_DIV_POS_BARRIER
+    // Found at the end of round 1 (SASS of the final build): the optimiser proves the substitution below dead
+    // and divides x itself, so the slow path still runs for zero numerators (1.0 M calls = 14 % of the executed
+    // instructions per launch).  An empty asm makes the value opaque.  Build with -DTSC_DIV_POS_BARRIER to
+    // measure it (not measured yet: the round's GPU time was spent); DIV_POS_HOT then covers three more sites.
+    double xs = zero ? 1.0 : x;
+    asm volatile("" : "+d"(xs));
+    return zero ? x : xs / y;
+#else
     const double q = (zero ? 1.0 : x) / y;
     return zero ? x : q;
+#endif
 }
+#ifdef TSC_DIV_POS_BARRIER
+#define DIV_POS_HOT(x, y) div_pos((x), (y))
+#else
+#define DIV_POS_HOT(x, y) ((x) / (y))
+#endif
 
 // dL > 0 (a deceleration the caller knows to be positive: a template's maxNegAcc, or v - vL > 0)
 __device__ __forceinline__ double no_collision_speed(double vL, double dL, double vF, double a, double half_over_a, double gap,
@@ -252,7 +267,7 @@ __device__ double stop_before_speed(const double *T, double v, double distance) 
 }
 
 __device__ __forceinline__ bool can_yield(const double *T, double v, double dist) {
-    double minBrake = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC];
+    double minBrake = DIV_POS_HOT(0.5 * v * v, T[TSC_T_MAX_NEG_ACC]);
     return (dist > 0 && minBrake < dist - T[TSC_T_YIELD_DIST]) || (dist < 0 && dist + T[TSC_T_LEN] < 0);
 }
 
@@ -415,7 +430,7 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
     const double dt = DT;
     ns = max2(ns, v - T[TSC_T_MAX_NEG_ACC] * dt);
     double delta;
-    if (ns < 0) { delta = 0.5 * v * v / T[TSC_T_MAX_NEG_ACC]; ns = 0; }
+    if (ns < 0) { delta = DIV_POS_HOT(0.5 * v * v, T[TSC_T_MAX_NEG_ACC]); ns = 0; }
     else delta = (v + ns) * dt / 2;
     double nx = delta + x;
     int q = rp, dd = d, hops = 0;
@@ -622,7 +637,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 enter = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
             }
             if (!ll_available(c, ll) || !enter) {
-                if (0.5 * v * v / T[TSC_T_MAX_NEG_ACC] > dlen - x) {
+                if (DIV_POS_HOT(0.5 * v * v, T[TSC_T_MAX_NEG_ACC]) > dlen - x) {
                     // cannot stop before the line any more
                 } else {
                     vi = min2(vi, stop_before_speed(T, v, dlen - x));
