@@ -1183,6 +1183,7 @@ int cfo_set_tl_phase(void *h, const char *id, int phase) {
 int cfo_set_tl_phase_idx(void *h, int inter, int phase) {
     auto *e = (Engine *) h;
     if (inter < 0 || inter >= (int) e->intersections.size()) return -1;
+    if (phase < 0 || phase >= (int) e->intersections[inter]->phases.size()) return -1;
     e->intersections[inter]->curPhase = phase;
     return 0;
 }

@@ -216,7 +216,8 @@ class Engine:
         self._L.cfo_next_steps(self._h, int(n))
 
     def set_tl_phase_idx(self, inter_index, phase):
-        self._L.cfo_set_tl_phase_idx(self._h, int(inter_index), int(phase))
+        if self._L.cfo_set_tl_phase_idx(self._h, int(inter_index), int(phase)) != 0:
+            raise RuntimeError(f"set_tl_phase_idx({inter_index}, {phase}) rejected")
 
     def get_finished_vehicle_count(self):
         return self._L.cfo_get_finished_count(self._h)

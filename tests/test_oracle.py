@@ -34,7 +34,7 @@ def test_engine_reproduces_golden_snapshots(case):
                 assert np.array_equal(s[k], g[f"snap{t}_{k}"]), (case, t, k)
 
 
-@pytest.mark.parametrize("name", ["syn_1x1", "hangzhou_4_4"])
+@pytest.mark.parametrize("name", ["syn_1x1", "hangzhou_4_4", "syn_1x3_gaussian", "syn_5x5_oneway", "new_york_arterial"])
 def test_vehicle_conservation_and_travel_time(name):
     cfg, parser, cs = build_scenario(name)
     orc = oracle_engine(cfg)
@@ -42,8 +42,9 @@ def test_vehicle_conservation_and_travel_time(name):
     tick = np.asarray(cs.veh_tick)
     for t in range(900):
         if t % 30 == 0:
-            for i in inter:
-                orc.set_tl_phase_idx(i, 1 + (t // 30) % 8)
+            for a, i in enumerate(inter):
+                n_raw = int(cs.sig_n_raw_phases[a])        # one-way grids have fewer light phases than the 9 of a four-way signal
+                orc.set_tl_phase_idx(i, 1 + (t // 30) % (n_raw - 1) if n_raw > 1 else 0)
         orc.next_step()
         if t % 50 == 49:
             created = int((tick <= t).sum())

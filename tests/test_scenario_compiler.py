@@ -7,7 +7,8 @@ import pytest
 
 from helpers import build_scenario
 
-SCENARIOS = ["syn_1x1", "syn_3x3", "hangzhou_4_4", "jinan_3_4", "manhattan_16_3"]
+SCENARIOS = ["syn_1x1", "syn_3x3", "hangzhou_4_4", "jinan_3_4", "manhattan_16_3",
+             "syn_1x3_gaussian", "syn_5x5_oneway", "new_york_arterial"]
 
 
 @pytest.fixture(scope="module", params=SCENARIOS)
