@@ -1,0 +1,23 @@
+#!/bin/bash
+# compute-sanitizer racecheck + memcheck over every kernel variant (run on the GPU box via gpurun).
+# Logs: gpurun_out/sanitizer/<tool>__<variant>.log ; summary: gpurun_out/sanitizer/summary.txt
+out=gpurun_out/sanitizer; mkdir -p $out; : > $out/summary.txt
+run() {   # name, env assignments, args...
+  name=$1; envs=$2; shift 2
+  for tool in racecheck memcheck; do
+    log=$out/${tool}__${name}.log
+    ( env $envs timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_case.py "$@" ) > $log 2>&1
+    rc=$?
+    echo "$tool $name rc=$rc :: $(grep -E 'sanitize_case ok' $log | head -1 | cut -c1-160) :: $(grep -E 'RACECHECK SUMMARY|ERROR SUMMARY' $log | tail -1)" >> $out/summary.txt
+  done
+}
+run hyb1_192x4        "X=1" --capacity 600
+run plain_192x4       "X=1" --capacity 520
+run t256x3            "TSC_B200_THREADS=256" --capacity 600
+run hyb2_256          "X=1" --capacity 2000
+run t512              "TSC_B200_THREADS=512" --capacity 2000
+run ctl_greedy        "X=1" --capacity 600 --controller greedy
+run ctl_max_pressure  "X=1" --capacity 600 --controller max_pressure --obs position_matrix
+run ctl_sotl          "X=1" --capacity 600 --controller sotl
+run flat_cross        "TSC_B200_FLAT_CROSS=1" --capacity 600
+cat $out/summary.txt
