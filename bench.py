@@ -2,33 +2,45 @@
 """bench.py -- agent-steps/s of the batched traffic-signal-control env-step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config hangzhou|jinan|manhattan|grid16] [--fast-forward F]
 
-One "step" = one ``TrafficSignalNetwork.step`` for every replica: phase program
-(fixed-time controller, green 25 s), delta_time = 5 engine ticks, Retriever
-reductions, per-signal stats, pressure reward, action mask and lane-feature
-observations -- a single launch of ``tsc_step_kernel`` through the C ABI.
-Workload: BASELINE.json configs[1], Hangzhou 4x4 (16 signals, 240 lanes, 576
-lane-links, 2983 vehicles/h), max_pressure reward, B = 4096 replicas per GPU.
+One "step" = one ``TrafficSignalNetwork.step`` for every replica: phase program (fixed-time controller, green
+25 s), delta_time = 5 engine ticks, Retriever reductions, per-signal stats, reward, action mask and
+lane-feature observations -- a single launch of ``tsc_step_kernel`` through the C ABI.
 
-Prints ONE JSON line (rank 0).  ``value``: device-resident throughput, CUDA
-events on the launching stream around every launch, L2 flushed between
-launches, max over ranks.  ``e2e``: the same metric through ``tsc_env_step_host``
-with pinned HOST buffers (actions in; observations, rewards, masks out), wall
-clock with a synchronize on both sides.  ``roofline``: algorithmic bytes per
-launch (SURVEY.md 8d formula, with the measured mean vehicle count) over the
-mean launch duration, against MEASURED_PEAKS.json.  ``cpu_baseline``: the CPU
-port (C++ oracle engine + Python port of pytsc's hot path) on all host cores.
+Workloads (``--config``; BASELINE.json ``configs``):
+  hangzhou   configs[1]  Hangzhou 4x4, max_pressure reward, B = 4096 replicas per GPU          (default: the metric's config)
+  jinan      configs[2]  Jinan 3x4, queue reward, through the batched EPyMARL wrapper, B = 2048 per GPU (16384 over 8)
+  grid16     configs[3]  generated 16x16 grid (256 signals), 900 veh/h/road, B = 128 per GPU (1024 over 8)
+  manhattan  configs[4]  Manhattan 16x3 (48 signals), 3600 s horizon, B = 4096 per GPU
 
-``--impl reference`` times only that CPU port (the reference's engine,
-CityFlow, is a third-party module that cannot be installed here).
+Both arms are measured in the LOADED regime: before warm-up every replica is fast-forwarded, untimed, by
+``--fast-forward`` env-steps (default 360 = tick 1800 of the simulated hour) under the same controller; the
+reference arm fast-forwards its engines likewise.  ``config.mean_running_vehicles`` reports the load.
+
+Prints ONE JSON line (rank 0).
+``value``     device-resident throughput: CUDA events on the launching stream around every launch, L2 flushed
+              (256 MiB write) between launches, max over ranks.
+``e2e``       the same metric through the public host API (``BatchedTrafficSignalNetwork.step_host`` ->
+              ``tsc_env_step_registered``): host policy (numpy) -> actions from page-locked host memory H2D -> ONE
+              launch whose replica blocks store compact packets into page-locked host memory -> host threads finish
+              the caller's fp32 observation rows / rewards / masks while the launch runs; wall clock, synchronous.
+``roofline``  algorithmic bytes per launch (SURVEY.md 8d formula with the measured mean vehicle count) over the mean
+              launch duration, against MEASURED_PEAKS.json; ``issue`` = the SM-side bound from the committed ncu capture.
+``cpu_baseline`` / ``--impl reference``: the reference's own Python (``baseline/_ref`` pytsc: TrafficSignalNetwork,
+              CityFlow backend plugin, FixedTimeController driven the way Evaluate.run does) over the C++ oracle engine
+              standing in for the absent ``cityflow`` module, one process per host core
+              (kind "reference-python+oracle-engine"); the Python port is the labelled fallback.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,87 +48,226 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SCENARIO = "hangzhou_4_4"
-SCENARIO_KW = dict(
-    cityflow=dict(flow_file="anon_4_4_hangzhou_real.json", flow_rate_type="constant"),
-    signal=dict(observation_space="lane_features", reward_function="max_pressure",
-                action_space="phase_selection", round_robin=False),
-)
 GREEN_TIME = 25
 METRIC = "agent-steps/sec (B=4096 4x4-grid envs)"
+LF = dict(observation_space="lane_features", action_space="phase_selection", round_robin=False)
+
+# name -> workload.  replicas = per GPU; capacity = running vehicles per replica the image is sized for
+# (oracle-measured peak under this controller + margin; exceeding it is reported by eng.check()).
+CONFIGS = {
+    "hangzhou": dict(scenario="hangzhou_4_4", label="BASELINE.json configs[1]",
+                     kw=dict(cityflow=dict(flow_file="anon_4_4_hangzhou_real.json", flow_rate_type="constant"),
+                             signal=dict(LF, reward_function="max_pressure")),
+                     replicas=4096, capacity=640, api="BatchedTrafficSignalNetwork"),
+    "jinan": dict(scenario="jinan_3_4", label="BASELINE.json configs[2]: B = 16384 over 8 GPUs = 2048 per GPU",
+                  kw=dict(cityflow=dict(flow_rate_type="constant"), signal=dict(LF, reward_function="queue_length")),
+                  replicas=2048, capacity=1150, api="BatchedEPyMARLTrafficSignalNetwork"),
+    "manhattan": dict(scenario="manhattan_16_3", label="BASELINE.json configs[4]: 3600 s horizon",
+                      kw=dict(cityflow=dict(flow_rate_type="constant", episode_limit=3600), signal=dict(LF, reward_function="queue_length")),
+                      replicas=4096, capacity=1560, api="BatchedTrafficSignalNetwork"),
+    "grid16": dict(scenario=None, label="BASELINE.json configs[3]: 16x16 grid, 900 veh/h/road, B = 1024 over 8 GPUs = 128 per GPU",
+                   kw=dict(cityflow=dict(flow_rate_type="constant"), signal=dict(LF, reward_function="max_pressure")),
+                   replicas=128, capacity=24000, api="BatchedTrafficSignalNetwork"),
+}
+
+
+def workload(name):
+    w = dict(CONFIGS[name])
+    w["name"] = name
+    if w["scenario"] is None:      # generated grid (the reference shells out to CityFlow's generator, grid_generator.py:39-73)
+        from pytsc_b200.generators import write_grid_scenario
+        w["scenario"] = write_grid_scenario(tempfile.mkdtemp(prefix="grid16_"), 16, 16, vehicles_per_hour_per_road=900,
+                                            horizon=3600, seed=0)
+    return w
+
+
+def build_hash():
+    from pytsc_b200 import _build
+    return _build.source_hash()[:16]
 
 
 # ---------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    """One process: fixed-time control of one Hangzhou replica for `n_steps` env-steps
-    through the full port (step + mask + observations + local rewards)."""
-    n_steps, engine_only = args
-    from oracle.pytsc_port import PortEnv
-    env = PortEnv(SCENARIO, **SCENARIO_KW)
+def materialise_reference_scenario(w, root):
+    """Write the workload's roadnet / flow as CityFlow JSON plus a config.yaml the way the reference lays its
+    scenarios out (scenarios/cityflow/<name>/), under ``root``: baseline/_ref ships code only."""
+    import shutil
+    import yaml
+    from pytsc_b200 import bundle
+    from pytsc_b200.backend.config import Config
+    cfg = Config(w["scenario"], **w["kw"])
+    name = os.path.basename(os.path.normpath(str(w["scenario"])))
+    d = os.path.join(root, "cityflow", name)
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "roadnet.json"), "w") as f:
+        json.dump(bundle.load_roadnet(cfg.cityflow_roadnet_file), f)
+    with open(os.path.join(d, "flow.json"), "w") as f:
+        json.dump(bundle.load_flow(cfg.create_and_save_cityflow_cfg()), f)
+    y = {"cityflow": {k: v for k, v in cfg.simulator.items() if k not in ("roadnet_file", "flow_file", "flow_files")},
+         "signal": dict(cfg.signal)}
+    y["cityflow"].update(roadnet_file="roadnet.json", flow_file="flow.json", flow_rate_type="constant",
+                         roadnet_log_file="roadnet_log_file.json", replay_log_file="replay_log_file.txt", save_replay=False)
+    with open(os.path.join(d, "config.yaml"), "w") as f:
+        yaml.safe_dump(y, f)
+    import pytsc
+    os.makedirs(os.path.join(root, "default"), exist_ok=True)
+    shutil.copy(os.path.join(os.path.dirname(pytsc.__file__), "scenarios", "default", "config.yaml"),
+                os.path.join(root, "default", "config.yaml"))
+    return name
+
+
+def _reference_python_worker(args):
+    """One process: the UNMODIFIED reference stack (baseline/_ref pytsc) on one replica -- TrafficSignalNetwork with the
+    CityFlow backend plugin, FixedTimeController objects driven as controllers/evaluate.py:112-137 does -- over the oracle
+    engine as ``cityflow.Engine``.  Modes: "step" = network.step + mask + observations + local rewards per env-step (what
+    an RL loop pulls); "evaluate" = Evaluate.run's own loop body (_get_actions recomputes all observations per agent)."""
+    w, n_ff, n_steps, mode = args
+    import logging
+    from pytsc_b200 import compat
+    from oracle.engine import Engine as OracleEngine
+    compat.install_stubs(engine_factory=OracleEngine)
+    where = compat.find_reference_pytsc()
+    if where is None:
+        raise RuntimeError("reference pytsc not importable")
+    logging.disable(logging.CRITICAL)
+    import pytsc
+    import pytsc.backends.cityflow.config as cf_config
+    import pytsc.common.config as base_config
+    root = tempfile.mkdtemp(prefix="tsc_refscn_")
+    name = materialise_reference_scenario(w, root)
+    base_config.CONFIG_DIR = root                               # where the reference looks scenarios up
+    cf_config.CONFIG_DIR = os.path.join(root, "cityflow")
+    kw = {k: dict(v) for k, v in w["kw"].items()}
+    kw.get("cityflow", {}).pop("flow_file", None)
+    net = pytsc.TrafficSignalNetwork(name, "cityflow", **kw)
+    for ts in net.traffic_signals.values():
+        ts.init_rule_based_controllers(green_time=GREEN_TIME)
+
+    def actions():
+        if mode == "evaluate":      # evaluate.py:112-124
+            acts = []
+            for ts in net.traffic_signals.values():
+                net.get_observations()
+                acts.append(ts.get_controller_action("fixed_time", inp=net.simulator.step_measurements))
+            return acts
+        return [ts.get_controller_action("fixed_time", inp=net.simulator.step_measurements) for ts in net.traffic_signals.values()]
+
+    def one():
+        net.step(actions())
+        if mode != "evaluate":
+            net.get_action_mask(); net.get_observations(); net.get_rewards()
+
+    for _ in range(n_ff):          # untimed fast-forward into the loaded regime
+        net.step(actions())
     t0 = time.perf_counter()
-    if engine_only:
+    for _ in range(n_steps):
+        one()
+    dt = time.perf_counter() - t0
+    return dt, len(net.traffic_signals), net.simulator.step_measurements["sim"]["n_vehicles"]
+
+
+def _port_worker(args):
+    """Fallback: the same loop through oracle/pytsc_port.py (restatement of the reference's Python half)."""
+    w, n_ff, n_steps, mode = args
+    from oracle.pytsc_port import PortEnv
+    env = PortEnv(w["scenario"], **w["kw"])
+    for _ in range(n_ff):
+        env.step(env.fixed_time_actions(GREEN_TIME))
+    t0 = time.perf_counter()
+    if mode == "engine":
         for _ in range(n_steps):
             env.engine.next_steps(5)
     else:
         for _ in range(n_steps):
-            acts = env.fixed_time_actions(GREEN_TIME)
-            env.step(acts)
-            env.get_action_mask()
-            env.get_observations()
-            env.get_rewards()
-    return time.perf_counter() - t0, env.n_agents, env.step_measurements["sim"]["n_vehicles"] if not engine_only else 0
+            env.step(env.fixed_time_actions(GREEN_TIME))
+            env.get_action_mask(); env.get_observations(); env.get_rewards()
+    return time.perf_counter() - t0, env.n_agents, env.engine.get_vehicle_count()
 
 
-def cpu_port_throughput(n_steps, procs=None, engine_only=False):
+def cpu_throughput(w, n_ff, n_steps, mode="step", procs=None, kind="reference"):
     """Sum of agent-steps/s over `procs` independent processes (one per host core)."""
     import multiprocessing as mp
     procs = procs or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
+    fn = _reference_python_worker if kind == "reference" else _port_worker
     with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(n_steps, engine_only)] * procs)
+        res = pool.map(fn, [(w, n_ff, n_steps, mode)] * procs)
     agents = res[0][1]
-    total = sum(agents * n_steps / r[0] for r in res)
-    return total, procs, max(r[0] for r in res)
+    return dict(value=sum(agents * n_steps / r[0] for r in res), cores=procs, wall=max(r[0] for r in res),
+                vehicles=float(sum(r[2] for r in res)) / len(res))
 
 
-def cpu_baseline_block(n_steps):
+def reference_kind():
+    """"reference" when the reference package (baseline/_ref) imports on this box, else "port"."""
+    try:
+        from pytsc_b200 import compat
+        if compat.find_reference_pytsc() is not None:
+            return "reference"
+    except Exception:
+        pass
+    return "port"
+
+
+def probe_cityflow():
+    import importlib.util
+    try:
+        return importlib.util.find_spec("cityflow") is not None
+    except Exception:
+        return False
+
+
+def cpu_baseline_block(w, n_ff, n_steps):
     from oracle import engine as oracle_engine
     oracle_engine.build()
-    v, cores, wall = cpu_port_throughput(n_steps)
-    ve, _, _ = cpu_port_throughput(n_steps, engine_only=True)
-    return {
-        "value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-        "sample": f"{cores} processes x {n_steps} env-steps ({5 * n_steps} s simulated) of {SCENARIO}, fixed-time, "
-                  f"step+mask+obs+rewards through the Python port over the C++ oracle engine; {wall:.1f} s wall",
-        "engine_only_value": ve,
-        "engine_only_note": "same processes, C++ oracle engine ticks only (no pytsc Python glue)",
-    }
+    kind = reference_kind()
+    r = cpu_throughput(w, n_ff, n_steps, "step", kind=kind)
+    label = "reference-python+oracle-engine" if kind == "reference" else "port"
+    out = {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"], "kind": label,
+           "sample": f"{r['cores']} processes x {n_steps} env-steps after {n_ff} untimed fast-forward steps of {w['name']}, fixed-time "
+                     f"green {GREEN_TIME} s: network.step + action mask + observations + local rewards per step, "
+                     + ("the unmodified reference Python (baseline/_ref) over the C++ oracle engine as cityflow.Engine"
+                        if kind == "reference" else "the Python port over the C++ oracle engine")
+                     + f"; {r['wall']:.1f} s wall; mean running vehicles at the end {r['vehicles']:.0f}",
+           "real_cityflow_importable": probe_cityflow()}
+    if kind == "reference":
+        ev = cpu_throughput(w, n_ff, max(8, n_steps // 4), "evaluate", kind=kind)
+        out["evaluate_run_value"] = ev["value"]
+        out["evaluate_run_note"] = ("Evaluate.run's own loop body (controllers/evaluate.py:71-95,112-124: observations "
+                                    "recomputed once per agent inside _get_actions), same processes")
+    eng = cpu_throughput(w, n_ff, n_steps, "engine", kind="port")
+    out["engine_only_value"] = eng["value"]
+    out["engine_only_note"] = "C++ oracle engine ticks only (no pytsc Python), same process count"
+    return out
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = max(8, min(720, args.steps))
-    # warm-up: build the oracle, import, page in
+    w = workload(args.config)
+    n = max(8, min(360, args.steps))
     from oracle import engine as oracle_engine
     oracle_engine.build()
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_throughput(8)
-    t0 = time.perf_counter()
-    v, cores, wall = cpu_port_throughput(n)
+    kind = reference_kind()
+    if args.warmup:
+        cpu_throughput(w, 0, 4, "step", kind=kind)       # imports, page-in
+    r = cpu_throughput(w, args.fast_forward, n, "step", kind=kind)
+    label = "reference-python+oracle-engine" if kind == "reference" else "port"
+    sample = (f"{r['cores']} processes x {n} env-steps of {w['name']} after {args.fast_forward} untimed fast-forward steps; "
+              + ("unmodified reference Python (baseline/_ref) over the C++ oracle engine as cityflow.Engine"
+                 if kind == "reference" else "Python port over the C++ oracle engine")
+              + " (CityFlow itself is not installable: real_cityflow_importable below)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "agent-steps/s", "n_gpus": args.gpus,
-        "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 * wall / n, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "agent-steps/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 * r["wall"] / n, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{SCENARIO}: 16 signals, max_pressure reward, lane_features obs, fixed-time green {GREEN_TIME} s",
-                   "replicas": cores, "parallelism": f"{cores} host processes"},
-        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} processes x {n} env-steps of {SCENARIO} through the Python port over the C++ "
-                                   f"oracle engine (CityFlow itself is not installable)"},
-        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{w['name']} ({w['label']}): fixed-time green {GREEN_TIME} s, step + mask + observations + rewards",
+                   "replicas": r["cores"], "parallelism": f"{r['cores']} host processes", "fast_forward_steps": args.fast_forward,
+                   "mean_running_vehicles": r["vehicles"]},
+        "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"], "kind": label, "sample": sample,
+                         "real_cityflow_importable": probe_cityflow()},
+        "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -170,9 +321,8 @@ class ClockSampler:
 # the GPU arm
 # ---------------------------------------------------------------------------------------
 def bind_to_gpu_numa_node(index):
-    """Pin this process (and the pinned buffers it is about to allocate) to the CPUs of the GPU's NUMA
-    node, as a multi-socket deployment would per rank: host <-> device copies then stay on the local PCIe
-    root.  Returns (description, previous affinity); silent no-op where the topology is not exposed."""
+    """Pin this process (and the buffers it is about to allocate) to the CPUs of the GPU's NUMA node, as a multi-socket
+    deployment would per rank.  Returns (description, previous affinity); silent no-op where the topology is not exposed."""
     try:
         if os.environ.get("BENCH_NO_AFFINITY"):
             return "unchanged (BENCH_NO_AFFINITY)", None
@@ -196,12 +346,12 @@ def bind_to_gpu_numa_node(index):
 
 
 class HostFixedTimePolicy:
-    """FixedTimeController.get_action (controllers/controllers.py:39-54) for all B x A signals on the
-    host, with its own copy of the programs' state: the e2e leg's stand-in for a user's policy.
+    """FixedTimeController.get_action (controllers/controllers.py:39-54) for all B x A signals on the host, with its own
+    copy of the programs' state: the e2e leg's stand-in for a user's policy.
 
-    The controller is a finite-state machine per signal -- state = (current phase index, time on phase in
-    units of delta_time, saturating) -- so the whole B x A batch advances with two table look-ups per
-    step (action, next state).  tests/test_port.py checks it against the rule written out."""
+    The controller is a finite-state machine per signal -- state = (signal, current phase index, time on phase in units of
+    delta_time, saturating) -- so the whole B x A batch advances with two table look-ups per step (action, next state).
+    tests/test_port.py checks it against the rule written out."""
     T = 64      # time-on-phase slots per phase (saturating: beyond green_time nothing changes)
 
     def __init__(self, sig_phase_green, sig_n_phases, B, A, green_time, n_ticks):
@@ -211,7 +361,7 @@ class HostFixedTimePolicy:
         P, T = green.shape[1], self.T
         assert green_time < (T - 1) * n_ticks
         nph = np.asarray(sig_n_phases, np.int64).reshape(A)
-        nxt_state = np.zeros((A, P * T), np.uint16)
+        nxt_state = np.zeros((A, P * T), np.intp)
         action = np.zeros((A, P * T), np.int32)
         for a in range(A):
             for c in range(int(nph[a])):
@@ -220,21 +370,27 @@ class HostFixedTimePolicy:
                     n = c if stay else (c + 1) % int(nph[a])
                     # BaseTSProgram.update_current_phase (common/traffic_signal.py:94-109): += delta_time or = delta_time
                     nt = min(t + 1, T - 1) if n == c else 1
-                    nxt_state[a, c * T + t] = n * T + nt
+                    nxt_state[a, c * T + t] = a * P * T + n * T + nt        # global table index: one take per step
                     action[a, c * T + t] = n
         self.nxt_state, self.action = nxt_state.ravel(), action.ravel()
-        self.base = (np.arange(A, dtype=np.intp) * (P * T))[None, :]
-        self.state = np.zeros((B, A), np.uint16)
-        self.idx = np.empty((B, A), np.intp)
+        self.state0 = np.ascontiguousarray(np.broadcast_to((np.arange(A, dtype=np.intp) * (P * T))[None, :], (B, A)))
+        self.state = self.state0.copy()
+        self.tmp = np.empty_like(self.state)
 
     def reset(self):
-        self.state.fill(0)
+        self.state[...] = self.state0
+
+    def snapshot(self):
+        return self.state.copy()
+
+    def restore(self, s):
+        self.state[...] = s
 
     def act(self, out):
         np = self.np
-        np.add(self.base, self.state, out=self.idx)
-        np.take(self.action, self.idx, out=out, mode="clip")
-        np.take(self.nxt_state, self.idx, out=self.state, mode="clip")
+        np.take(self.action, self.state, out=out)
+        np.take(self.nxt_state, self.state, out=self.tmp)
+        self.state, self.tmp = self.tmp, self.state
 
 
 def algorithmic_bytes_per_env_step(V, L, K, A, obs_dim, P, n_ticks=5):
@@ -243,15 +399,29 @@ def algorithmic_bytes_per_env_step(V, L, K, A, obs_dim, P, n_ticks=5):
     return n_ticks * (40.0 * V + 8 * (L + K) + 4 * A) + 16 * L + A * (4 * obs_dim + P + 8)
 
 
+def ncu_side_table(name, vbar):
+    """DRAM bytes and executed warp instructions per launch from the committed ncu capture of this workload
+    (profiles/traffic.json, written by tools/make_profile_summary.py) -- only when that capture was taken at a
+    comparable load (mean running vehicles within 15 %); otherwise null: a number measured at another load is not
+    printed beside this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        t = t.get(name, t if name == "hangzhou" and "dram_bytes_per_launch" in t else None)
+        if not t or not t.get("mean_running_vehicles"):
+            return None
+        if abs(t["mean_running_vehicles"] - vbar) > 0.15 * vbar:
+            return None
+        return t
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from pytsc_b200 import _build
-    from pytsc_b200.backend.config import Config
-    from pytsc_b200.backend.network_parser import NetworkParser
-    from pytsc_b200.binding import Engine
-    from pytsc_b200.scenario import compile_scenario
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,30 +436,59 @@ def run_gpu_arm(args):
         _build.build()
     if world > 1:
         dist.barrier()
+    from pytsc_b200 import BatchedEPyMARLTrafficSignalNetwork, BatchedTrafficSignalNetwork
 
-    cfg = Config(SCENARIO, **SCENARIO_KW)
-    parser = NetworkParser(cfg)
-    cs = compile_scenario(cfg, parser)
-    B = args.replicas
-    eng = Engine(cs, B, local, vehicle_capacity=args.vehicle_capacity)
+    w = workload(args.config)
+    B = args.replicas or w["replicas"]
+    cap = args.vehicle_capacity or w["capacity"]
+    kw = {k: dict(v) for k, v in w["kw"].items()}
+    kw["gpu"] = dict(vehicle_capacity=cap)
+    if w["api"] == "BatchedEPyMARLTrafficSignalNetwork":      # config 3: the MARL wrapper's API shape (epymarl.py:96-111)
+        wrapper = BatchedEPyMARLTrafficSignalNetwork(map_name=w["scenario"], simulator_backend="gpu", n_replicas=B, device=local, **kw)
+        env = wrapper.tsc_env
+    else:
+        wrapper = None
+        env = BatchedTrafficSignalNetwork(w["scenario"], n_replicas=B, device=local, **kw)
+    eng, cs, cfg = env.engine, env.scenario, env.config
     A, L, K = eng.A, cs.n_lanes, cs.n_lanelinks
     n_ticks = int(cfg.simulator["delta_time"])
     sim_len_steps = int(cfg.simulator["sim_length"]) // n_ticks
-    names = ["obs", "reward", "reward_global", "mask", "lane_count", "lane_queued", "lane_occupancy",
-             "lane_mean_speed", "sim"]
+    ff = min(args.fast_forward, sim_len_steps - 1)
+    names = ["obs", "reward", "reward_global", "mask", "lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed", "sim"]
     bufs = eng.alloc_outputs(names)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     vsum = torch.zeros((), dtype=torch.float64, device="cuda")
+    policy = HostFixedTimePolicy(cs.sig_phase_green, cs.sig_n_phases, B, A, GREEN_TIME, n_ticks)
+    act_pinned = torch.zeros((B, A), dtype=torch.int32, pin_memory=True)
+    act_np = act_pinned.numpy()
     state = {"step": 0}
 
-    def restart():
-        eng.reset()
-        eng.init_program(0)
-        state["step"] = 0
+    # ---- untimed fast-forward into the loaded regime; the state (and the host policy's) is kept for both legs ----------
+    eng.reset()
+    eng.init_program(0)
+    policy.reset()
+    for _ in range(ff):
+        eng.env_step(None, None, n_ticks=n_ticks, controller=1, controller_arg=GREEN_TIME)
+        policy.act(act_np)
+    torch.cuda.synchronize()
+    eng.check()
+    loaded_state = eng.save_state(device=True)
+    loaded_policy = policy.snapshot()
+
+    def restart(from_loaded):
+        if from_loaded:
+            eng.load_state(loaded_state)
+            policy.restore(loaded_policy)
+            state["step"] = ff
+        else:                                   # simulator.is_terminated -> a new engine at tick 0 (pytsc/__init__.py:164-176)
+            eng.reset()
+            eng.init_program(0)
+            policy.reset()
+            state["step"] = 0
 
     def one_step():
-        if state["step"] == sim_len_steps:      # simulator.is_terminated -> restart (pytsc/__init__.py:164-176)
-            restart()
+        if state["step"] == sim_len_steps:
+            restart(False)
         eng.env_step(None, bufs, n_ticks=n_ticks, controller=1, controller_arg=GREEN_TIME)
         state["step"] += 1
 
@@ -300,7 +499,7 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
 
     # ---- device-resident leg ----------------------------------------------------------
-    restart()
+    restart(True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -327,38 +526,29 @@ def run_gpu_arm(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     vbar = float(vsum.item()) / (args.steps * B)
     final_tick = int(eng.counters()["tick"][0])
+    sim_end = bufs["sim"].clone()
 
-    # ---- end-to-end leg: host actions in, host observations / rewards / masks out ----------
-    pin = dict(pin_memory=True)
-    h_act = torch.zeros((B, A), dtype=torch.int32, **pin)
-    h_obs = torch.empty((B, A, eng.dims["obs_dim"]), dtype=torch.float32, **pin)
-    h_rew = torch.empty((B, A), dtype=torch.float32, **pin)
-    h_mask = torch.empty((B, A, eng.dims["n_actions"]), dtype=torch.uint8, **pin)
-    h_rg = torch.empty((B,), dtype=torch.float32, **pin)
-    policy = HostFixedTimePolicy(cs.sig_phase_green, cs.sig_n_phases, B, A, GREEN_TIME, n_ticks)
-    act_np = h_act.numpy()
-
-    def host_policy():
-        policy.act(act_np)
-
-    def e2e_restart():
-        restart()
-        policy.reset()
-        torch.cuda.synchronize()
-
+    # ---- end-to-end leg: the public host API ------------------------------------------------------------------
+    # host policy -> actions (page-locked host memory) -> step_host -> observation rows, rewards, masks, global
+    # reward in HOST numpy arrays, every step, synchronous
+    host_out = env.register_host_buffers()
     policy_s = [0.0]
 
     def e2e_step():
         if state["step"] == sim_len_steps:
-            e2e_restart()
+            restart(False)
         t_p = time.perf_counter()
-        host_policy()
+        policy.act(act_np)
         policy_s[0] += time.perf_counter() - t_p
-        eng.env_step_host(h_act.numpy(), obs=h_obs.numpy(), reward=h_rew.numpy(), mask=h_mask.numpy(),
-                          reward_global=h_rg.numpy(), n_ticks=n_ticks)
+        if wrapper is not None:
+            env.step_host(act_np, controller="phase_index")
+            _ = host_out["reward_global"] / A          # epymarl.py:106-108: common reward = global / n_agents
+        else:
+            env.step_host(act_np, controller="phase_index")
         state["step"] += 1
 
-    e2e_restart()
+    restart(True)
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         e2e_step()
     sync_all()
@@ -371,20 +561,26 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
     e2e_launches = eng.launch_count() - l0
     eng.check()
-    h2d = h_act.numel() * 4
-    d2h = h_obs.numel() * 4 + h_rew.numel() * 4 + h_mask.numel() + h_rg.numel() * 4
-    e2e_reward = float(h_rg.mean())
+    h2d = act_np.nbytes
+    d2h = eng.host_packet_bytes()
+    host_bytes_finished = sum(v.nbytes for v in host_out.values())
+    e2e_reward = float(host_out["reward_global"].mean())
+    # the host arrays must hold what the device leg computed for the same state and actions (both legs ran the same
+    # number of steps from the same state under the same rule)
+    e2e_matches_device = bool(np.array_equal(host_out["obs"], bufs["obs"].cpu().numpy())
+                              and np.array_equal(host_out["reward"], bufs["reward"].cpu().numpy())
+                              and np.array_equal(host_out["mask"], bufs["mask"].cpu().numpy()))
 
     # ---- max over ranks; episode metrics all-reduced once (the only collective) ----------
     t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device="cuda")
-    sim = bufs["sim"]
-    epi = torch.stack([sim[:, 1].sum(), sim[:, 3].sum(), vsum, torch.tensor(float(B), device="cuda", dtype=torch.float64)])
+    epi = torch.stack([sim_end[:, 1].sum(), sim_end[:, 3].sum(), vsum, torch.tensor(float(B), device="cuda", dtype=torch.float64)])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(epi, op=dist.ReduceOp.SUM)
     dev_ms, e2e_s, t_wall = [float(x) for x in t.tolist()]
     info = eng.kernel_info()
-    eng.close()
+    host_threads = os.environ.get("TSC_B200_HOST_THREADS", "auto")
+    env.close()
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -404,32 +600,39 @@ def run_gpu_arm(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     launch_ms = dev_ms / args.steps
     achieved = alg * B / (launch_ms / 1e3) / 1e9          # per GPU: one launch handles this rank's B replicas
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    side = ncu_side_table(w["name"], vbar)
+    issue = None
+    if side and side.get("inst_executed_per_launch") and clk and clk.get("sm_mhz"):
+        slots = 148 * 4 * clk["sm_mhz"] * 1e6 * (launch_ms / 1e3)       # SM sub-partitions x clock x launch time: one warp instruction each
+        issue = {"warp_instructions_per_launch": side["inst_executed_per_launch"], "issue_slots_per_launch": slots,
+                 "frac": side["inst_executed_per_launch"] / slots, "source": side.get("source")}
     line = {
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{SCENARIO} (BASELINE.json configs[1]): 16 signals, 240 lanes, 576 lane-links, "
-                               f"anon_4_4_hangzhou_real flows, max_pressure reward, lane_features obs, "
-                               f"fixed-time controller green {GREEN_TIME} s, delta_time 5",
+        "config": {"workload": f"{w['name']} ({w['label']}): {A} signals, {L} lanes, {K} lane-links, "
+                               f"{cfg.signal['reward_function']} reward, lane_features obs, fixed-time controller green {GREEN_TIME} s, "
+                               f"delta_time {n_ticks}, through {w['api']}",
                    "replicas_per_gpu": B, "replicas_total": total_B, "parallelism": f"replica-sharded x{world}, no step-path collective",
-                   "l2": "256 MiB flush write between timed launches", "mean_running_vehicles": vbar,
-                   "final_tick": final_tick, "env_steps_per_s": value / A, "engine_ticks_per_s": value / A * n_ticks,
+                   "l2": "256 MiB flush write between timed launches", "fast_forward_steps": ff,
+                   "mean_running_vehicles": vbar, "final_tick": final_tick, "env_steps_per_s": value / A,
+                   "engine_ticks_per_s": value / A * n_ticks, "vehicle_capacity": cap,
                    "kernel": {"name": "tsc_step_kernel", **info}, "wall_s_timed_region": t_wall,
-                   "host_cpu_affinity": affinity},
+                   "host_cpu_affinity": affinity, "build_hash": build_hash()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_env_step": alg, "units_per_launch": B},
+                     "traffic": side.get("dram_bytes_per_launch") if side else None,
+                     "traffic_source": side.get("source") if side else "no ncu capture at this load committed",
+                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg, "units_per_launch": B, "issue": issue},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "mean_global_reward_last_step": e2e_reward,
                 "host_policy_ms_per_step": 1e3 * policy_s[0] / args.steps,
-                "note": "host fixed-time policy (numpy, inside the timed region) -> actions H2D -> chunked launches, "
-                        "observation rows D2H while the next chunk is stepped -> rewards / masks D2H"},
+                "host_result_bytes_per_step": host_bytes_finished, "host_threads": host_threads,
+                "matches_device_leg": e2e_matches_device,
+                "note": "host fixed-time policy (numpy, inside the timed region) -> actions H2D from page-locked memory -> one launch; "
+                        "each replica block stores a compact packet (per-lane queue / occupancy / speed as the row shows them, phase, "
+                        "rewards, action bits) into page-locked host memory and raises a flag; host threads finish the fp32 "
+                        "observation rows, rewards and masks in the caller's numpy arrays while the launch runs (d2h = packet bytes; "
+                        "host_result_bytes = the arrays the caller reads)"},
         "gpu_launches": int(launches),
         "e2e_gpu_launches": int(e2e_launches),
         "clocks": clk,
@@ -438,20 +641,23 @@ def run_gpu_arm(args):
     if world == 1 and not args.no_cpu_baseline:
         if prev_affinity:
             os.sched_setaffinity(0, prev_affinity)      # the CPU baseline gets every host core back
-        line["cpu_baseline"] = cpu_baseline_block(args.cpu_steps)
+        line["cpu_baseline"] = cpu_baseline_block(w, ff, args.cpu_steps)
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=648)
-    ap.add_argument("--warmup", type=int, default=72)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
-    ap.add_argument("--vehicle-capacity", type=int, default=640,
-                    help="running vehicles per replica the shared-memory image is sized for (peak on this workload: 561)")
-    ap.add_argument("--cpu-steps", type=int, default=360, help="env-steps per process of the cpu_baseline sample")
+    ap.add_argument("--config", default="hangzhou", choices=sorted(CONFIGS))
+    ap.add_argument("--fast-forward", type=int, default=360,
+                    help="untimed env-steps before warm-up (both arms): 360 = tick 1800, the loaded regime")
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = the config's)")
+    ap.add_argument("--vehicle-capacity", type=int, default=0,
+                    help="running vehicles per replica the image is sized for (0 = the config's)")
+    ap.add_argument("--cpu-steps", type=int, default=60, help="env-steps per process of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define TSC_ABI_VERSION 2
+#define TSC_ABI_VERSION 3
 
 enum {
     TSC_OK = 0,
@@ -99,14 +99,19 @@ typedef struct tsc_scenario {
     int32_t max_phases;           /* P: row stride of the pytsc phase tables */
     int32_t n_in_total, n_out_total, n_nbr_total;
     int32_t n_ctl_total;          /* length of ctl_in_lane / ctl_out_lane */
+    int32_t n_flow_sets;          /* F >= 1: alternative flow files compiled into this scenario (pytsc's
+                                     cityflow.flow_files with flow_rate_type random / sequential,
+                                     backends/cityflow/config.py:63-76; DisruptedConfig :106-175).  Every replica
+                                     runs one of them, chosen at reset (tsc_reset_flows). */
 
     /* --- engine tables (CityFlow semantics) --- */
     const double  *drv_length;        /* [D] */
     const double  *drv_max_speed;     /* [D] lane-links: 10000 */
     const int32_t *lane_ll_off;       /* [L+1] CSR: lane -> lane-links leaving it (roadnet appearance order) */
     const int32_t *lane_ll;           /* lane-link index 0..K-1 */
-    const int32_t *lane_spawn_off;    /* [L+1] CSR: lane -> vehicles that start on it, FIFO order */
-    const int32_t *lane_spawn_vid;    /* [N] */
+    const int32_t *lane_spawn_off;    /* [F][L+1] CSR per flow set: lane -> vehicles that start on it, FIFO order;
+                                         rows index one shared lane_spawn_vid (row f starts where row f-1 ended) */
+    const int32_t *lane_spawn_vid;    /* [N] vehicle ids (the N vehicles of all flow sets, set-major) */
     const int32_t *ll_start_lane;     /* [K] */
     const int32_t *ll_end_lane;       /* [K] */
     const int32_t *ll_signal;         /* [K] signal (agent) index */
@@ -180,6 +185,9 @@ typedef struct tsc_outputs {
     double  *sim;               /* [B][4] n_vehicles, average_travel_time, time_step, n_finished (retriever.py:101-112) */
     double  *metrics;           /* [B][8] n_queued, mean_speed, mean_delay, density, pressure, network_flow,
                                           flickering_signal, norm_mean_speed  (backends/cityflow/metrics.py:221-232) */
+    int32_t *err;               /* [B] sticky error bits of the replica (0 = healthy; 1 | 4 vehicle capacity exceeded,
+                                       2 FIFO order lost, 8 bad light phase): a replica with a bit set is frozen and its
+                                       rows are stale -- the same bits tsc_check reports, readable without a sync */
 } tsc_outputs_t;
 
 typedef struct tsc_engine *tsc_handle;
@@ -199,13 +207,21 @@ int  tsc_get_dims(tsc_handle h, int32_t *n_replicas, int32_t *n_lanes, int32_t *
                   int32_t *obs_dim, int32_t *state_dim, int32_t *n_actions,
                   int32_t *n_in_total, int32_t *n_out_total, int32_t *visibility);
 
-/* All replicas back to tick 0, empty network, light phase 0, program state cleared. */
+/* All replicas back to tick 0, empty network, light phase 0, program state cleared; every replica keeps
+ * the flow set it was last given (0 after tsc_create). */
 int  tsc_reset(tsc_handle h, void *stream);
+
+/* The same, and replica b restarts on flow set flow_set_per_replica[b] (host int32 [B], each in
+ * [0, n_flow_sets)): what a new cityflow.Engine built on a newly drawn flow file is to the reference
+ * (pytsc/__init__.py:164-176 -> backends/cityflow/config.py:63-76, per replica).  NULL = keep. */
+int  tsc_reset_flows(tsc_handle h, const int32_t *flow_set_per_replica, void *stream);
 
 /* Selected replicas back to tick 0 (as tsc_reset does for all of them), e.g. the replicas whose
  * episode has ended while the others run on.  replicas: host int32 [n], indices in [0, B).  The
  * caller re-applies tsc_init_program / phases as after tsc_reset.  Ordered on `stream`. */
 int  tsc_reset_replicas(tsc_handle h, const int32_t *replicas, int32_t n, void *stream);
+/* The same with a new flow set for each of them (host int32 [n]; NULL = keep). */
+int  tsc_reset_replicas_flows(tsc_handle h, const int32_t *replicas, const int32_t *flow_sets, int32_t n, void *stream);
 
 /* Engine state snapshot / restore -- the batched counterpart of CityFlow's engine.snapshot() /
  * engine.load(archive) (cityflow.Engine API; pytsc's save_replay / mid-episode restarts).
@@ -258,6 +274,27 @@ int  tsc_controller_act(tsc_handle h, int32_t controller, int32_t controller_arg
 int  tsc_env_step_host(tsc_handle h, const int32_t *actions_host, int32_t controller, int32_t controller_arg,
                        int32_t n_ticks, float *obs_host, float *reward_host, uint8_t *mask_host,
                        float *reward_global_host);
+
+/* Registered end-to-end path.  tsc_host_register takes the caller's HOST result buffers once (ordinary
+ * or page-locked memory, any may be NULL): obs [B][A][obs_dim] float32 (lane_features observations only),
+ * reward [B][A] float32, mask [B][A][n_actions] uint8, reward_global [B] float32.  It writes the static
+ * and padding columns of every observation row (156 of 212 floats per Hangzhou row) once.
+ * tsc_env_step_registered then runs the fused step in ONE launch; each replica block stores a compact
+ * packet (per incoming lane n_queued / occupancy / mean_speed as the row shows them, per signal the phase
+ * index, reward, allowed-action bits; the global reward: < 1 KB per Hangzhou replica instead of 13.6 KB of
+ * fp32 rows) straight into page-locked host memory and raises a per-replica flag behind a system fence.
+ * Host worker threads (TSC_B200_HOST_THREADS, default min(8, cores / LOCAL_WORLD_SIZE)) follow the flags
+ * while the launch is still running and finish the rows in the caller's buffers: only values that changed
+ * since the previous step are rewritten.  After the call the registered buffers hold exactly what
+ * tsc_env_step + a device-to-host copy of obs / reward / mask / reward_global would (bit for bit).
+ * actions_host: host int32 [B][A] (ignored by the in-kernel controllers).  Synchronous.
+ * tsc_host_packet_bytes: bytes that cross PCIe device-to-host per step (packets + flags). */
+int  tsc_host_register(tsc_handle h, float *obs_host, float *reward_host, uint8_t *mask_host,
+                       float *reward_global_host);
+int  tsc_host_unregister(tsc_handle h);
+int  tsc_env_step_registered(tsc_handle h, const int32_t *actions_host, int32_t controller,
+                             int32_t controller_arg, int32_t n_ticks);
+int64_t tsc_host_packet_bytes(tsc_handle h);
 
 /* Copy the running vehicles of replica b to host arrays of capacity `cap`
  * (drivable-major, front to back): vehicle id (creation order), drivable,

@@ -34,7 +34,7 @@ DEFAULTS = {
     "gpu": {
         "n_replicas": 1,          # B: scenario replicas stepped in lockstep on this device
         "device": 0,
-        "vehicle_capacity": 0,    # 0 = derive from the scenario (max simultaneously running vehicles)
+        "vehicle_capacity": 0,    # 0 = a bound derived from the scenario (scenario.derive_vehicle_capacity); smaller = faster
         "reference_exact": True,  # reproduce pad_list's integer truncation in observations (utils.py:91-112)
     },
     "misc": {
@@ -125,6 +125,14 @@ class Config:
             raise NotImplementedError("gpu backend: rl_traffic_light must be True (pytsc default)")
         if float(self.simulator["interval"]) != 1.0:
             raise NotImplementedError("gpu backend: interval must be 1.0 (pytsc default)")
+        # reference features the device path does not implement are refused, not ignored
+        if float(self.signal.get("obs_noise_std", 0.0) or 0.0) != 0.0:
+            raise NotImplementedError("gpu backend: signal.obs_noise_std (observations.py:70-88) is not supported")
+        if float(self.signal.get("obs_dropout_prob", 0.0) or 0.0) != 0.0:
+            raise NotImplementedError("gpu backend: signal.obs_dropout_prob is not supported")
+        if self.network.get("control_scheme", "decentralized") != "decentralized":
+            raise NotImplementedError("gpu backend: network.control_scheme must be 'decentralized' "
+                                      "(CentralizedActionSpace enumerates the joint action set)")
 
     def _set_flow_file(self):
         """``cityflow/config.py:63-76``."""
@@ -145,3 +153,48 @@ class Config:
     def create_and_save_cityflow_cfg(self):
         self.cityflow_flow_file = self._set_flow_file()
         return self.cityflow_flow_file
+
+    def flow_file_universe(self):
+        """Every flow file ``_set_flow_file`` can pick, in a fixed order: the batched environment compiles them
+        all into one scenario (``n_flow_sets``) and gives each replica the one drawn for it at reset."""
+        if self.simulator.get("flow_rate_type", "constant") == "constant":
+            return [self.simulator["flow_file"]]
+        return list(dict.fromkeys(self.simulator["flow_files"]))
+
+    def resolve_flow_file(self, name):
+        return resolve_data_file(self.dir, name)
+
+
+class DisruptedConfig(Config):
+    """``DisruptedConfig`` (``pytsc/backends/cityflow/config.py:106-175``): the ``cityflow:`` section holds, per
+    ``mode`` (train / test), ``{domain: {disruption value: [flow files]}}``; every new engine runs a flow file
+    drawn from a (drawn or fixed) domain class, found under ``<mode>/<domain>/<value>/`` in the scenario
+    directory."""
+
+    def __init__(self, scenario, mode="train", debug=False, **kwargs):
+        self.mode = mode
+        self.domain_class = kwargs.get("domain_class", None)
+        super().__init__(scenario, debug=debug, **kwargs)
+        self.domains = list(self.simulator[mode].keys())
+        self.disrup_values = {d: list(self.simulator[mode][d].keys()) for d in self.domains}
+        self.domain_classes = [(d, v) for d in self.domains for v in self.disrup_values[d]]
+        self.current_domain_class = None
+        random.seed(self.simulator["seed"])
+
+    def _set_flow_file(self):
+        self.flow_rate_type = self.simulator.get("flow_rate_type", "constant")
+        if self.domain_class is None:
+            domain = random.choice(self.domains)
+            value = random.choice(self.disrup_values[domain])
+        else:
+            domain, value = self.domain_class[0], self.domain_class[1]
+        self.current_domain_class = self.domain_classes.index((domain, value))
+        flow_file = random.choice(self.simulator[self.mode][domain][value])
+        self.flow_file = os.path.join(self.mode, domain, value, flow_file)
+        return resolve_data_file(self.dir, self.flow_file)
+
+    def set_domain_class(self, domain_class):
+        self.domain_class = domain_class
+
+    def flow_file_universe(self):
+        return [os.path.join(self.mode, d, v, f) for d, v in self.domain_classes for f in self.simulator[self.mode][d][v]]

@@ -23,7 +23,8 @@ SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "ts
            "tsc_set_phase", "tsc_init_program", "tsc_step", "tsc_retrieve", "tsc_env_step", "tsc_env_step_host",
            "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
            "tsc_debug_timing", "tsc_controller_act", "tsc_kernel_variant", "tsc_reset_replicas", "tsc_state_bytes",
-           "tsc_save_state", "tsc_load_state")
+           "tsc_save_state", "tsc_load_state", "tsc_reset_flows", "tsc_reset_replicas_flows", "tsc_host_register",
+           "tsc_host_unregister", "tsc_env_step_registered", "tsc_host_packet_bytes")
 
 # tsc_env_step / tsc_controller_act controller codes (include/tsc_b200.h)
 CONTROLLERS = {"external": 0, "fixed_time": 1, "phase_index": 2, "greedy": 3, "max_pressure": 4, "sotl": 5, "random": 6}
@@ -38,7 +39,7 @@ def sotl_arg(theta=3, mu=4, phi_min=5):
 class tsc_outputs_t(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed", "lane_meas64", "pos_in", "pos_out",
-        "sig_stats64", "obs", "state", "reward", "reward_global", "mask", "sim", "metrics")]
+        "sig_stats64", "obs", "state", "reward", "reward_global", "mask", "sim", "metrics", "err")]
 
 
 class TscError(RuntimeError):
@@ -66,6 +67,13 @@ def load_library(path=None):
     L.tsc_get_dims.argtypes = [vp] + [pi32] * 9
     L.tsc_reset.argtypes = [vp, vp]
     L.tsc_reset_replicas.argtypes = [vp, vp, i32, vp]
+    L.tsc_reset_flows.argtypes = [vp, vp, vp]
+    L.tsc_reset_replicas_flows.argtypes = [vp, vp, vp, i32, vp]
+    L.tsc_host_register.argtypes = [vp, vp, vp, vp, vp]
+    L.tsc_host_unregister.argtypes = [vp]
+    L.tsc_env_step_registered.argtypes = [vp, vp, i32, i32, i32]
+    L.tsc_host_packet_bytes.argtypes = [vp]
+    L.tsc_host_packet_bytes.restype = C.c_int64
     L.tsc_state_bytes.argtypes = [vp]
     L.tsc_state_bytes.restype = C.c_int64
     L.tsc_save_state.argtypes = [vp, vp, C.c_int64, vp]
@@ -117,6 +125,7 @@ OUTPUT_SPECS = {   # name -> (shape builder, torch dtype name)
     "mask": (lambda d: (d["B"], d["A"], d["n_actions"]), "uint8"),
     "sim": (lambda d: (d["B"], 4), "float64"),
     "metrics": (lambda d: (d["B"], 8), "float64"),
+    "err": (lambda d: (d["B"],), "int32"),
 }
 
 
@@ -179,13 +188,22 @@ class Engine:
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- engine-level calls --------------------------------------------------------------
-    def reset(self):
-        self._check(self.lib.tsc_reset(self.h, self._stream()))
+    def reset(self, flow_sets=None):
+        """All replicas back to tick 0; ``flow_sets`` (int array [B]) = the flow set every replica restarts on
+        (``tsc_reset_flows``; None keeps the current assignment)."""
+        if flow_sets is None:
+            self._check(self.lib.tsc_reset(self.h, self._stream()))
+        else:
+            fs = np.ascontiguousarray(np.asarray(flow_sets, np.int32).reshape(-1))
+            assert fs.size == self.B, "one flow set per replica"
+            self._check(self.lib.tsc_reset_flows(self.h, _np_ptr(fs), self._stream()))
 
-    def reset_replicas(self, replicas):
-        """Selected replicas back to tick 0 (host list / array of replica indices)."""
+    def reset_replicas(self, replicas, flow_sets=None):
+        """Selected replicas back to tick 0 (host list / array of replica indices), optionally on new flow sets."""
         idx = np.ascontiguousarray(np.asarray(replicas, np.int32).reshape(-1))
-        self._check(self.lib.tsc_reset_replicas(self.h, _np_ptr(idx), len(idx), self._stream()))
+        fs = None if flow_sets is None else np.ascontiguousarray(np.asarray(flow_sets, np.int32).reshape(-1))
+        assert fs is None or fs.size == idx.size
+        self._check(self.lib.tsc_reset_replicas_flows(self.h, _np_ptr(idx), _np_ptr(fs), len(idx), self._stream()))
 
     def save_state(self, device=False):
         """Snapshot of all replicas (CityFlow's engine.snapshot()): a uint8 tensor, pinned host or device."""
@@ -236,6 +254,31 @@ class Engine:
         """numpy in, numpy out (host buffers), synchronous: the end-to-end path."""
         self._check(self.lib.tsc_env_step_host(self.h, _np_ptr(actions), controller, controller_arg, n_ticks,
                                                _np_ptr(obs), _np_ptr(reward), _np_ptr(mask), _np_ptr(reward_global)))
+
+    def host_register(self, obs=None, reward=None, mask=None, reward_global=None):
+        """Register the caller's HOST result arrays (numpy, C-contiguous) for ``env_step_registered``: one launch
+        per step, compact per-replica packets over PCIe, rows finished by host threads (``tsc_host_register``).
+        The arrays must stay alive and must not be written by the caller until ``host_unregister``."""
+        d = self.dims
+        for arr, shape, dt in ((obs, (d["B"], d["A"], d["obs_dim"]), np.float32), (reward, (d["B"], d["A"]), np.float32),
+                               (mask, (d["B"], d["A"], d["n_actions"]), np.uint8), (reward_global, (d["B"],), np.float32)):
+            assert arr is None or (arr.shape == shape and arr.dtype == dt and arr.flags["C_CONTIGUOUS"]), (shape, dt)
+        self._registered = (obs, reward, mask, reward_global)
+        self._check(self.lib.tsc_host_register(self.h, _np_ptr(obs), _np_ptr(reward), _np_ptr(mask), _np_ptr(reward_global)))
+
+    def host_unregister(self):
+        self._check(self.lib.tsc_host_unregister(self.h))
+        self._registered = None
+
+    def env_step_registered(self, actions=None, n_ticks=5, controller=0, controller_arg=0):
+        """numpy int32 [B, A] actions in (None for the in-kernel controllers); the registered arrays hold the results
+        on return (synchronous)."""
+        if actions is not None:
+            assert actions.dtype == np.int32 and actions.shape == (self.B, self.A) and actions.flags["C_CONTIGUOUS"]
+        self._check(self.lib.tsc_env_step_registered(self.h, _np_ptr(actions), controller, controller_arg, n_ticks))
+
+    def host_packet_bytes(self):
+        return int(self.lib.tsc_host_packet_bytes(self.h))
 
     # ---- debugging / parity ------------------------------------------------------------------
     def snapshot(self, replica=0):

@@ -22,9 +22,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <sched.h>
 
 // ----------------------------------------------------------------------------
 // Device-side views
@@ -55,7 +60,7 @@ static_assert(sizeof(CrossEntry) == 48, "CrossEntry must be 48 bytes");
 struct DevScn {   // device copies of tsc_scenario_t tables
     const LLInfo *llinfo;
     const CrossEntry *cross;
-    int L, K, D, A, N, T, horizon, max_raw, P;
+    int L, K, D, A, N, T, F, horizon, max_raw, P;
     int n_in_total, n_out_total, n_spawn_lanes;
     const double *drv_length, *drv_max_speed;
     const double2 *drv_lm;      // [D] (length, max speed) packed for the per-vehicle pass
@@ -66,10 +71,15 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     const double *xr_dist, *xr_foe_dist;
     const int *xr_foe_ll;
     const u32 *sig_phase_mask;
+    const int *sig_n_raw;            // [A] raw light phases per signal
     const int *route_seq, *veh_tick, *veh_seq_start, *veh_tmpl, *veh_priority;
     const double *tmpl;
-    const int *created_cnt;          // [horizon+2] vehicles created before tick t
-    const long long *created_enter;  // [horizon+2] sum of their creation ticks
+    const int *created_cnt;          // [F][horizon+2] vehicles of flow set f created before tick t
+    const long long *created_enter;  // [F][horizon+2] sum of their creation ticks
+    // host packet of the registered end-to-end path (tsc_env_step_registered)
+    const u32 *pk_lane;              // [n_in_total] incoming lanes in observation-row order: lane | truncate << 31
+    int pk_mode;                     // 1: one u32 per lane (n_queued | occupancy << 8 | mean_speed << 16, integers); 0: three floats
+    int pk_o_phase, pk_o_reward, pk_o_mask, pk_o_rg, pk_bytes;      // byte offsets inside a replica's packet; its size (multiple of 16)
     // pytsc tables
     const double *lane_pytsc_length, *lane_feat, *lane_cells;
     const int *sig_in_off, *sig_in_lane, *sig_out_off, *sig_out_lane;
@@ -97,13 +107,15 @@ struct RepHeader {   // 64 bytes, first thing in every replica image
     int n_x;              // scratch: vehicles deferred to the cross phase this tick
     int n_h, n_a;         // scratch: head vehicles / vehicles in an intersection zone this tick
     int n_pairs;          // scratch: (deferred vehicle, cross) pairs this tick
-    int pad[2];
+    int flow_set;         // which of the scenario's flow sets this replica runs (set at reset)
+    int pad;
 };
 static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 
 #define ERR_OVERFLOW 1u
 #define ERR_ORDER 2u
 #define ERR_ENT_OVERFLOW 4u
+#define ERR_BAD_PHASE 8u      // tsc_set_phase / actions named a phase the signal does not have
 
 struct Layout {
     int Vcap, ent_cap;
@@ -140,6 +152,9 @@ struct StepArgs {
     const int *raw_phase;  // [B][A]
     unsigned long long *phase_cycles;   // debug: per-phase clock64 sums (thread 0 of every block), or NULL
     unsigned char *workspace;           // GMEM variant: one working set of Y.smem_bytes (256-byte aligned stride) per block
+    unsigned char *pk;                  // registered host path: packets [B][pk_bytes] in mapped page-locked host memory, or NULL
+    u32 *pk_flags;                      // [B] raised to pk_seq (behind a system fence) once replica b's packet is complete
+    u32 pk_seq;
     tsc_outputs_t out;
 };
 
@@ -168,6 +183,7 @@ struct Ctx {
     u8 *sraw, *scur, *schg, *pj, *pj2, *nflag, *fresh;
     int *stop, *rpos, *vid, *vid2, *ellt, *ellt2, *nrpos, *scan;
     int *sp_lane, *sp_vid, *sp_tick;   // head of every spawn lane's waiting buffer
+    const int *lso;                    // this replica's flow set: row of lane_spawn_off
     short *blk, *nblk;
     double *pos, *spd, *npos, *nspd, *entpos;
     int tick;
@@ -511,8 +527,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 c.cnt[l] = (u16) (n + 1);
                 const int hd = c.wq[s] + 1;
                 c.wq[s] = (u16) hd;
-                const int at = __ldg(S.lane_spawn_off + l) + hd;
-                if (at < __ldg(S.lane_spawn_off + l + 1)) {
+                const int at = __ldg(c.lso + l) + hd;
+                if (at < __ldg(c.lso + l + 1)) {
                     const int nv = __ldg(S.lane_spawn_vid + at);
                     c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
                 } else c.sp_tick[s] = INT_MAX;
@@ -1120,7 +1136,11 @@ __device__ void controller_decide(const DevScn &S, Ctx &c, const StepArgs &a, in
 template <int NT>
 __device__ void apply_controller(const DevScn &S, Ctx &c, const StepArgs &a, int b, const int *decided) {
     for (int s = threadIdx.x; s < S.A; s += NT) {
-        if (a.set_raw_phase) c.sraw[s] = (u8) a.raw_phase[(size_t) b * S.A + s];
+        if (a.set_raw_phase) {
+            const int r = a.raw_phase[(size_t) b * S.A + s];
+            if (r < 0 || r >= __ldg(S.sig_n_raw + s)) atomicOr(&c.h->err, ERR_BAD_PHASE);
+            else c.sraw[s] = (u8) r;
+        }
         if (a.init_program >= 0) {
             c.scur[s] = (u8) a.init_program; c.schg[s] = 0; c.stop[s] = 0;
             c.sraw[s] = (u8) __ldg(S.sig_phase_raw + s * S.P + a.init_program);
@@ -1164,6 +1184,8 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     double *s_loc = c.nspd;              // [A] local reward term
     double *s_prs = c.nspd + A;          // [A] pressure
     int *l_q = (int *) (c.nspd + 2 * A); // [L]
+    // registered host path: the replica's packet is assembled here, then stored to host memory in 16-byte pieces
+    unsigned char *const pkst = a.pk ? (unsigned char *) c.nrpos : nullptr;
 
     // --- Retriever._compute_lane_measurements (retriever.py:54-85) ---
     for (int l = tid; l < L; l += NT) {
@@ -1193,6 +1215,20 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         if (O.lane_meas64) { O.lane_meas64[2 * o] = occ; O.lane_meas64[2 * o + 1] = ms; }
     }
     __syncthreads();
+    if (pkst) {      // per incoming lane, in observation-row order, the three values the row shows (observations.py:313-321)
+        for (int i = tid; i < S.n_in_total; i += NT) {
+            const u32 e = __ldg(S.pk_lane + i);
+            const int l = (int) (e & 0x7FFFFFFFu);
+            const bool tr = (e >> 31) != 0;
+            if (S.pk_mode) {
+                const u32 q = (u32) min(l_q[l], 255), oc = (u32) min((int) trunc(l_occ[l]), 255), ms = (u32) min((int) trunc(l_ms[l]), 255);
+                ((u32 *) pkst)[i] = q | (oc << 8) | (ms << 16);
+            } else {
+                float *f = (float *) pkst + 3 * i;
+                f[0] = (float) l_q[l]; f[1] = ref_trunc(l_occ[l], tr); f[2] = ref_trunc(l_ms[l], tr);
+            }
+        }
+    }
 
     // --- position-matrix windows (retriever.py:20-52, traffic_signal.py:124,135) ---
     const int vis = S.visibility;
@@ -1270,25 +1306,28 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
             for (int p = 0; p < MP; ++p) dst[k++] = p < P ? (p == cur ? 1.0f : 0.0f) : -1.0f;
         }
         // action mask (common/traffic_signal.py:329-361, 375-404; actions.py:119-131, 169-188)
-        if (O.mask) {
+        if (O.mask || pkst) {
             const u32 allow = allowable_phases(S, c, s);
-            u8 *m = O.mask + ((size_t) b * A + s) * S.n_actions;
-            if (S.action_space == TSC_ACT_PHASE_SWITCH) {
-                m[0] = (allow >> cur) & 1; m[1] = (allow >> ((cur + 1) % P)) & 1;
-            } else {
-                for (int p = 0; p < S.n_actions; ++p) m[p] = p < P ? ((allow >> p) & 1) : 0;
+            u32 bits;      // bit k = action k allowed
+            if (S.action_space == TSC_ACT_PHASE_SWITCH) bits = ((allow >> cur) & 1u) | (((allow >> ((cur + 1) % P)) & 1u) << 1);
+            else bits = P >= 32 ? allow : (allow & ((1u << P) - 1u));
+            if (O.mask) {
+                u8 *m = O.mask + ((size_t) b * A + s) * S.n_actions;
+                for (int p = 0; p < S.n_actions; ++p) m[p] = (u8) ((bits >> p) & 1u);
             }
+            if (pkst) { pkst[S.pk_o_phase + s] = (u8) cur; ((u32 *) (pkst + S.pk_o_mask))[s] = bits; }
         }
     }
     __syncthreads();
 
     // --- local rewards with spatially discounted neighbours (reward.py:81-88 | 129-136) ---
-    if (O.reward) {
+    if (O.reward || pkst) {
         for (int s = tid; s < A; s += NT) {
             double r = s_loc[s];
             int n0 = __ldg(S.nbr_off + s), n1 = __ldg(S.nbr_off + s + 1);
             for (int e = n0; e < n1; ++e) r += __ldg(S.nbr_weight + e) * s_loc[__ldg(S.nbr_idx + e)];
-            O.reward[(size_t) b * A + s] = (float) r;
+            if (O.reward) O.reward[(size_t) b * A + s] = (float) r;
+            if (pkst) ((float *) (pkst + S.pk_o_reward))[s] = (float) r;
         }
     }
 
@@ -1325,18 +1364,21 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
                 m[0] = qsum; m[1] = vsum ? div_pos(wspeed, (double) vsum) : 0.0; m[2] = 1 - norm_ms; m[3] = density;
                 m[4] = psum; m[5] = density * norm_ms; m[6] = flicker; m[7] = norm_ms;
             }
-            if (O.reward_global) {
+            if (O.reward_global || pkst) {
                 double r;
                 if (S.reward_type == TSC_REWARD_QUEUE) { r = 1e-6; r += S.flick * flicker; r += qsum; r = -1 * r; }
                 else { r = 1e-6; r -= S.flick * flicker; r -= psum; }
-                O.reward_global[b] = (float) r;
+                if (O.reward_global) O.reward_global[b] = (float) r;
+                if (pkst) *(float *) (pkst + S.pk_o_rg) = (float) r;
             }
+            if (O.err) O.err[b] = (int) c.h->err;
             if (O.sim) {
                 int now = c.h->tick;
                 int tt = now < S.horizon + 1 ? now : S.horizon + 1;
-                long long created = __ldg(S.created_cnt + tt);
+                const size_t fo = (size_t) c.h->flow_set * (S.horizon + 2) + tt;
+                long long created = __ldg(S.created_cnt + fo);
                 long long alive = created - c.h->n_finished;
-                double total = (double) (c.h->cum_tt + alive * now - (__ldg(S.created_enter + tt) - c.h->fin_enter)) * S.interval;
+                double total = (double) (c.h->cum_tt + alive * now - (__ldg(S.created_enter + fo) - c.h->fin_enter)) * S.interval;
                 long long n = c.h->n_finished + alive;
                 double *o = O.sim + (size_t) b * 4;
                 o[0] = c.h->n_running; o[1] = n == 0 ? 0.0 : total / (double) n; o[2] = now * S.interval; o[3] = c.h->n_finished;
@@ -1382,6 +1424,21 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
                     if (state) state[idx] = val;
                 }
             }
+        }
+    }
+    // ---- registered host path: the packet goes straight to page-locked host memory (coalesced 16-byte
+    //      stores over PCIe), then a flag is raised behind a system-scope fence; host threads follow the
+    //      flags while the other replicas of the launch are still being stepped ----
+    if (pkst) {
+        __syncthreads();
+        uint4 *dst = (uint4 *) (a.pk + (size_t) b * S.pk_bytes);
+        const uint4 *src = (const uint4 *) pkst;
+        for (int i = tid; i < S.pk_bytes / 16; i += NT) dst[i] = src[i];
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            *(volatile u32 *) (a.pk_flags + b) = a.pk_seq;
         }
     }
     // no trailing barrier: nothing below writes what the slower warps still read (the caller
@@ -1457,6 +1514,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         copy16(smem, img, Y.o_meta_end, tid, NT);
         __syncthreads();
         const int n_in = c.h->n_slots;
+        c.lso = S.lane_spawn_off + (size_t) c.h->flow_set * (S.L + 1);
         {
             const int n8 = (n_in * 8 + 15) & ~15, n4 = (n_in * 4 + 15) & ~15, n2 = (n_in * 2 + 15) & ~15, n1 = (n_in + 15) & ~15;
             if (!GMEM && Y.async_stage) {
@@ -1481,8 +1539,8 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_pairs = 0; }
         for (int s = tid; s < S.n_spawn_lanes; s += NT) {
             const int l = __ldg(S.spawn_lane + s);
-            const int at = __ldg(S.lane_spawn_off + l) + c.wq[s];
-            if (at < __ldg(S.lane_spawn_off + l + 1)) {
+            const int at = __ldg(c.lso + l) + c.wq[s];
+            if (at < __ldg(c.lso + l + 1)) {
                 const int nv = __ldg(S.lane_spawn_vid + at);
                 c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
             } else { c.sp_vid[s] = -1; c.sp_tick[s] = INT_MAX; }
@@ -1576,7 +1634,8 @@ static int fail(int code, const char *fmt, ...) {
 #define CUDA_TRY(x)                                                                                   \
     do {                                                                                              \
         cudaError_t e__ = (x);                                                                        \
-        if (e__ != cudaSuccess) return fail(TSC_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(e__ == cudaErrorMemoryAllocation ? TSC_ENOMEM : TSC_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
     } while (0)
 
 // Kernel variants.  256 threads per replica block while at least two replicas fit an SM's shared memory
@@ -1636,12 +1695,145 @@ struct tsc_engine {
     int host_lead = 0;                  // TSC_B200_HOST_LEAD=1 / =N: a short first chunk (one replica per SM / N replicas) so that the copies start early -- measured slower (1.58 vs 1.39-1.50 ms)
     bool host_zero_copy = false;        // TSC_B200_HOST_ZERO_COPY=1: kernel stores straight into mapped page-locked buffers
     std::vector<unsigned char> init_image;   // host copy of the tick-0 image
+    std::vector<int> h_flow_set;             // [B] flow set every replica runs (applied at reset)
+    int *d_flow_set = nullptr;
+    struct HostPath *hp = nullptr;           // registered end-to-end path (tsc_host_register)
+    std::vector<u32> h_obs_code;             // host copies of the observation recipe (tsc_host_register fills the static columns)
+    std::vector<float> h_obs_static;
+    std::vector<int> h_pk_dst;               // [n_in_total] float offset of the lane's n_queued element inside a replica's observation block, -1 = not shown
+    std::vector<int> h_sig_n_phases;
     // host copies needed by snapshot/load
     std::vector<int> h_route_seq, h_veh_seq_start;
     int n_spawn_lanes = 0;
     std::vector<int> h_spawn_lane;
     std::vector<u8> h_is_spawn;
 };
+
+
+// ----------------------------------------------------------------------------
+// Registered end-to-end path (tsc_host_register / tsc_env_step_registered)
+// ----------------------------------------------------------------------------
+// The launch stores one compact packet per replica into mapped page-locked host memory and raises the
+// replica's flag behind a system-scope fence (retrieve()).  Host worker threads follow the flags while the
+// launch is still running and finish the caller's rows: the packets ping-pong between two buffers, so the
+// previous step's packet is the shadow copy that tells which values changed.
+struct HostPath {
+    tsc_engine *E = nullptr;
+    float *obs = nullptr, *reward = nullptr, *rg = nullptr;
+    u8 *mask = nullptr;
+    unsigned char *pk[2] = {nullptr, nullptr};       // host addresses
+    unsigned char *pk_dev[2] = {nullptr, nullptr};   // the same buffers as the device sees them
+    u32 *flags = nullptr, *flags_dev = nullptr;
+    u32 seq = 0;
+    int cur = 0;
+    int nthreads = 1;
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv;
+    u32 job_seq = 0;          // guarded by mu: the step the workers should process
+    bool quit = false;
+    std::atomic<int> done{0};
+    std::atomic<int> failed{0};
+    uint64_t mask_lut[256];   // byte k of entry x = bit k of x
+};
+
+static const int HOST_GROUP = 16;      // consecutive replicas a worker takes at a time
+
+// Finish replica b's rows in the caller's buffers from its packet (new) against the previous one (old).
+static void host_finish_replica(HostPath *H, int b) {
+    tsc_engine *E = H->E;
+    const DevScn &S = E->S;
+    const int A = S.A, row = S.state_dim, pkb = S.pk_bytes;
+    const unsigned char *np = H->pk[H->cur] + (size_t) b * pkb, *op = H->pk[H->cur ^ 1] + (size_t) b * pkb;
+    if (H->obs) {
+        float *ob = H->obs + (size_t) b * A * row;
+        const int *dst = E->h_pk_dst.data();
+        const int n = S.n_in_total;
+        if (S.pk_mode) {
+            const u32 *nw = (const u32 *) np, *ow = (const u32 *) op;
+            for (int i = 0; i < n; ++i) {
+                const u32 v = nw[i];
+                if (v != ow[i] && dst[i] >= 0) {
+                    float *d = ob + dst[i];
+                    d[0] = (float) (v & 255u); d[1] = (float) ((v >> 8) & 255u); d[2] = (float) ((v >> 16) & 255u);
+                }
+            }
+        } else {
+            const u32 *nw = (const u32 *) np, *ow = (const u32 *) op;      // compared as bit patterns
+            for (int i = 0; i < n; ++i) {
+                if ((nw[3 * i] != ow[3 * i] || nw[3 * i + 1] != ow[3 * i + 1] || nw[3 * i + 2] != ow[3 * i + 2]) && dst[i] >= 0)
+                    memcpy(ob + dst[i], nw + 3 * i, 12);
+            }
+        }
+        const u8 *nph = np + S.pk_o_phase, *oph = op + S.pk_o_phase;
+        const int hot0 = S.max_lanes_per_signal * 12;
+        for (int sg = 0; sg < A; ++sg) {
+            if (nph[sg] != oph[sg]) {      // phase one-hot (observations.py:322-324): move the 1
+                float *d = ob + (size_t) sg * row + hot0;
+                d[oph[sg]] = 0.0f; d[nph[sg]] = 1.0f;
+            }
+        }
+    }
+    if (H->reward) memcpy(H->reward + (size_t) b * A, np + S.pk_o_reward, (size_t) A * 4);
+    if (H->rg) H->rg[b] = *(const float *) (np + S.pk_o_rg);
+    if (H->mask) {
+        const u32 *bits = (const u32 *) (np + S.pk_o_mask);
+        const int na = S.n_actions;
+        u8 *m = H->mask + (size_t) b * A * na;
+        for (int sg = 0; sg < A; ++sg, m += na) {
+            const u32 x = bits[sg];
+            int p = 0;
+            for (; p + 8 <= na; p += 8) memcpy(m + p, &H->mask_lut[(x >> p) & 255u], 8);
+            for (; p < na; ++p) m[p] = (u8) ((x >> p) & 1u);
+        }
+    }
+}
+
+static void host_work(HostPath *H, int w, u32 seq) {
+    const int B = H->E->B, ngroups = (B + HOST_GROUP - 1) / HOST_GROUP;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int g = w; g < ngroups; g += H->nthreads) {
+        const int b1 = std::min(B, (g + 1) * HOST_GROUP);
+        for (int b = g * HOST_GROUP; b < b1; ++b) {
+            unsigned spins = 0;
+            while (__atomic_load_n(&H->flags[b], __ATOMIC_ACQUIRE) != seq) {
+                __builtin_ia32_pause();
+                if ((++spins & 0xFFFF) == 0) {
+                    if (H->failed.load(std::memory_order_relaxed)) return;
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) { H->failed.store(2); return; }
+                }
+            }
+            host_finish_replica(H, b);
+        }
+    }
+}
+
+static void host_worker_main(HostPath *H, int w) {
+    u32 seen = 0;
+    for (;;) {
+        u32 seq;
+        {
+            std::unique_lock<std::mutex> lk(H->mu);
+            H->cv.wait(lk, [&] { return H->quit || H->job_seq != seen; });
+            if (H->quit) return;
+            seq = seen = H->job_seq;
+        }
+        host_work(H, w, seq);
+        H->done.fetch_add(1, std::memory_order_release);
+    }
+}
+
+static int host_thread_count() {
+    if (const char *env = getenv("TSC_B200_HOST_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 64) return v; }
+    int cpus = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);
+    if (cpus <= 0) cpus = (int) std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char *env = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(env); if (v >= 1) ranks = v; }
+    int n = cpus / ranks;
+    return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
 
 template <typename Tp>
 static int upload(tsc_engine *E, const Tp *host, size_t n, const Tp **dev) {
@@ -1706,7 +1898,7 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged, int c
     Y.o_spawn = o; o = align16(o + 12 * (S.n_spawn_lanes + 1));
     // the tick's decision buffers; npos / nspd / nrpos double as retrieve scratch: make sure they are large enough
     int need_np = 3 * S.L, need_ns = 2 * S.A + (S.L + 1) / 2 + 2;
-    int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : 0;
+    int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : (S.pk_bytes + 3) / 4;
     auto decision_buffers = [&]() {
         Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
         Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
@@ -1732,8 +1924,11 @@ extern "C" {
 int tsc_abi_version(void) { return TSC_ABI_VERSION; }
 const char *tsc_last_error(void) { return g_err.c_str(); }
 
+static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int32_t vehicle_capacity);
+
 int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int32_t vehicle_capacity, tsc_handle *out) {
     if (!s || !out) return fail(TSC_EINVAL, "null argument");
+    *out = nullptr;
     if (s->abi_version != TSC_ABI_VERSION) return fail(TSC_EINVAL, "scenario abi_version %d != %d", s->abi_version, TSC_ABI_VERSION);
     if (n_replicas <= 0) return fail(TSC_EINVAL, "n_replicas must be positive");
     if (s->interval != 1.0) return fail(TSC_EINVAL, "interval must be 1.0");
@@ -1747,18 +1942,39 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(TSC_EINVAL, "device %d not available (%d devices)", device, ndev);
+    if (s->n_flow_sets < 1) return fail(TSC_EINVAL, "n_flow_sets must be at least 1");
+    for (int a = 0; a < s->n_signals; ++a)
+        if (s->sig_n_raw_phases[a] < 1 || s->sig_n_raw_phases[a] > s->max_raw_phases || s->sig_n_phases[a] < 1 || s->sig_n_phases[a] > s->max_phases)
+            return fail(TSC_EINVAL, "signal %d: phase counts out of range", a);
     CUDA_TRY(cudaSetDevice(device));
     auto *E = new tsc_engine();
     E->device = device; E->B = n_replicas;
+    // every failure below releases the handle and whatever it already owns (device tables, pinned buffers, streams)
+    const int rc = create_body(E, s, n_replicas, device, vehicle_capacity);
+    if (rc) { tsc_destroy(E); return rc; }
+    *out = E;
+    return 0;
+}
+
+}  // extern "C"
+
+static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int32_t vehicle_capacity) {
     DevScn &S = E->S;
     S.L = s->n_lanes; S.K = s->n_lanelinks; S.D = S.L + S.K; S.A = s->n_signals; S.N = s->n_vehicles; S.T = s->n_templates;
+    S.F = s->n_flow_sets;
     S.horizon = s->horizon_ticks; S.max_raw = s->max_raw_phases; S.P = s->max_phases;
     S.n_in_total = s->n_in_total; S.n_out_total = s->n_out_total;
     const int L = S.L, K = S.K, D = S.D, A = S.A, N = S.N;
     int rc = 0;
-#define UP(field, n) if ((rc = upload(E, s->field, (size_t) (n), &S.field))) { tsc_destroy(E); return rc; }
+#define UP(field, n) if ((rc = upload(E, s->field, (size_t) (n), &S.field))) return rc;
     UP(drv_length, D) UP(drv_max_speed, D) UP(lane_ll_off, L + 1) UP(lane_ll, s->lane_ll_off[L])
-    UP(lane_spawn_off, L + 1) UP(lane_spawn_vid, N)
+    UP(lane_spawn_off, (size_t) S.F * (L + 1)) UP(lane_spawn_vid, N)
+    if ((rc = upload(E, s->sig_n_raw_phases, (size_t) A, &S.sig_n_raw))) return rc;
+    for (int f = 0; f < S.F; ++f) {
+        const int *row = s->lane_spawn_off + (size_t) f * (L + 1);
+        if (row[0] != (f ? s->lane_spawn_off[(size_t) f * (L + 1) - 1] : 0) || row[L] > N) return fail(TSC_EINVAL, "lane_spawn_off row %d does not continue the previous one", f);
+        for (int l = 0; l < L; ++l) if (row[l + 1] < row[l]) return fail(TSC_EINVAL, "lane_spawn_off row %d is not ascending", f);
+    }
     UP(ll_start_lane, K) UP(ll_end_lane, K) UP(ll_signal, K) UP(ll_roadlink, K) UP(ll_type, K) UP(ll_cross_off, K + 1)
     UP(xr_dist, s->n_cross_entries) UP(xr_foe_ll, s->n_cross_entries) UP(xr_foe_dist, s->n_cross_entries)
     UP(sig_phase_mask, A * s->max_raw_phases) UP(route_seq, s->n_route_seq)
@@ -1773,12 +1989,12 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         std::vector<double> cells(L > 0 ? L : 1, 1.0);
         for (int l = 0; l < L; ++l) {
             cells[l] = s->lane_pytsc_length[l] / s->veh_size_min_gap;
-            if (!(cells[l] > 0.0)) { tsc_destroy(E); return fail(TSC_EINVAL, "lane %d: pytsc length / veh_size_min_gap must be positive", l); }
+            if (!(cells[l] > 0.0)) { return fail(TSC_EINVAL, "lane %d: pytsc length / veh_size_min_gap must be positive", l); }
         }
-        if ((rc = upload(E, cells.data(), (size_t) L, &S.lane_cells))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, cells.data(), (size_t) L, &S.lane_cells))) return rc;
     }
     for (int k = 0; k < D; ++k)
-        if (!(s->drv_max_speed[k] > 0.0)) { tsc_destroy(E); return fail(TSC_EINVAL, "drivable %d: max speed must be positive", k); }
+        if (!(s->drv_max_speed[k] > 0.0)) { return fail(TSC_EINVAL, "drivable %d: max speed must be positive", k); }
     S.reward_type = s->reward_type; S.obs_type = s->obs_type; S.action_space = s->action_space; S.round_robin = s->round_robin;
     S.visibility = s->visibility; S.yellow_time = s->yellow_time; S.obs_dim = s->obs_dim; S.state_dim = s->state_dim;
     S.n_actions = s->n_actions; S.reference_exact = s->reference_exact; S.max_lanes_per_signal = s->max_lanes_per_signal;
@@ -1786,9 +2002,9 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     {   // lane-feature rows (observations.py:305-329): per incoming lane [9 static, n_queued, occupancy, mean_speed],
         // -1 padding up to max_lanes_per_signal lanes, then the phase one-hot over max_obs_phases entries
         const int per = 12, ML = S.max_lanes_per_signal, MP = S.max_obs_phases, row = ML * per + MP;
-        if (row != S.state_dim) { tsc_destroy(E); return fail(TSC_EINVAL, "state_dim %d != %d * 12 + %d", S.state_dim, ML, MP); }
-        if (S.obs_type == TSC_OBS_LANE_FEATURES && S.obs_dim != row) { tsc_destroy(E); return fail(TSC_EINVAL, "obs_dim %d != state_dim %d", S.obs_dim, row); }
-        if (A > 0xFFFFF || MP > 256) { tsc_destroy(E); return fail(TSC_EINVAL, "too many signals / phases for the observation recipe"); }
+        if (row != S.state_dim) { return fail(TSC_EINVAL, "state_dim %d != %d * 12 + %d", S.state_dim, ML, MP); }
+        if (S.obs_type == TSC_OBS_LANE_FEATURES && S.obs_dim != row) { return fail(TSC_EINVAL, "obs_dim %d != state_dim %d", S.obs_dim, row); }
+        if (A > 0xFFFFF || MP > 256) { return fail(TSC_EINVAL, "too many signals / phases for the observation recipe"); }
         std::vector<u32> code((size_t) A * row > 0 ? (size_t) A * row : 1, 0u);
         std::vector<float> sval(code.size(), 0.0f);
         for (int sg = 0; sg < A; ++sg) {
@@ -1808,8 +2024,40 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
                 }
             }
         }
-        if ((rc = upload(E, code.data(), code.size(), &S.obs_code))) { tsc_destroy(E); return rc; }
-        if ((rc = upload(E, sval.data(), sval.size(), &S.obs_static))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, code.data(), code.size(), &S.obs_code))) return rc;
+        if ((rc = upload(E, sval.data(), sval.size(), &S.obs_static))) return rc;
+        E->h_obs_code = code; E->h_obs_static = sval;
+        E->h_sig_n_phases.assign(s->sig_n_phases, s->sig_n_phases + A);
+        // host packet of the registered end-to-end path: per incoming lane (observation-row order) the lane and whether
+        // its row truncates; one u32 per lane when every shown value is a small integer, three floats otherwise
+        std::vector<u32> pkl(s->n_in_total > 0 ? s->n_in_total : 1, 0u);
+        E->h_pk_dst.assign(s->n_in_total > 0 ? s->n_in_total : 1, -1);
+        double min_len = 1e300, max_speed = 0.0;
+        for (int t = 0; t < s->n_templates; ++t) {
+            min_len = std::min(min_len, s->tmpl[(size_t) t * TSC_T_STRIDE + TSC_T_LEN]);
+            max_speed = std::max(max_speed, s->tmpl[(size_t) t * TSC_T_STRIDE + TSC_T_MAX_SPEED]);
+        }
+        bool small_ints = S.reference_exact != 0 && max_speed < 255.0 && min_len > 0.0;
+        for (int sg = 0; sg < A; ++sg) {
+            const int i0 = s->sig_in_off[sg], nin = s->sig_in_off[sg + 1] - i0;
+            const bool tr = S.reference_exact && nin < ML;
+            small_ints = small_ints && tr;
+            for (int e = 0; e < nin; ++e) {
+                const int l = s->sig_in_lane[i0 + e];
+                pkl[i0 + e] = (u32) l | (tr ? 0x80000000u : 0u);
+                if (e < ML) E->h_pk_dst[i0 + e] = sg * row + e * per + 9;
+                // vehicles on the lane < 255, occupancy = n / cells <= n
+                small_ints = small_ints && s->drv_length[l] / min_len + 2.0 < 255.0 && s->lane_pytsc_length[l] / s->veh_size_min_gap >= 1.0;
+            }
+        }
+        if ((rc = upload(E, pkl.data(), pkl.size(), &S.pk_lane))) return rc;
+        S.pk_mode = small_ints ? 1 : 0;
+        int o = align16((small_ints ? 4 : 12) * s->n_in_total);
+        S.pk_o_phase = o; o = align16(o + A);
+        S.pk_o_reward = o; o = align16(o + 4 * A);
+        S.pk_o_mask = o; o = align16(o + 4 * A);
+        S.pk_o_rg = o; o = align16(o + 4);
+        S.pk_bytes = o;
     }
     {   // vehicle templates, extended with the per-template constants of the car-following law
         std::vector<double> td((size_t) s->n_templates * TD_STRIDE, 0.0);
@@ -1817,15 +2065,15 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
             const double *src = s->tmpl + (size_t) t * TSC_T_STRIDE;
             double *dst = td.data() + (size_t) t * TD_STRIDE;
             for (int k = 0; k < TSC_T_STRIDE; ++k) dst[k] = src[k];
-            if (!(src[TSC_T_MAX_NEG_ACC] > 0.0) || !(src[TSC_T_MAX_NEG_ACC] < 1e300)) { tsc_destroy(E); return fail(TSC_EINVAL, "template %d: maxNegAcc must be positive and finite", t); }
+            if (!(src[TSC_T_MAX_NEG_ACC] > 0.0) || !(src[TSC_T_MAX_NEG_ACC] < 1e300)) { return fail(TSC_EINVAL, "template %d: maxNegAcc must be positive and finite", t); }
             const double a = 0.5 / src[TSC_T_MAX_NEG_ACC];
             dst[TD_A] = a;
             dst[TD_HALF_OVER_A] = 0.5 / a;
             dst[TD_HEADWAY_DEN] = src[TSC_T_HEADWAY] + s->interval / 2;
             const double approach = src[TSC_T_MAX_SPEED] * src[TSC_T_MAX_SPEED] / src[TSC_T_USUAL_NEG_ACC] / 2 + src[TSC_T_MAX_SPEED] * s->interval * 2;
-            if (src[TSC_T_APPROACH_DIST] != approach) { tsc_destroy(E); return fail(TSC_EINVAL, "template %d: TSC_T_APPROACH_DIST is not maxSpeed^2/usualNegAcc/2 + 2 maxSpeed interval", t); }
+            if (src[TSC_T_APPROACH_DIST] != approach) { return fail(TSC_EINVAL, "template %d: TSC_T_APPROACH_DIST is not maxSpeed^2/usualNegAcc/2 + 2 maxSpeed interval", t); }
         }
-        if ((rc = upload(E, td.data(), td.size(), &S.tmpl))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, td.data(), td.size(), &S.tmpl))) return rc;
     }
     // packed lane-link / cross tables
     {
@@ -1835,7 +2083,7 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
             li[k].cross_off = s->ll_cross_off[k]; li[k].cross_end = s->ll_cross_off[k + 1];
             li[k].length = s->drv_length[L + k]; li[k].type = s->ll_type[k];
             if (s->ll_signal[k] < 0 || s->ll_signal[k] >= A || s->ll_roadlink[k] < 0 || s->ll_roadlink[k] >= 32) {
-                tsc_destroy(E); return fail(TSC_EINVAL, "lane-link %d: bad signal / road-link index", k);
+                return fail(TSC_EINVAL, "lane-link %d: bad signal / road-link index", k);
             }
             li[k].sigbit = s->ll_signal[k] | (s->ll_roadlink[k] << 16);
         }
@@ -1843,19 +2091,19 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         std::vector<CrossEntry> ce(nx > 0 ? nx : 1);
         for (int x = 0; x < nx; ++x) {
             int f = s->xr_foe_ll[x];
-            if (f < 0 || f >= K) { tsc_destroy(E); return fail(TSC_EINVAL, "cross %d: bad lane-link index", x); }
+            if (f < 0 || f >= K) { return fail(TSC_EINVAL, "cross %d: bad lane-link index", x); }
             ce[x].dist = s->xr_dist[x]; ce[x].foe_dist = s->xr_foe_dist[x];
             ce[x].foe_len = s->drv_length[L + f]; ce[x].foe_sl_len = s->drv_length[s->ll_start_lane[f]];
             ce[x].foe_ll = f; ce[x].foe_start_lane = s->ll_start_lane[f]; ce[x].foe_end_lane = s->ll_end_lane[f];
             ce[x].foe_type = s->ll_type[f];
         }
-        if ((rc = upload(E, li.data(), li.size(), &S.llinfo))) { tsc_destroy(E); return rc; }
-        if ((rc = upload(E, ce.data(), ce.size(), &S.cross))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, li.data(), li.size(), &S.llinfo))) return rc;
+        if ((rc = upload(E, ce.data(), ce.size(), &S.cross))) return rc;
     }
     {
         std::vector<double2> lm(D > 0 ? D : 1);
         for (int k = 0; k < D; ++k) lm[k] = make_double2(s->drv_length[k], s->drv_max_speed[k]);
-        if ((rc = upload(E, lm.data(), lm.size(), &S.drv_lm))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, lm.data(), lm.size(), &S.drv_lm))) return rc;
     }
     {   // packed sibling lists for the head look-ahead
         std::vector<int4> sib(L > 0 ? L : 1);
@@ -1867,36 +2115,48 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
             if (n > 2 && n <= 3) v.w = L + s->lane_ll[e0 + 2];
             sib[l] = v;
         }
-        if ((rc = upload(E, sib.data(), sib.size(), &S.lane_sib))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, sib.data(), sib.size(), &S.lane_sib))) return rc;
     }
     // spawn lanes and creation prefix tables
     E->h_is_spawn.assign(L, 0);
-    for (int l = 0; l < L; ++l) if (s->lane_spawn_off[l + 1] > s->lane_spawn_off[l]) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
+    for (int l = 0; l < L; ++l) {      // a lane that spawns in ANY flow set owns a spare slot in every replica
+        bool any = false;
+        for (int f = 0; f < S.F; ++f) any = any || s->lane_spawn_off[(size_t) f * (L + 1) + l + 1] > s->lane_spawn_off[(size_t) f * (L + 1) + l];
+        if (any) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
+    }
     S.n_spawn_lanes = E->n_spawn_lanes = (int) E->h_spawn_lane.size();
-    if ((rc = upload(E, E->h_spawn_lane.data(), E->h_spawn_lane.size(), &S.spawn_lane))) { tsc_destroy(E); return rc; }
+    if ((rc = upload(E, E->h_spawn_lane.data(), E->h_spawn_lane.size(), &S.spawn_lane))) return rc;
     {
-        if (E->n_spawn_lanes > 32767) { tsc_destroy(E); return fail(TSC_EINVAL, "more than 32767 spawn lanes"); }
+        if (E->n_spawn_lanes > 32767) { return fail(TSC_EINVAL, "more than 32767 spawn lanes"); }
         std::vector<short> idx(L > 0 ? L : 1, (short) -1);
         for (int k = 0; k < E->n_spawn_lanes; ++k) idx[E->h_spawn_lane[k]] = (short) k;
-        if ((rc = upload(E, idx.data(), (size_t) L, &S.lane_spawn_idx))) { tsc_destroy(E); return rc; }
+        if ((rc = upload(E, idx.data(), (size_t) L, &S.lane_spawn_idx))) return rc;
     }
-    { const u8 *p; if ((rc = upload(E, E->h_is_spawn.data(), (size_t) L, &p))) { tsc_destroy(E); return rc; } E->d_is_spawn_lane = (u8 *) p; }
-    std::vector<int> ccnt(S.horizon + 2, 0);
-    std::vector<long long> cent(S.horizon + 2, 0);
-    for (int v = 0; v < N; ++v) {
-        int t = s->veh_tick[v];
-        if (t < 0 || t > S.horizon) { tsc_destroy(E); return fail(TSC_EINVAL, "veh_tick out of horizon"); }
-        ccnt[t + 1] += 1; cent[t + 1] += t;
+    { const u8 *p; if ((rc = upload(E, E->h_is_spawn.data(), (size_t) L, &p))) return rc; E->d_is_spawn_lane = (u8 *) p; }
+    const int H2 = S.horizon + 2;
+    std::vector<int> ccnt((size_t) S.F * H2, 0);
+    std::vector<long long> cent((size_t) S.F * H2, 0);
+    for (int f = 0; f < S.F; ++f) {
+        const int *row = s->lane_spawn_off + (size_t) f * (L + 1);
+        int *cc = ccnt.data() + (size_t) f * H2;
+        long long *ce = cent.data() + (size_t) f * H2;
+        for (int at = row[0]; at < row[L]; ++at) {
+            const int v = s->lane_spawn_vid[at];
+            if (v < 0 || v >= N) return fail(TSC_EINVAL, "lane_spawn_vid[%d] out of range", at);
+            const int t = s->veh_tick[v];
+            if (t < 0 || t > S.horizon) { return fail(TSC_EINVAL, "veh_tick out of horizon"); }
+            cc[t + 1] += 1; ce[t + 1] += t;
+        }
+        for (int t = 1; t <= S.horizon + 1; ++t) { cc[t] += cc[t - 1]; ce[t] += ce[t - 1]; }
     }
-    for (int t = 1; t <= S.horizon + 1; ++t) { ccnt[t] += ccnt[t - 1]; cent[t] += cent[t - 1]; }
-    if ((rc = upload(E, ccnt.data(), ccnt.size(), &S.created_cnt))) { tsc_destroy(E); return rc; }
-    if ((rc = upload(E, cent.data(), cent.size(), &S.created_enter))) { tsc_destroy(E); return rc; }
+    if ((rc = upload(E, ccnt.data(), ccnt.size(), &S.created_cnt))) return rc;
+    if ((rc = upload(E, cent.data(), cent.size(), &S.created_enter))) return rc;
     E->h_route_seq.assign(s->route_seq, s->route_seq + s->n_route_seq);
     E->h_veh_seq_start.assign(s->veh_seq_start, s->veh_seq_start + N);
 
     int Vcap = vehicle_capacity > 0 ? vehicle_capacity : 1024;
     Vcap = (Vcap + E->n_spawn_lanes + 7) & ~7;
-    if (Vcap > 32767) { tsc_destroy(E); return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
+    if (Vcap > 32767) { return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     // Pick the variant from what fits: 256-thread blocks (ping-pong re-pack) while >= 2 replicas fit an
@@ -2006,6 +2266,10 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
         for (int i = 0; i < E->Y.Vcap; ++i) vid[i] = -1;
         short *blk = (short *) (E->init_image.data() + E->Y.o_blk);
         for (int i = 0; i < E->Y.Vcap; ++i) blk[i] = -1;
+        // the signal programs start on pytsc phase 0 (TSProgram.set_initial_phase, backends/cityflow/traffic_signal.py:26-32):
+        // a caller that steps before its first tsc_init_program / action sees that light phase, not raw phase 0
+        u8 *sraw = E->init_image.data() + E->Y.o_sraw;
+        for (int a = 0; a < A; ++a) sraw[a] = (u8) s->sig_phase_raw[(size_t) a * s->max_phases];
     }
     size_t io = (size_t) n_replicas * A;
     CUDA_TRY(cudaMalloc((void **) &E->d_actions, io * sizeof(int)));
@@ -2027,16 +2291,21 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     if (const char *env = getenv("TSC_B200_HOST_CHUNKS")) { int v = atoi(env); if (v >= 1 && v <= MAX_HOST_CHUNKS) E->host_chunks = v; }
     if (const char *env = getenv("TSC_B200_HOST_ZERO_COPY")) E->host_zero_copy = atoi(env) != 0;
     if (const char *env = getenv("TSC_B200_HOST_LEAD")) E->host_lead = atoi(env) > 0 ? atoi(env) : 0;
-    *out = E;
-    int r = tsc_reset(E, nullptr);
-    if (r) { tsc_destroy(E); *out = nullptr; return r; }
+    E->h_flow_set.assign(n_replicas, 0);
+    CUDA_TRY(cudaMalloc((void **) &E->d_flow_set, (size_t) n_replicas * sizeof(int)));
+    CUDA_TRY(cudaMemset(E->d_flow_set, 0, (size_t) n_replicas * sizeof(int)));
+    if ((rc = tsc_reset(E, nullptr))) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
     return 0;
 }
 
+extern "C" {
+
 void tsc_destroy(tsc_handle E) {
     if (!E) return;
     cudaSetDevice(E->device);
+    tsc_host_unregister(E);
+    cudaFree(E->d_flow_set);
     for (void *p : E->dev_allocs) cudaFree(p);
     cudaFree(E->d_phase_cycles);
     cudaFree(E->workspace);
@@ -2078,21 +2347,52 @@ int tsc_reset(tsc_handle E, void *stream) {
         CUDA_TRY(cudaMemcpyAsync(E->images + done * E->Y.img_bytes, E->images, n * E->Y.img_bytes, cudaMemcpyDeviceToDevice, st));
         done += n;
     }
+    // every replica's flow set: one strided copy of the [B] table into the image headers
+    if (E->S.F > 1)
+        CUDA_TRY(cudaMemcpy2DAsync(E->images + offsetof(RepHeader, flow_set), E->Y.img_bytes, E->d_flow_set, sizeof(int), sizeof(int),
+                                   E->B, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 
-int tsc_reset_replicas(tsc_handle E, const int32_t *replicas, int32_t n, void *stream) {
+int tsc_reset_flows(tsc_handle E, const int32_t *flow_set_per_replica, void *stream) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    if (flow_set_per_replica) {
+        for (int b = 0; b < E->B; ++b)
+            if (flow_set_per_replica[b] < 0 || flow_set_per_replica[b] >= E->S.F)
+                return fail(TSC_EINVAL, "replica %d: flow set %d out of range (the scenario has %d)", b, flow_set_per_replica[b], E->S.F);
+        CUDA_TRY(cudaSetDevice(E->device));
+        E->h_flow_set.assign(flow_set_per_replica, flow_set_per_replica + E->B);
+        CUDA_TRY(cudaMemcpyAsync(E->d_flow_set, E->h_flow_set.data(), (size_t) E->B * sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t) stream));
+    }
+    return tsc_reset(E, stream);
+}
+
+int tsc_reset_replicas_flows(tsc_handle E, const int32_t *replicas, const int32_t *flow_sets, int32_t n, void *stream) {
     if (!E || n < 0 || (n && !replicas)) return fail(TSC_EINVAL, "bad argument");
     CUDA_TRY(cudaSetDevice(E->device));
     cudaStream_t st = (cudaStream_t) stream;
-    for (int k = 0; k < n; ++k)
+    for (int k = 0; k < n; ++k) {
         if (replicas[k] < 0 || replicas[k] >= E->B) return fail(TSC_EINVAL, "replica index %d out of range", replicas[k]);
+        if (flow_sets && (flow_sets[k] < 0 || flow_sets[k] >= E->S.F)) return fail(TSC_EINVAL, "flow set %d out of range (the scenario has %d)", flow_sets[k], E->S.F);
+    }
     // the tick-0 image is kept on the device right behind the B replica images
-    for (int k = 0; k < n; ++k)
-        CUDA_TRY(cudaMemcpyAsync(E->images + (size_t) replicas[k] * E->Y.img_bytes, E->images + (size_t) E->B * E->Y.img_bytes,
+    for (int k = 0; k < n; ++k) {
+        const int b = replicas[k];
+        CUDA_TRY(cudaMemcpyAsync(E->images + (size_t) b * E->Y.img_bytes, E->images + (size_t) E->B * E->Y.img_bytes,
                                  E->Y.img_bytes, cudaMemcpyDeviceToDevice, st));
+        if (flow_sets) E->h_flow_set[b] = flow_sets[k];
+        if (E->S.F > 1) {
+            if (flow_sets) CUDA_TRY(cudaMemcpyAsync(E->d_flow_set + b, &E->h_flow_set[b], sizeof(int), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(E->images + (size_t) b * E->Y.img_bytes + offsetof(RepHeader, flow_set), E->d_flow_set + b, sizeof(int),
+                                     cudaMemcpyDeviceToDevice, st));
+        }
+    }
     return 0;
+}
+
+int tsc_reset_replicas(tsc_handle E, const int32_t *replicas, int32_t n, void *stream) {
+    return tsc_reset_replicas_flows(E, replicas, nullptr, n, stream);
 }
 
 // blob = StateHeader + B replica images
@@ -2163,6 +2463,8 @@ int tsc_set_phase(tsc_handle E, const int32_t *raw_phase, void *stream) {
 
 int tsc_init_program(tsc_handle E, int32_t phase_index, void *stream) {
     if (!E || phase_index < 0) return fail(TSC_EINVAL, "bad argument");
+    for (size_t a = 0; a < E->h_sig_n_phases.size(); ++a)
+        if (phase_index >= E->h_sig_n_phases[a]) return fail(TSC_EINVAL, "phase index %d: signal %d has %d phases", phase_index, (int) a, E->h_sig_n_phases[a]);
     StepArgs a = blank_args(E);
     a.init_program = phase_index;
     return launch(E, a, stream);
@@ -2320,6 +2622,123 @@ int tsc_env_step_host(tsc_handle E, const int32_t *actions_host, int32_t control
     return 0;
 }
 
+
+int tsc_host_unregister(tsc_handle E) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    HostPath *H = E->hp;
+    if (!H) return 0;
+    cudaSetDevice(E->device);
+    cudaStreamSynchronize(E->host_compute);
+    {
+        std::lock_guard<std::mutex> lk(H->mu);
+        H->quit = true;
+    }
+    H->cv.notify_all();
+    for (auto &t : H->threads) t.join();
+    for (int k = 0; k < 2; ++k) if (H->pk[k]) cudaFreeHost(H->pk[k]);
+    if (H->flags) cudaFreeHost(H->flags);
+    delete H;
+    E->hp = nullptr;
+    return 0;
+}
+
+int64_t tsc_host_packet_bytes(tsc_handle E) { return E ? (int64_t) E->B * (E->S.pk_bytes + 4) : 0; }
+
+int tsc_host_register(tsc_handle E, float *obs_host, float *reward_host, uint8_t *mask_host, float *reward_global_host) {
+    if (!E) return fail(TSC_EINVAL, "null handle");
+    if (obs_host && E->S.obs_type != TSC_OBS_LANE_FEATURES)
+        return fail(TSC_EINVAL, "the registered host path builds lane_features observation rows only (use tsc_env_step_host)");
+    CUDA_TRY(cudaSetDevice(E->device));
+    tsc_host_unregister(E);
+    HostPath *H = new HostPath();
+    E->hp = H;
+    H->E = E; H->obs = obs_host; H->reward = reward_host; H->mask = mask_host; H->rg = reward_global_host;
+    const DevScn &S = E->S;
+    const size_t pk_total = (size_t) E->B * S.pk_bytes;
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaHostAlloc((void **) &H->pk[k], pk_total, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(H->pk[k], 0, pk_total);
+        CUDA_TRY(cudaHostGetDevicePointer((void **) &H->pk_dev[k], H->pk[k], 0));
+    }
+    CUDA_TRY(cudaHostAlloc((void **) &H->flags, (size_t) E->B * sizeof(u32), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(H->flags, 0, (size_t) E->B * sizeof(u32));
+    CUDA_TRY(cudaHostGetDevicePointer((void **) &H->flags_dev, H->flags, 0));
+    for (int x = 0; x < 256; ++x) {
+        uint64_t v = 0;
+        for (int k = 0; k < 8; ++k) v |= (uint64_t) ((x >> k) & 1) << (8 * k);
+        H->mask_lut[x] = v;
+    }
+    // the rows as an all-zero packet describes them: static and padding columns from the recipe, dynamic lane
+    // values 0, every program on phase 0 -- written once; afterwards only changes are written
+    if (obs_host) {
+        const int A = S.A, row = S.state_dim;
+        std::vector<float> block((size_t) A * row);
+        for (int sg = 0; sg < A; ++sg)
+            for (int k = 0; k < row; ++k) {
+                const size_t at = (size_t) sg * row + k;
+                const u32 code = E->h_obs_code[at];
+                float v = E->h_obs_static[at];
+                if (code) v = ((code & 7) == 4 && ((code >> 4) & 0xFF) == 0) ? 1.0f : 0.0f;
+                block[at] = v;
+            }
+        for (int b = 0; b < E->B; ++b) memcpy(obs_host + (size_t) b * A * row, block.data(), block.size() * sizeof(float));
+    }
+    H->nthreads = host_thread_count();
+    const int ngroups = (E->B + HOST_GROUP - 1) / HOST_GROUP;
+    if (H->nthreads > ngroups) H->nthreads = ngroups;
+    for (int w = 1; w < H->nthreads; ++w) H->threads.emplace_back(host_worker_main, H, w);
+    return 0;
+}
+
+int tsc_env_step_registered(tsc_handle E, const int32_t *actions_host, int32_t controller, int32_t controller_arg, int32_t n_ticks) {
+    if (!E || n_ticks < 0) return fail(TSC_EINVAL, "bad argument");
+    HostPath *H = E->hp;
+    if (!H) return fail(TSC_EINVAL, "tsc_host_register has not been called");
+    if (!controller_mode(controller)) return fail(TSC_EINVAL, "unknown controller %d", controller);
+    CUDA_TRY(cudaSetDevice(E->device));
+    cudaStream_t sc = E->host_compute;
+    CUDA_TRY(cudaEventRecord(E->host_ev[0], 0));         // ordered after whatever the caller queued on the default stream
+    CUDA_TRY(cudaStreamWaitEvent(sc, E->host_ev[0], 0));
+    const size_t io = (size_t) E->B * E->S.A;
+    if (controller_needs_actions(controller)) {
+        if (!actions_host) return fail(TSC_EINVAL, "actions required by controller %d", controller);
+        const int32_t *src = actions_host;
+        if (!is_pinned(actions_host)) { memcpy(E->h_actions, actions_host, io * sizeof(int)); src = E->h_actions; }
+        CUDA_TRY(cudaMemcpyAsync(E->d_actions, src, io * sizeof(int), cudaMemcpyHostToDevice, sc));
+    }
+    H->seq += 1;
+    if (H->seq == 0) { memset(H->flags, 0, (size_t) E->B * sizeof(u32)); H->seq = 1; }
+    H->cur ^= 1;
+    StepArgs a = blank_args(E);
+    a.apply_actions = controller_mode(controller);
+    a.controller_arg = controller_arg; a.actions = E->d_actions; a.n_ticks = n_ticks;
+    a.do_retrieve = 1;
+    a.pk = H->pk_dev[H->cur]; a.pk_flags = H->flags_dev; a.pk_seq = H->seq;
+    H->failed.store(0);
+    H->done.store(0);
+    int rc = launch(E, a, sc);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(H->mu);
+        H->job_seq = H->seq;
+    }
+    H->cv.notify_all();
+    host_work(H, 0, H->seq);
+    unsigned spins = 0;
+    while (H->done.load(std::memory_order_acquire) < H->nthreads - 1) {
+        __builtin_ia32_pause();
+        if ((++spins & 0x3FFF) == 0 && !H->failed.load() && cudaStreamQuery(sc) != cudaErrorNotReady) {
+            // the launch is over (or failed): flags that are still missing will never come
+            bool missing = false;
+            for (int b = 0; b < E->B && !missing; ++b) missing = __atomic_load_n(&H->flags[b], __ATOMIC_ACQUIRE) != H->seq;
+            if (missing) H->failed.store(1);
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(sc));
+    if (H->failed.load()) return fail(TSC_ECUDA, "registered host step: replica packets did not arrive (code %d)", H->failed.load());
+    return 0;
+}
+
 int tsc_snapshot(tsc_handle E, int32_t b, int32_t cap, int32_t *vid, int32_t *drivable, double *distance, double *speed,
                  int32_t *blocker_vid, int32_t *enter_ll_time) {
     if (!E || b < 0 || b >= E->B) return fail(TSC_EINVAL, "bad replica index");
@@ -2401,6 +2820,8 @@ int tsc_check(tsc_handle E, int32_t *first_bad) {
             if (first_bad) *first_bad = b;
             if (hs[b].err & (ERR_OVERFLOW | ERR_ENT_OVERFLOW))
                 return fail(TSC_EOVERFLOW, "replica %d exceeded vehicle_capacity (flags 0x%x)", b, hs[b].err);
+            if (hs[b].err & ERR_BAD_PHASE)
+                return fail(TSC_EINVAL, "replica %d was given a light phase its signal does not have (flags 0x%x)", b, hs[b].err);
             return fail(TSC_EORDER, "replica %d: a vehicle left its drivable out of order (flags 0x%x)", b, hs[b].err);
         }
     }

@@ -18,10 +18,12 @@ instance (``device=LOCAL_RANK``); nothing on the step path communicates.
 """
 from __future__ import annotations
 
-from .backend.config import Config
+import numpy as np
+
+from .backend.config import Config, DisruptedConfig
 from .backend.network_parser import NetworkParser
 from .binding import CONTROLLERS, Engine, sotl_arg
-from .scenario import compile_scenario
+from .scenario import compile_scenario, derive_vehicle_capacity
 
 def shard_replicas(total_replicas: int, world_size: int, rank: int):
     """Contiguous block of replicas owned by ``rank``: (first, count).  Replicas are
@@ -72,19 +74,32 @@ def batched_density_map(lane_occupancy, W, adjacency):
     return (dm + dm.transpose(1, 2)) / 2 + 1e-6 * adjacency
 
 
-STEP_OUTPUTS = ("obs", "state", "reward", "reward_global", "mask", "sim", "metrics")
+STEP_OUTPUTS = ("obs", "state", "reward", "reward_global", "mask", "sim", "metrics", "err")
 LANE_OUTPUTS = ("lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed")
 
 
 class BatchedTrafficSignalNetwork:
     def __init__(self, scenario, n_replicas=None, device=None, lane_outputs=False, **kwargs):
-        self.config = Config(scenario, **kwargs)
+        # pytsc/__init__.py:21-33: disrupted=True selects the DisruptedConfig (mode, domain_class in kwargs)
+        self.disrupted = bool(kwargs.get("disrupted", False))
+        self.config = (DisruptedConfig if self.disrupted else Config)(scenario, **kwargs)
         gpu = self.config.gpu
         self.parsed_network = NetworkParser(self.config)
-        self.scenario = compile_scenario(self.config, self.parsed_network)
+        # every flow file the config can draw (flow_rate_type random / sequential, DisruptedConfig) is compiled
+        # into the scenario as a flow set; each replica gets the one drawn for it whenever its engine restarts
+        self._flow_files = self.config.flow_file_universe()
+        self._flow_index = {f: k for k, f in enumerate(self._flow_files)}
+        if len(self._flow_files) > 1:
+            paths = [self.config.resolve_flow_file(f) for f in self._flow_files]
+            self.scenario = compile_scenario(self.config, self.parsed_network, flow_sets=paths)
+        else:
+            self.scenario = compile_scenario(self.config, self.parsed_network)
         self.n_replicas = int(n_replicas if n_replicas is not None else gpu.get("n_replicas", 1))
         dev = int(device if device is not None else gpu.get("device", 0))
-        self.engine = Engine(self.scenario, self.n_replicas, dev, int(gpu.get("vehicle_capacity", 0)) or 1024)
+        cap = int(gpu.get("vehicle_capacity", 0)) or derive_vehicle_capacity(self.scenario)
+        self.engine = Engine(self.scenario, self.n_replicas, dev, cap)
+        self.flow_sets = np.zeros(self.n_replicas, np.int32)
+        self._host = None
         self.torch = self.engine.torch
         self.device = self.engine.device
         self.n_agents = self.engine.A
@@ -130,7 +145,8 @@ class BatchedTrafficSignalNetwork:
     def reset(self):
         """Engine back to tick 0 (a new ``cityflow.Engine`` in the reference,
         pytsc/__init__.py:164-176), programs on phase 0, first measurements."""
-        self.engine.reset()
+        self.engine.check()      # a replica that overflowed its vehicle capacity froze: never hand out its stale rows silently
+        self.engine.reset(self._draw_flow_sets())
         self.engine.init_program(0)
         self._tick = 0
         if self._wait:
@@ -138,6 +154,20 @@ class BatchedTrafficSignalNetwork:
             self._tick = self._wait
         self.engine.retrieve(self.out)
         return self.out["obs"], self.out["mask"]
+
+    def _draw_flow_sets(self):
+        """One ``Config._set_flow_file()`` draw per replica (backends/cityflow/config.py:63-76, 146-169): what B
+        independent reference environments would do for their new engines.  None with a single flow file."""
+        if len(self._flow_files) <= 1:
+            return None
+        for b in range(self.n_replicas):
+            self.config._set_flow_file()
+            self.flow_sets[b] = self._flow_index[self.config.flow_file]
+        return self.flow_sets
+
+    def set_domain_class(self, domain_class):
+        """epymarl.py:85-89 -> DisruptedConfig.set_domain_class: takes effect at the next engine restart."""
+        self.config.set_domain_class(domain_class)
 
     def restart(self):
         """pytsc/__init__.py:164-176."""
@@ -168,6 +198,34 @@ class BatchedTrafficSignalNetwork:
         self._acc[1] += self.out["metrics"][:, 0].sum()
         self._acc[2] += self.n_replicas
         return self.out["reward_global"], self.episode_over, self.get_env_info()
+
+    # ---- the same step through HOST arrays (what a CPU-side trainer / the reference's callers hold) ---------
+    def register_host_buffers(self):
+        """Allocate and register the host result arrays of ``step_host``: ``obs`` float32 [B, A, obs_dim],
+        ``reward`` [B, A], ``mask`` uint8 [B, A, n_actions], ``reward_global`` [B] (numpy).  Lane-feature
+        observations only."""
+        d = self.engine.dims
+        self._host = {"obs": np.empty((d["B"], d["A"], d["obs_dim"]), np.float32),
+                      "reward": np.empty((d["B"], d["A"]), np.float32),
+                      "mask": np.empty((d["B"], d["A"], d["n_actions"]), np.uint8),
+                      "reward_global": np.empty((d["B"],), np.float32)}
+        self.engine.host_register(**self._host)
+        return self._host
+
+    def step_host(self, actions=None, controller=None, green_time=25, seed=0, theta=3, mu=4, phi_min=5):
+        """``step`` with numpy int32 [B, A] actions in and the registered numpy arrays out (synchronous): one
+        launch, < 1 KB per replica over PCIe, rows finished by host threads while the launch runs."""
+        if self._host is None:
+            self.register_host_buffers()
+        if controller is None or controller == "external":
+            self.engine.env_step_registered(actions, n_ticks=self.delta_time, controller=0)
+        elif controller == "phase_index":
+            self.engine.env_step_registered(actions, n_ticks=self.delta_time, controller=CONTROLLERS["phase_index"])
+        else:
+            arg = {"fixed_time": green_time, "sotl": sotl_arg(theta, mu, phi_min)}.get(controller, seed)
+            self.engine.env_step_registered(None, n_ticks=self.delta_time, controller=CONTROLLERS[controller], controller_arg=arg)
+        self._tick += self.delta_time
+        return self._host["reward_global"], self.episode_over, self._host
 
     def controller_actions(self, controller, scores=False, **kw):
         """The phase indices ``controller`` would choose in the current state (``tsc_controller_act``)."""
@@ -211,7 +269,8 @@ class BatchedTrafficSignalNetwork:
         m, s = self.out["metrics"], self.out["sim"]
         return {"time_step": s[:, 2], "average_travel_time": s[:, 1], "n_queued": m[:, 0], "mean_speed": m[:, 1],
                 "mean_delay": m[:, 2], "density": m[:, 3], "pressure": m[:, 4], "network_flow": m[:, 5],
-                "episode_count": self.episode_count, "episode_limit": self.episode_limit}
+                "episode_count": self.episode_count, "episode_limit": self.episode_limit,
+                "error_flags": self.out["err"]}      # non-zero = that replica froze (capacity exceeded): its rows are stale
 
     def check(self):
         """Synchronise and raise if any replica overflowed its vehicle capacity."""
@@ -222,6 +281,7 @@ class BatchedTrafficSignalNetwork:
         """Global episode metrics over every rank's replicas: a single NCCL
         all-reduce(SUM) of a 7-element fp64 vector."""
         torch = self.torch
+        self.engine.check()
         s = self.out["sim"]
         vec = torch.stack([s[:, 1].sum(), s[:, 3].sum(), s[:, 0].sum(),
                            self._acc[0], self._acc[1], self._acc[2],

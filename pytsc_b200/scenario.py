@@ -20,7 +20,7 @@ import numpy as np
 from . import bundle
 from .roadnet import RoadNet, VEHICLE_KEYS, expand_flows
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 T_STRIDE = 12
 REWARD_TYPES = {"queue_length": 0, "max_pressure": 1}
 OBS_TYPES = {"lane_features": 0, "position_matrix": 1}
@@ -40,7 +40,7 @@ class tsc_scenario_t(C.Structure):
         ("abi_version", _i), ("n_lanes", _i), ("n_lanelinks", _i), ("n_signals", _i), ("n_vehicles", _i),
         ("n_templates", _i), ("n_route_seq", _i), ("n_cross_entries", _i), ("horizon_ticks", _i),
         ("max_raw_phases", _i), ("max_phases", _i), ("n_in_total", _i), ("n_out_total", _i), ("n_nbr_total", _i),
-        ("n_ctl_total", _i),
+        ("n_ctl_total", _i), ("n_flow_sets", _i),
         ("drv_length", _pd), ("drv_max_speed", _pd), ("lane_ll_off", _pi), ("lane_ll", _pi),
         ("lane_spawn_off", _pi), ("lane_spawn_vid", _pi), ("ll_start_lane", _pi), ("ll_end_lane", _pi),
         ("ll_signal", _pi), ("ll_roadlink", _pi), ("ll_type", _pi), ("ll_cross_off", _pi),
@@ -117,14 +117,77 @@ def static_lane_features(parser):
     return feats
 
 
-def compile_scenario(config, parser, flows=None, flow_file=None) -> CompiledScenario:
-    """``config``: backend.config.Config; ``parser``: backend.network_parser.NetworkParser."""
+def derive_vehicle_capacity(cs, margin=1.1) -> int:
+    """Upper bound on simultaneously running vehicles per replica when ``gpu.vehicle_capacity`` is 0: no more
+    than a flow set creates in total, and no more than bumper to bumper on every drivable (vehicle length +
+    minGap per vehicle, the standing spacing CityFlow's car-following rule converges to), with a margin.
+    Safe rather than tight: a smaller explicit capacity keeps more replicas per SM (bench.py passes one);
+    exceeding it freezes the replica and is reported by ``Engine.check()`` / the ``err`` output."""
+    off = cs.stats.get("flow_set_off", [0, int(cs.n_vehicles)])
+    created = max(int(off[k + 1] - off[k]) for k in range(len(off) - 1))
+    tm = np.asarray(cs.tmpl).reshape(-1, T_STRIDE)
+    spacing = float((tm[:, 0] + tm[:, 5]).min()) if tm.size else 7.5
+    packed = int(sum(np.ceil(np.asarray(cs.drv_length) / max(spacing, 1.0)) + 1))
+    return int(min(32000, max(64, min(created, int(np.ceil(packed * margin))))))
+
+
+def merge_flow_sets(sps):
+    """Spawn lists of several flow files (``expand_flows`` results) as ONE vehicle table, set-major: the
+    vehicles of set f follow those of set f-1; routes and vehicle templates are shared.  Adds ``set_off``
+    ([F+1] vehicle index ranges)."""
+    if len(sps) == 1:
+        sp = dict(sps[0])
+        sp["set_off"] = [0, len(sp["tick"])]
+        return sp
+    routes, route_index, templates, tmpl_index = [], {}, [], {}
+    out = {k: [] for k in ("tick", "flow", "flow_cnt", "route", "tmpl", "priority", "first_lane")}
+    set_off, dup, invalid = [0], 0, []
+    for sp in sps:
+        rmap = []
+        for key in sp["routes"]:
+            if key not in route_index:
+                route_index[key] = len(routes)
+                routes.append(key)
+            rmap.append(route_index[key])
+        tmap = []
+        for t in sp["templates"]:
+            if t not in tmpl_index:
+                tmpl_index[t] = len(templates)
+                templates.append(t)
+            tmap.append(tmpl_index[t])
+        for k in ("tick", "flow", "flow_cnt", "priority", "first_lane"):
+            out[k].append(np.asarray(sp[k], np.int64))
+        out["route"].append(np.asarray([rmap[r] for r in sp["route"]], np.int64))
+        out["tmpl"].append(np.asarray([tmap[t] for t in sp["tmpl"]], np.int64))
+        set_off.append(set_off[-1] + len(sp["tick"]))
+        dup += sp["duplicate_priorities"]
+        invalid.append(sp["invalid_flows"])
+    res = {k: np.concatenate(v) if v else np.zeros(0, np.int64) for k, v in out.items()}
+    res.update(routes=routes, templates=templates, duplicate_priorities=dup, invalid_flows=invalid, set_off=set_off)
+    return res
+
+
+def compile_scenario(config, parser, flows=None, flow_file=None, flow_sets=None) -> CompiledScenario:
+    """``config``: backend.config.Config; ``parser``: backend.network_parser.NetworkParser.
+
+    One flow set by default -- ``flows`` (a CityFlow flow list), else ``flow_file``, else the file the config
+    picks (``backends/cityflow/config.py:63-76``).  ``flow_sets`` = a list of flow lists / file paths compiles
+    several alternatives into one scenario (``n_flow_sets``): replicas are assigned one each at reset
+    (``tsc_reset_flows``), which is how ``flow_rate_type: random | sequential`` and ``DisruptedConfig`` map
+    onto a batch."""
     sim, sig, misc = config.simulator, config.signal, config.misc
     rn = RoadNet(parser.net)
-    if flows is None:
-        flows = bundle.load_flow(flow_file or config.create_and_save_cityflow_cfg())
     horizon = int(sim["sim_length"]) + int(sim["initial_wait_time"])
-    sp = expand_flows(rn, flows, float(sim["interval"]), int(sim["seed"]), horizon)
+    if flow_sets is None:
+        if flows is None:
+            flows = bundle.load_flow(flow_file or config.create_and_save_cityflow_cfg())
+        flow_sets = [flows]
+    flow_sets = [bundle.load_flow(f) if isinstance(f, str) else f for f in flow_sets]
+    if not flow_sets:
+        raise ValueError("compile_scenario: empty flow_sets")
+    # every flow file is what a fresh cityflow.Engine(seed) would make of it: the generator restarts per set
+    sp = merge_flow_sets([expand_flows(rn, f, float(sim["interval"]), int(sim["seed"]), horizon) for f in flow_sets])
+    F = len(flow_sets)
     L, K = len(rn.lanes), len(rn.lanelinks)
     a, s = {}, {}
     f64, i32 = np.float64, np.int32
@@ -170,10 +233,20 @@ def compile_scenario(config, parser, flows=None, flow_file=None) -> CompiledScen
     a["veh_seq_start"] = np.asarray([starts[r] for r in sp["route"]] or [0], i32)
     a["veh_tmpl"] = sp["tmpl"].astype(i32) if N else np.zeros(1, i32)
     a["veh_priority"] = sp["priority"].astype(i32) if N else np.zeros(1, i32)
-    per_lane = [[] for _ in range(L)]
-    for v in range(N):
-        per_lane[int(sp["first_lane"][v])].append(v)
-    a["lane_spawn_off"], a["lane_spawn_vid"] = _csr(per_lane)
+    per_lane = [[] for _ in range(L)]      # union over the flow sets (which lanes spawn at all)
+    spawn_off = np.zeros((F, L + 1), i32)
+    spawn_vid = []
+    for f in range(F):
+        lanes_f = [[] for _ in range(L)]
+        for v in range(sp["set_off"][f], sp["set_off"][f + 1]):
+            lanes_f[int(sp["first_lane"][v])].append(v)
+            per_lane[int(sp["first_lane"][v])].append(v)
+        spawn_off[f, 0] = len(spawn_vid)
+        for l in range(L):
+            spawn_vid += lanes_f[l]
+            spawn_off[f, l + 1] = len(spawn_vid)
+    a["lane_spawn_off"] = spawn_off.reshape(-1)
+    a["lane_spawn_vid"] = np.asarray(spawn_vid or [0], i32)
     interval = float(sim["interval"])
     tm = np.zeros((max(len(sp["templates"]), 1), T_STRIDE), f64)
     for i, t in enumerate(sp["templates"]):
@@ -262,7 +335,7 @@ def compile_scenario(config, parser, flows=None, flow_file=None) -> CompiledScen
              n_templates=len(sp["templates"]) or 1, n_route_seq=len(seq), n_cross_entries=len(xs),
              horizon_ticks=horizon, max_raw_phases=max_raw, max_phases=P,
              n_in_total=int(a["sig_in_off"][-1]), n_out_total=int(a["sig_out_off"][-1]),
-             n_nbr_total=int(a["nbr_off"][-1]), n_ctl_total=int(a["ctl_off"][-1]),
+             n_nbr_total=int(a["nbr_off"][-1]), n_ctl_total=int(a["ctl_off"][-1]), n_flow_sets=F,
              reward_type=REWARD_TYPES[sig["reward_function"]], obs_type=obs_type, action_space=act,
              round_robin=int(bool(sig["round_robin"])), visibility=vis, yellow_time=int(sig["yellow_time"]),
              obs_dim=obs_dim, state_dim=state_dim, n_actions=(P if act == 0 else 2),
@@ -273,6 +346,7 @@ def compile_scenario(config, parser, flows=None, flow_file=None) -> CompiledScen
     for k, v in a.items():
         a[k] = np.ascontiguousarray(v)
     names = [f"flow_{f}_{c}" for f, c in zip(sp["flow"], sp["flow_cnt"])]
-    stats = dict(n_routes=len(sp["routes"]), n_crosses=rn.n_crosses, duplicate_priorities=sp["duplicate_priorities"],
+    stats = dict(flow_set_off=[int(x) for x in sp["set_off"]],
+                 n_routes=len(sp["routes"]), n_crosses=rn.n_crosses, duplicate_priorities=sp["duplicate_priorities"],
                  invalid_flows=sp["invalid_flows"], n_spawn_lanes=sum(1 for p in per_lane if p))
     return CompiledScenario(a, s, lane_ids, signal_ids, names, stats)

@@ -48,6 +48,10 @@ def oracle_engine(config):
 
 
 def build_scenario(name, **kwargs):
+    # the fixed flow file of the scenario unless the test asks for the reference's random / sequential draw
+    # (several shipped config.yaml files say flow_rate_type: random)
+    kwargs = {k: dict(v) if isinstance(v, dict) else v for k, v in kwargs.items()}
+    kwargs.setdefault("cityflow", {}).setdefault("flow_rate_type", "constant")
     cfg = Config(name, **kwargs)
     parser = NetworkParser(cfg)
     return cfg, parser, compile_scenario(cfg, parser)

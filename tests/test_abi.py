@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     assert set(names) == set(binding.SYMBOLS)
     for n in names:
         assert getattr(cuda_lib, n) is not None
-    assert cuda_lib.tsc_abi_version() == 2
+    assert cuda_lib.tsc_abi_version() == 3
 
 
 def test_library_is_sm100a_sass(cuda_lib):

@@ -13,7 +13,8 @@ from pytsc_b200.scenario import compile_scenario
 
 cap = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-cfg = Config(bench.SCENARIO, **bench.SCENARIO_KW)
+W = bench.workload(os.environ.get("BENCH_CONFIG", "hangzhou"))
+cfg = Config(W["scenario"], **W["kw"])
 cs = compile_scenario(cfg, NetworkParser(cfg))
 eng = Engine(cs, B, 0, vehicle_capacity=cap)
 bufs = eng.alloc_outputs(["obs", "reward", "reward_global", "mask", "lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed", "sim"])
