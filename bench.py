@@ -121,7 +121,7 @@ def _reference_python_worker(args):
     """One process: the UNMODIFIED reference stack (baseline/_ref pytsc) on one replica -- TrafficSignalNetwork with the
     CityFlow backend plugin, FixedTimeController objects driven as controllers/evaluate.py:112-137 does -- over the oracle
     engine as ``cityflow.Engine``.  Modes: "step" = network.step + mask + observations + local rewards per env-step (what
-    an RL loop pulls); "evaluate" = Evaluate.run's own loop body (_get_actions recomputes all observations per agent)."""
+    an RL loop pulls); "evaluate" = Evaluate.run itself (its _get_actions recomputes all observations once per agent)."""
     w, n_ff, n_steps, mode = args
     import logging
     from pytsc_b200 import compat
@@ -140,30 +140,24 @@ def _reference_python_worker(args):
     cf_config.CONFIG_DIR = os.path.join(root, "cityflow")
     kw = {k: dict(v) for k, v in w["kw"].items()}
     kw.get("cityflow", {}).pop("flow_file", None)
-    net = pytsc.TrafficSignalNetwork(name, "cityflow", **kw)
-    for ts in net.traffic_signals.values():
-        ts.init_rule_based_controllers(green_time=GREEN_TIME)
+    from pytsc.controllers.evaluate import Evaluate
+    ev = Evaluate(name, "cityflow", "fixed_time", add_env_args=kw, add_controller_args={"green_time": GREEN_TIME})
+    net = ev.network
 
-    def actions():
-        if mode == "evaluate":      # evaluate.py:112-124
-            acts = []
-            for ts in net.traffic_signals.values():
-                net.get_observations()
-                acts.append(ts.get_controller_action("fixed_time", inp=net.simulator.step_measurements))
-            return acts
-        return [ts.get_controller_action("fixed_time", inp=net.simulator.step_measurements) for ts in net.traffic_signals.values()]
-
-    def one():
-        net.step(actions())
-        if mode != "evaluate":
-            net.get_action_mask(); net.get_observations(); net.get_rewards()
+    def cheap_actions():      # the controllers' own get_action, without Evaluate._get_actions' per-agent observation rebuild
+        return [ev.controllers[ts_id].get_action(None) for ts_id in net.traffic_signals]
 
     for _ in range(n_ff):          # untimed fast-forward into the loaded regime
-        net.step(actions())
+        net.step(cheap_actions())
     t0 = time.perf_counter()
-    for _ in range(n_steps):
-        one()
+    if mode == "evaluate":         # Evaluate.run itself (controllers/evaluate.py:71-95)
+        ev.run((n_steps + 0.5) * ev.delta_time / 3600.0, output_folder=tempfile.mkdtemp(prefix="tsc_eval_"))
+    else:
+        for _ in range(n_steps):
+            net.step(cheap_actions())
+            net.get_action_mask(); net.get_observations(); net.get_rewards()
     dt = time.perf_counter() - t0
+    net = ev.network
     return dt, len(net.traffic_signals), net.simulator.step_measurements["sim"]["n_vehicles"]
 
 
@@ -233,8 +227,8 @@ def cpu_baseline_block(w, n_ff, n_steps):
     if kind == "reference":
         ev = cpu_throughput(w, n_ff, max(8, n_steps // 4), "evaluate", kind=kind)
         out["evaluate_run_value"] = ev["value"]
-        out["evaluate_run_note"] = ("Evaluate.run's own loop body (controllers/evaluate.py:71-95,112-124: observations "
-                                    "recomputed once per agent inside _get_actions), same processes")
+        out["evaluate_run_note"] = ("Evaluate.run itself (controllers/evaluate.py:71-95,112-124: observations recomputed once "
+                                    "per agent inside _get_actions; no mask / reward pulls), same process count")
     eng = cpu_throughput(w, n_ff, n_steps, "engine", kind="port")
     out["engine_only_value"] = eng["value"]
     out["engine_only_note"] = "C++ oracle engine ticks only (no pytsc Python), same process count"

@@ -38,7 +38,7 @@ def test_registered_path_equals_device_path(cuda_lib, case, exact, threads, monk
     bufs = dev.alloc_outputs(["obs", "reward", "mask", "reward_global"])
     h = _host_arrays(host)
     host.host_register(**h)
-    assert host.host_packet_bytes() < h["obs"].nbytes / 8
+    assert host.host_packet_bytes() < h["obs"].nbytes / (8 if exact else 4)      # u32 per lane / three floats per lane
     dev.init_program(0); host.init_program(0)
     T = int(g["n_steps"])
     rng = np.random.RandomState(3)
