@@ -96,17 +96,17 @@ struct DevScn {   // device copies of tsc_scenario_t tables
 };
 
 struct RepHeader {   // 64 bytes, first thing in every replica image
-    int n_slots;          // slots in use (vehicles + one spare slot per spawn lane)
+    int n_slots;          // slots in use: live vehicles and holes left by finished ones (compacted away now and then)
     int tick;             // engine step counter
     int n_running;
     int n_finished;
     long long cum_tt;     // sum over finished vehicles of (finish tick - creation tick)
     long long fin_enter;  // sum of creation ticks of finished vehicles
     u32 err;              // sticky error bits
-    int n_ent;            // scratch: movers this tick
+    int n_ent;            // scratch: vehicles changing drivable (or finishing) this tick
     int n_x;              // scratch: vehicles deferred to the cross phase this tick
     int n_h, n_a;         // scratch: head vehicles / vehicles in an intersection zone this tick
-    int n_pairs;          // scratch: (deferred vehicle, cross) pairs this tick
+    int n_new;            // scratch: n_slots after this tick's spawns
     int flow_set;         // which of the scenario's flow sets this replica runs (set at reset)
     int pad;
 };
@@ -117,22 +117,24 @@ static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 #define ERR_ENT_OVERFLOW 4u
 #define ERR_BAD_PHASE 8u      // tsc_set_phase / actions named a phase the signal does not have
 
+#define NONE16 0xFFFFu        // "no vehicle" in the per-drivable lists
+#define PJ_MOVER 0x80u        // pj[] bit: the vehicle leaves its drivable this tick (set by its decision, cleared by the list surgery)
+#define HOLE_MAX 32           // finished vehicles leave holes; the slots are compacted once this many have piled up
+
 struct Layout {
-    int Vcap, ent_cap;
+    int Vcap;              // vehicle slots (running vehicles + holes)
+    int Vlay;              // slots the columns are laid out for (>= Vcap: the retrieve scratch lives in a pos/spd pair)
+    int ent_cap;           // vehicles that may change drivable in one tick
     int async_stage;       // 1: cp.async staging of the image columns (TSC_B200_ASYNC_STAGE)
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
-    int cross_group;       // lanes per vehicle in the per-vehicle cross phase: 32, 16, 8, 4, 2, or 0 = chosen per tick from the list length
-    int pair_cap;          // (vehicle, cross) pairs the optional flat cross phase can list (0, the default: lane groups per vehicle)
-    int cold_level;        // 2: the decision buffers are laid out in the cold region (D)
-    int staged;            // 1: the tick's re-pack stages identity columns in registers instead of a second copy (Vcap <= SCATTER_PER * threads)
-    // persistent part: identical byte offsets in the HBM image and in shared memory
-    int o_cnt, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
-    int o_pos, o_spd, o_rpos, o_vid, o_ellt, o_blk, o_drv, o_pj, img_bytes;
-    // shared-memory-only scratch
-    int o_vid2, o_ellt2, o_pj2;
-    int o_dn, o_dn2, o_xlist, o_avail, o_tmpl, o_spawn;
-    int o_npos, o_nspd, o_nrpos, o_nblk, o_nflag, o_off, o_leave, o_ent, o_fresh, o_entlist,
-        o_entpos, o_entdrv, o_scan, o_cold, o_img_cold, hybrid_smem_bytes, smem_bytes;
+    int cross_group;       // lanes per vehicle in the cross phase: 32, 16, 8, 4, 2, or 0 = chosen per tick from the list length
+    // persistent part: identical byte offsets in the HBM image and in the working set
+    int o_cnt, o_head, o_tail, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
+    int o_pos, o_spd, o_rpos, o_vid, o_lead, o_foll, o_drv, o_pj, o_blk;
+    int o_ellt, img_bytes;      // the cold column (enterLaneLinkTime) is worked on in place in the image
+    // working-set-only arrays (they start where the image's cold column starts)
+    int o_dn, o_npos, o_nspd, o_nblk, o_xlist, o_leave, o_ent, o_fresh, o_mvslot, o_mvto, o_mvq, o_mvpj,
+        o_scan, o_avail, o_tmpl, o_spawn, smem_bytes;
 };
 
 struct StepArgs {
@@ -171,29 +173,37 @@ __device__ __forceinline__ int trunc_int_x86(double x) {
     return (int) x;
 }
 
-#define SMEM_TEMPLATES 4
-#define SCATTER_PER 8    // vehicles per thread the register-staged re-pack can hold   // vehicle templates cached in shared memory (more: read from global)
+#define SMEM_TEMPLATES 4      // vehicle templates cached in shared memory (more: read from global)
 
 struct Ctx {
     RepHeader *h;
-    u16 *cnt, *off, *wq, *leave, *ent, *newslot, *entlist, *entdrv, *xlist;
-    u32 *dn, *dn2;        // per vehicle: drivable | next drivable << 16 (0xFFFF = route ends)
+    // per drivable: vehicle count and the ends of its list (front = head, back = tail)
+    u16 *cnt, *head, *tail, *wq, *leave, *ent;
+    // per vehicle slot.  Slots are STABLE: a vehicle keeps its slot from spawn to finish; order on a drivable is
+    // the doubly linked list lead (vehicle ahead) / foll (vehicle behind).
+    u16 *lead, *foll;
+    u16 *xlist, *alist;   // per-tick work lists (heads / cross phase share one, intersection zone the other)
+    u16 *mv_slot, *mv_to; // this tick's movers: slot, new drivable (NONE16 = route ends)
+    int *mv_q;            // ... new route cursor
+    u8 *mv_pj;            // ... skipped a whole drivable
+    u32 *dn;              // per vehicle: drivable | next drivable << 16 (0xFFFF = route ends)
     u32 *avail;           // bit per lane-link: its road-link is green in the signal's current phase
     const double *tmpl;   // vehicle templates (shared-memory copy when they fit)
-    u8 *sraw, *scur, *schg, *pj, *pj2, *nflag, *fresh;
-    int *stop, *rpos, *vid, *vid2, *ellt, *ellt2, *nrpos, *scan;
+    u8 *sraw, *scur, *schg, *pj, *fresh;
+    int *stop, *rpos, *vid, *ellt, *scan;
     int *sp_lane, *sp_vid, *sp_tick;   // head of every spawn lane's waiting buffer
     const int *lso;                    // this replica's flow set: row of lane_spawn_off
+    // kinematics ping-pong: every tick reads pos / spd / blk and writes npos / nspd / nblk, then they swap
     short *blk, *nblk;
-    double *pos, *spd, *npos, *nspd, *entpos;
+    double *pos, *spd, *npos, *nspd;
     int tick;
     unsigned long long *pt;   // debug phase timing (NULL = off)
     long long pt_last;
 };
 
 // phase ids of the debug timing
-enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1A, PT_PHASE1, PT_PHASE1C, PT_PHASE2, PT_COUNT_SCAN, PT_NEWSLOT, PT_SCATTER, PT_RETRIEVE,
-       PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_NPAIR, PT_N };
+enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1A, PT_PHASE1, PT_PHASE1C, PT_PHASE2, PT_LEAVE, PT_ENTER, PT_COMPACT, PT_RETRIEVE,
+       PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_NENT, PT_N };
 __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
     if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
 }
@@ -315,27 +325,24 @@ template <bool ONE_T>
 __device__ int cross_claimant(const DevScn &S, const Ctx &c, const CrossEntry &X, double *d2) {
     const int f = X.foe_ll, fl = S.L + f;
     const double dc = X.foe_dist;
-    int n = c.cnt[X.foe_end_lane];
-    if (n > 0) {   // the vehicle that has just moved onto the end lane
-        int t = c.off[X.foe_end_lane] + n - 1;
+    if (c.cnt[X.foe_end_lane] > 0) {   // the vehicle that has just moved onto the end lane
+        const int t = c.tail[X.foe_end_lane];
         double crossDistance = X.foe_len - dc;
         double vehDistance = c.pos[t] - tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN];
-        if (crossDistance + vehDistance < 0.0 && !c.pj[t] && __ldg(S.route_seq + c.rpos[t] - 1) == fl) {
+        if (crossDistance + vehDistance < 0.0 && !(c.pj[t] & 1) && __ldg(S.route_seq + c.rpos[t] - 1) == fl) {
             *d2 = -(c.pos[t] + crossDistance);
             return t;
         }
     }
-    n = c.cnt[fl];
-    int base = c.off[fl];
-    for (int k = 0; k < n; ++k) {   // vehicles on the link, front to back
-        int v = base + k;
+    int n = c.cnt[fl];
+    for (int v = n > 0 ? (int) c.head[fl] : (int) NONE16; n > 0 && v != (int) NONE16; --n, v = c.foll[v]) {   // vehicles on the link, front to back
         double vd = c.pos[v];
         if (vd > dc) {
             if (vd - dc - tmpl_of<ONE_T>(S, c, c.vid[v])[TSC_T_LEN] <= 0.0) { *d2 = dc - vd; return v; }
         } else { *d2 = dc - vd; return v; }
     }
     if (c.cnt[X.foe_start_lane] > 0 && ll_available(c, f)) {   // first vehicle of the incoming lane, heading here on green
-        int hd = c.off[X.foe_start_lane];
+        int hd = c.head[X.foe_start_lane];
         if ((int) (c.dn[hd] >> 16) == fl) {
             *d2 = (X.foe_sl_len - c.pos[hd]) + dc;
             return hd;
@@ -397,50 +404,8 @@ __device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T,
     return yield == -1;
 }
 
-// ---- block-wide exclusive scan of u16 counts into u16 offsets -------------------
-// in[i] (+ extra[i] if given) for i < n; out[n] = total.  All threads call.
-// With `cnt` / `leave` given, in[i] is first set to cnt[i] - leave[i] + in[i] (a tick's new per-drivable counts).
-template <int NT>
-__device__ void block_scan_counts(u16 *in, const u8 *extra_lane, int n_lane, u16 *out, int n, int *scratch,
-                                  const u16 *cnt = nullptr, const u16 *leave = nullptr) {
-    const int per = (n + NT - 1) / NT;
-    int lo = threadIdx.x * per, hi = min(lo + per, n);
-    int s = 0;
-    if (cnt)
-        for (int i = lo; i < hi; ++i) in[i] = (u16) (cnt[i] - leave[i] + in[i]);
-    for (int i = lo; i < hi; ++i) s += in[i] + ((extra_lane && i < n_lane) ? extra_lane[i] : 0);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) scratch[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        int ws = lane < NT / 32 ? scratch[lane] : 0;
-        int wi = ws;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += t;
-        }
-        if (lane < NT / 32) scratch[lane] = wi - ws;
-        if (lane == NT / 32 - 1) scratch[32] = wi;
-    }
-    __syncthreads();
-    int run = scratch[w] + incl - s;
-    for (int i = lo; i < hi; ++i) {
-        out[i] = (u16) run;
-        run += in[i] + ((extra_lane && i < n_lane) ? extra_lane[i] : 0);
-    }
-    if (threadIdx.x == 0) out[n] = (u16) scratch[32];
-    __syncthreads();
-}
-
-// Commit one vehicle's decision into the tick's buffers: clamp the speed, advance
-// along the route, and register the move if it leaves its drivable (A.4).
+// Commit one vehicle's decision into the tick's next-state buffers: clamp the speed, advance along the
+// route, and register the move if it leaves its drivable (A.4).
 __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y, Ctx &c, int i, const double *T, int d, int rp,
                                                double x, double v, double dlen, double ns, int blocker) {
     const double dt = DT;
@@ -459,71 +424,167 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
         ++q; dd = nxt; ++hops;
         cl = __ldg(S.drv_length + dd);
     }
-    c.npos[i] = nx; c.nspd[i] = ns; c.nrpos[i] = q; c.nblk[i] = (short) blocker;
-    u8 fl = 8;                       // bit3: valid vehicle
-    if (hops > 0 || end) fl |= 1;    // leaves its drivable
-    if (end) fl |= 2;
-    if (hops > 1) fl |= 4;           // skipped a whole drivable
-    c.nflag[i] = fl;
-    if (fl & 1) {
+    c.npos[i] = nx; c.nspd[i] = ns; c.nblk[i] = (short) blocker;
+    if (hops > 0 || end) {           // leaves its drivable: the list surgery at the end of the tick moves it
+        c.pj[i] |= PJ_MOVER;
         atomicAdd((unsigned *) &c.leave[d & ~1], (d & 1) ? 0x10000u : 1u);
-        if (!end) {
-            atomicAdd((unsigned *) &c.ent[dd & ~1], (dd & 1) ? 0x10000u : 1u);
-            int k = atomicAdd(&c.h->n_ent, 1);
-            if (k < Y.ent_cap) { c.entlist[k] = (u16) i; c.entdrv[k] = (u16) dd; c.entpos[k] = nx; }
-        }
+        if (!end) atomicAdd((unsigned *) &c.ent[dd & ~1], (dd & 1) ? 0x10000u : 1u);
+        const int k = atomicAdd(&c.h->n_ent, 1);
+        if (k < Y.ent_cap) {
+            c.mv_slot[k] = (u16) i; c.mv_to[k] = end ? (u16) NONE16 : (u16) dd; c.mv_q[k] = q; c.mv_pj[k] = hops > 1 ? 1 : 0;
+        } else atomicOr(&c.h->err, ERR_ENT_OVERFLOW);
     }
 }
 
+// ---- stable compaction of the vehicle slots (holes left by finished vehicles squeezed out) ----
+// Rare: runs at the start of a tick once HOLE_MAX holes have piled up, or when the spawns of the tick could
+// run out of slots.  Live slots keep their relative order; every slot reference (list links, blockers, list
+// ends) is renumbered.  Rounds of NT slots: a round's sources are read into registers before any of its
+// destinations (all at or below the sources) is written.
+template <int NT>
+__device__ void compact_slots(const DevScn &S, const Layout &Y, Ctx &c) {
+    const int tid = threadIdx.x;
+    const int n = c.h->n_slots;
+    u16 *map = c.xlist;          // dead between ticks
+    // exclusive scan of the live flags: thread t owns the contiguous chunk [t * per, (t + 1) * per)
+    const int per = (n + NT - 1) / NT;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int live = 0;
+    for (int i = lo; i < hi; ++i) live += c.vid[i] >= 0;
+    const int lane = tid & 31, w = tid >> 5;
+    int incl = live;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) c.scan[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int ws = lane < NT / 32 ? c.scan[lane] : 0;
+        int wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < NT / 32) c.scan[lane] = wi - ws;
+        if (lane == NT / 32 - 1) c.scan[32] = wi;
+    }
+    __syncthreads();
+    int run = c.scan[w] + incl - live;
+    for (int i = lo; i < hi; ++i) {
+        const bool lv = c.vid[i] >= 0;
+        map[i] = lv ? (u16) run : (u16) NONE16;
+        run += lv;
+    }
+    __syncthreads();
+    const int n_live = c.scan[32];
+    for (int d = tid; d < S.D; d += NT) {
+        if (c.cnt[d] > 0) { c.head[d] = map[c.head[d]]; c.tail[d] = map[c.tail[d]]; }
+    }
+    for (int i0 = 0; i0 < n; i0 += NT) {
+        const int i = i0 + tid;
+        const int dst = i < n ? (int) map[i] : (int) NONE16;
+        double p = 0, s = 0;
+        int rp = 0, vd = 0, el = 0;
+        u32 dnv = 0;
+        u16 ld = NONE16, fo = NONE16;
+        short bk = -1;
+        u8 pjv = 0;
+        if (dst != (int) NONE16) {
+            p = c.pos[i]; s = c.spd[i]; rp = c.rpos[i]; vd = c.vid[i]; dnv = c.dn[i]; pjv = c.pj[i];
+            el = (int) (dnv & 0xFFFF) >= S.L ? c.ellt[i] : INT_MAX;
+            ld = c.lead[i]; fo = c.foll[i];
+            if (ld != NONE16) ld = map[ld];
+            if (fo != NONE16) fo = map[fo];
+            int b = c.blk[i];
+            if (b >= 0) { const u16 nb = map[b]; b = nb == NONE16 ? -1 : (int) nb; }
+            bk = (short) b;
+        }
+        __syncthreads();
+        if (dst != (int) NONE16) {
+            c.pos[dst] = p; c.spd[dst] = s; c.rpos[dst] = rp; c.vid[dst] = vd; c.dn[dst] = dnv; c.pj[dst] = pjv;
+            if ((int) (dnv & 0xFFFF) >= S.L) c.ellt[dst] = el;
+            c.lead[dst] = ld; c.foll[dst] = fo; c.blk[dst] = bk;
+        }
+    }
+    __syncthreads();
+    for (int i = n_live + tid; i < n; i += NT) { c.vid[i] = -1; c.blk[i] = -1; c.nblk[i] = -1; }
+    if (tid == 0) c.h->n_slots = n_live;
+    __syncthreads();
+}
+
 // ----------------------------------------------------------------------------
-// One engine tick for the replica held in shared memory (A.2)
+// One engine tick for the replica held in the working set (A.2)
 // ----------------------------------------------------------------------------
-template <int NT, bool STAGED, bool ONE_T>
-__device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *is_spawn_lane) {
+template <int NT, bool ONE_T>
+__device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
     const int tid = threadIdx.x;
     const int tick = c.h->tick;
     const double dt = DT;
-    const int L = S.L, D = S.D;
-    const int n_slots = c.h->n_slots;
+    const int L = S.L;
     if (c.h->err) {   // a replica that overflowed or lost its order is frozen: its result is reported invalid by tsc_check
         __syncthreads();
         if (tid == 0) c.h->tick = tick + 1;
         __syncthreads();
         return;
     }
+    {   // holes left by finished vehicles are squeezed out now and then (uniform decision: every thread reads the same header)
+        const int ns = c.h->n_slots, holes = ns - c.h->n_running;
+        if (holes >= HOLE_MAX || (holes > 0 && ns + S.n_spawn_lanes > Y.Vcap)) {
+            compact_slots<NT>(S, Y, c);
+            pt_mark(c, PT_COMPACT);
+        }
+    }
+    const int n_old = c.h->n_slots;
 
     // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer.  The head of every
-    //      buffer (lane, vehicle, creation tick) is cached in shared memory, so a tick without an arrival
-    //      costs one compare per spawn lane.  The move counters were reset and the non-empty drivables
-    //      listed for sub-phase 1a when the previous tick (or the launch prologue) finished: a lane that
-    //      receives its only vehicle here adds itself.
+    //      buffer (lane, vehicle, creation tick) is cached in the working set, so a tick without an arrival
+    //      costs one compare per spawn lane.  The first warp serves the spawn lanes 32 at a time: a new
+    //      vehicle's slot is n_slots + its rank among the lanes that spawn (ballot), so slot numbers do
+    //      not depend on thread timing.  Meanwhile every thread lists the head vehicles (no vehicle ahead on
+    //      their drivable) for sub-phase 1a.
     //      getAction is split so that every sub-phase runs the same code in all its lanes:
-    //      1a  head vehicles (one per non-empty drivable): look-ahead leader + gap
+    //      1a  head vehicles: look-ahead leader + gap
     //      1b  every vehicle: car following; vehicles in an intersection zone go on a list
     //      1c  listed vehicles: red light / blocked exit / turn speed; those that must examine
     //          the crosses of a lane-link go on a second list
     //      2   a group of lanes per vehicle of the second list, one lane per cross ----
     u16 *hlist = c.xlist;      // dead before 1c fills xlist
-    u16 *alist = c.newslot;    // dead before the new slots are computed
-    for (int s = tid; s < S.n_spawn_lanes; s += NT) {
-        const int l = c.sp_lane[s];
-        u8 fr = 0;
-        if (c.sp_tick[s] <= tick) {
-            const int v = c.sp_vid[s];
-            const int n = c.cnt[l];
-            bool ok = true;
-            if (n > 0) {
-                int t = c.off[l] + n - 1;
-                ok = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, v)[TSC_T_MIN_GAP];
+    u16 *alist = c.alist;
+    if (tid < 32) {
+        int base = n_old, spawned = 0;
+        for (int s0 = 0; s0 < S.n_spawn_lanes; s0 += 32) {
+            const int s = s0 + tid;
+            bool want = false;
+            int l = 0, v = 0, n = 0;
+            if (s < S.n_spawn_lanes) {
+                l = c.sp_lane[s];
+                if (c.sp_tick[s] <= tick) {
+                    v = c.sp_vid[s];
+                    n = c.cnt[l];
+                    want = true;
+                    if (n > 0) {
+                        const int t = c.tail[l];
+                        want = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, v)[TSC_T_MIN_GAP];
+                    }
+                }
             }
-            if (ok) {
-                int slot = c.off[l] + n;
-                int rp0 = __ldg(S.veh_seq_start + v);
+            const unsigned m = __ballot_sync(0xffffffffu, want);
+            const int slot = base + __popc(m & ((1u << tid) - 1u));
+            if (want && slot >= Y.Vcap) { atomicOr(&c.h->err, ERR_OVERFLOW); want = false; }
+            if (want) {
+                const int rp0 = __ldg(S.veh_seq_start + v);
                 c.pos[slot] = 0.0; c.spd[slot] = 0.0;
                 c.rpos[slot] = rp0;
                 c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
                 c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
                 c.pj[slot] = 0;
+                c.foll[slot] = (u16) NONE16;
+                if (n > 0) { const int t = c.tail[l]; c.lead[slot] = (u16) t; c.foll[t] = (u16) slot; }
+                else { c.lead[slot] = (u16) NONE16; c.head[l] = (u16) slot; hlist[atomicAdd(&c.h->n_h, 1)] = (u16) slot; }
+                c.tail[l] = (u16) slot;
                 c.cnt[l] = (u16) (n + 1);
                 const int hd = c.wq[s] + 1;
                 c.wq[s] = (u16) hd;
@@ -532,23 +593,28 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                     const int nv = __ldg(S.lane_spawn_vid + at);
                     c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
                 } else c.sp_tick[s] = INT_MAX;
-                fr = 1;
-                atomicAdd(&c.h->n_running, 1);
-                if (n == 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) l;
+                ++spawned;
             }
+            if (s < S.n_spawn_lanes) c.fresh[l] = want ? 1 : 0;
+            base += __popc(m);
         }
-        c.fresh[l] = fr;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) spawned += __shfl_xor_sync(0xffffffffu, spawned, o);
+        if (tid == 0) { c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned; }
     }
+    for (int i = tid; i < n_old; i += NT)      // the heads among the vehicles that were here before this tick
+        if (c.vid[i] >= 0 && c.lead[i] == NONE16) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) i;
     __syncthreads();
     pt_mark(c, PT_SPAWN);
+    const int n_slots = c.h->n_new;
 
     // 1a: leader and gap of head vehicles as of the end of the previous tick (A.7): vehicles that
     // entered from the waiting buffer this tick are not yet visible to others
     for (int e = tid, n_h = c.h->n_h; e < n_h; e += NT) {
-        const int d = hlist[e];
-        const int i = c.off[d];
+        const int i = hlist[e];
         const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
         const u32 dnv = c.dn[i];
+        const int d = dnv & 0xFFFF;
         const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
         const int rp = c.rpos[i];
         int leader = -1;
@@ -563,9 +629,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 // all lane-links leaving that lane, in roadnet order: one packed load for up to three of them
                 const int4 sib = __ldg(S.lane_sib + sl);
                 auto consider = [&](int dl) {
-                    int n = c.cnt[dl];
-                    if (n > 0) {
-                        int cand = c.off[dl] + n - 1;
+                    if (c.cnt[dl] > 0) {
+                        int cand = c.tail[dl];
                         double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
                         if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
                     }
@@ -580,9 +645,11 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
                 }
                 if (leader >= 0) break;
             } else {
-                int n = c.cnt[nd] - c.fresh[nd];
-                if (n > 0) {
-                    leader = c.off[nd] + n - 1;
+                const int n = c.cnt[nd] - c.fresh[nd];
+                if (n > 0) {      // the lane's last vehicle, not counting one that left the waiting buffer this tick
+                    int t = c.tail[nd];
+                    if (c.fresh[nd]) t = c.lead[t];
+                    leader = t;
                     gap = dist + c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN];
                     break;
                 }
@@ -595,14 +662,14 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     __syncthreads();
     if (tid == 0) {
         if (c.pt) atomicAdd(c.pt + PT_NH, (unsigned long long) c.h->n_h);
-        c.h->n_h = 0;       // every thread has read it; the end of the tick lists the next tick's heads
+        c.h->n_h = 0;       // every thread has read it
     }
     pt_mark(c, PT_PHASE1A);
 
     // 1b: next speed from acceleration, speed limits and the car-following law (A.4)
     for (int i = tid; i < n_slots; i += NT) {
         int vid = c.vid[i];
-        if (vid < 0) { c.nflag[i] = 0; continue; }
+        if (vid < 0) continue;
         const double *T = tmpl_of<ONE_T>(S, c, vid);
         const u32 dnv = c.dn[i];
         const int d = dnv & 0xFFFF;
@@ -610,12 +677,10 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         const double x = c.pos[i], v = c.spd[i];
         const double2 lm = __ldg(S.drv_lm + d);       // length, speed limit: one 16-byte load
         const double dlen = lm.x;
-        int leader;
+        int leader = c.lead[i];
         double gap;
-        if (i > c.off[d]) {
-            leader = i - 1;
-            gap = c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN] - x;
-        } else { leader = c.nblk[i]; gap = c.npos[i]; }
+        if (leader != (int) NONE16) gap = c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN] - x;
+        else { leader = c.nblk[i]; gap = c.npos[i]; }
         double ns = T[TSC_T_MAX_SPEED];
         ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
         ns = min2(ns, lm.y);
@@ -647,9 +712,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
             const int ll = (int) (dnv >> 16) - L;
             const int el = __ldg(&S.llinfo[ll].end_lane);
             bool enter = true;
-            int n = c.cnt[el];
-            if (n > 0) {
-                int t = c.off[el] + n - 1;
+            if (c.cnt[el] > 0) {
+                int t = c.tail[el];
                 enter = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
             }
             if (!ll_available(c, ll) || !enter) {
@@ -664,86 +728,23 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
         }
         if (!done) {   // phase 2 examines the crosses of the lane-link
             c.npos[i] = vi;
-            const int e = atomicAdd(&c.h->n_x, 1);
-            c.xlist[e] = (u16) i;
-            if (!STAGED && Y.pair_cap > 0) {     // one (vehicle, cross) pair per cross of the link
-                const int ll = d >= L ? d - L : (int) (dnv >> 16) - L;
-                const int2 cr = __ldg((const int2 *) &S.llinfo[ll].cross_off);
-                const int nc = cr.y - cr.x;
-                u32 *pairs = c.dn2;
-                ((u32 *) c.vid2)[e] = 0xFFFFFFFFu;
-                const int p0 = atomicAdd(&c.h->n_pairs, nc);
-                if (p0 + nc <= Y.pair_cap)
-                    for (int k = 0; k < nc; ++k) pairs[p0 + k] = ((u32) e << 8) | (u32) k;
-            }
+            c.xlist[atomicAdd(&c.h->n_x, 1)] = (u16) i;
             continue;
         }
         ns = min2(ns, vi);
         finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
     }
     __syncthreads();
-    if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); atomicAdd(c.pt + PT_NPAIR, (unsigned long long) c.h->n_pairs); }
+    if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); }
     pt_mark(c, PT_PHASE1C);
 
     // ---- getAction, phase 2: Cross::canPass for every cross ahead of every deferred vehicle.  canPass
     //      has no side effects, so all crosses are evaluated at once and the first refusal in link order
-    //      is the sequential scan of A.5(iii).
-    //      Optional flat form (TSC_B200_FLAT_CROSS=1): one thread per (vehicle, cross) pair listed by 1c, the
-    //      first refusal found by an atomicMin on (cross position in the link << 16 | announced vehicle),
-    //      then one thread per vehicle commits.  Default (and the flat form's fallback when the list
-    //      overflows): a group of lanes per vehicle, one lane per cross, group width chosen per tick. ----
-    const int n_x = c.h->n_x;
-    if (!STAGED && Y.pair_cap > 0 && c.h->n_pairs <= Y.pair_cap) {
-        const int n_pairs = c.h->n_pairs;
-        const u32 *pairs = c.dn2;
-        u32 *first_refusal = (u32 *) c.vid2;
-        for (int p = tid; p < n_pairs; p += NT) {
-            const u32 pr = pairs[p];
-            const int e = (int) (pr >> 8), k = (int) (pr & 0xFFu);
-            const int i = c.xlist[e];
-            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
-            const u32 dnv = c.dn[i];
-            const int d = dnv & 0xFFFF;
-            const bool on_ll = d >= L;
-            const int ll = on_ll ? d - L : (int) (dnv >> 16) - L;
-            const double dts = on_ll ? c.pos[i] : -(__ldg(S.drv_length + d) - c.pos[i]);
-            const int4 head = __ldg((const int4 *) &S.llinfo[ll]);   // start_lane, end_lane, cross_off, cross_end
-            const int t1 = __ldg(&S.llinfo[ll].type);
-            CrossEntry X;
-            const int4 *src = (const int4 *) &S.cross[head.z + k];
-            int4 *dst = (int4 *) &X;
-            dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
-            int foe = -1;
-            if (!(X.dist < dts) && !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe))
-                atomicMin(first_refusal + e, ((u32) k << 16) | (u32) foe);
-        }
-        __syncthreads();
-        for (int e = tid; e < n_x; e += NT) {
-            const int i = c.xlist[e];
-            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
-            const u32 dnv = c.dn[i];
-            const int d = dnv & 0xFFFF;
-            const bool on_ll = d >= L;
-            const int ll = on_ll ? d - L : (int) (dnv >> 16) - L;
-            const double x = c.pos[i], v = c.spd[i];
-            const double dlen = __ldg(S.drv_length + d);
-            const double dts = on_ll ? x : -(dlen - x);
-            double vi = c.npos[i], ns = c.nspd[i];
-            int blocker = -1;
-            const u32 fr = first_refusal[e];
-            if (fr != 0xFFFFFFFFu) {
-                const double dOn = __ldg(&S.cross[__ldg(&S.llinfo[ll].cross_off) + (int) (fr >> 16)].dist);
-                vi = min2(vi, stop_before_speed(T, v, dOn - dts - T[TSC_T_YIELD_DIST]));
-                blocker = (int) (fr & 0xFFFFu);
-            }
-            ns = min2(ns, vi);
-            finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
-        }
-    } else {
-        // a group of G lanes (a whole warp, or a half / quarter of one: links rarely have more than a dozen
-        // crosses) per vehicle, one lane per cross; groups of one warp work on different vehicles
-        // cross_group = 0 (default): the widest group that still gives every listed vehicle its own group in
-        // one round -- 16 lanes for up to NT/16 vehicles, 8, 4, then 2
+    //      is the sequential scan of A.5(iii): a group of G lanes (a whole warp, or a half / quarter of one:
+    //      links rarely have more than a dozen crosses) per vehicle, one lane per cross; cross_group = 0
+    //      (default): the widest group that still gives every listed vehicle its own group in one round ----
+    {
+        const int n_x = c.h->n_x;
         int G = Y.cross_group;
         if (G == 0) G = n_x * 16 <= NT ? 16 : (n_x * 8 <= NT ? 8 : (n_x * 4 <= NT ? 4 : 2));
         const int lane = tid & 31, sl = lane & (G - 1);
@@ -792,153 +793,102 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c, const u8 *
     __syncthreads();
     pt_mark(c, PT_PHASE2);
 
-    // ---- updateLocation: new per-drivable counts, then a stable re-pack ----
-    // leave[] = number of leavers, new count = cnt - leave + ent (kept in ent[])
-    u16 *noff = (u16 *) (c.scan + 64);
-    block_scan_counts<NT>(c.ent, is_spawn_lane, L, noff, D, c.scan, c.cnt, c.leave);
-    const int n_ent = min(c.h->n_ent, Y.ent_cap);
-    if (tid == 0) {
-        if (c.h->n_ent > Y.ent_cap) c.h->err |= ERR_ENT_OVERFLOW;
-        if (noff[D] > Y.Vcap) c.h->err |= ERR_OVERFLOW;
-    }
-    const bool overflow = noff[D] > Y.Vcap;
-    pt_mark(c, PT_COUNT_SCAN);
-    // destination slot of every vehicle
-    for (int i = tid; i < n_slots; i += NT) {
-        u8 fl = c.nflag[i];
-        u16 ns = 0xFFFF;
-        if (fl & 8) {
-            int d = c.dn[i] & 0xFFFF;
-            int rank = i - c.off[d];
-            int nl = c.leave[d];
-            if (!(fl & 1)) {
-                if (rank < nl) atomicOr(&c.h->err, ERR_ORDER);
-                ns = (u16) (noff[d] + rank - nl);
-            } else {
-                if (rank >= nl) atomicOr(&c.h->err, ERR_ORDER);
-                if (!(fl & 2)) {
-                    int dd = __ldg(S.route_seq + c.nrpos[i]);
-                    double nx = c.npos[i];
-                    int myv = c.vid[i];
-                    int ahead = 0;
-                    for (int k = 0; k < n_ent; ++k) {
-                        if (c.entdrv[k] != dd) continue;
-                        int o = c.entlist[k];
-                        if (o == i) continue;
-                        double ox = c.entpos[k];
-                        if (ox > nx || (ox == nx && c.vid[o] < myv)) ++ahead;
-                    }
-                    ns = (u16) (noff[dd] + (c.cnt[dd] - c.leave[dd]) + ahead);
-                }
-            }
-        }
-        c.newslot[i] = ns;
-    }
-    __syncthreads();
-    pt_mark(c, PT_NEWSLOT);
-    if (overflow || c.h->err) {   // keep the old state; the sticky flag reports it
+    // ---- updateLocation.  Slots are stable, so there is nothing to re-pack: every vehicle's next state is
+    //      already in the next-state buffers, and only the movers of the tick (a few dozen) touch the lists.
+    //      Leaving: movers are a prefix of their drivable's list (FIFO); the mover at its head walks the prefix
+    //      and hands the head over.  Entering (after a barrier): entrants go behind the vehicles that stay,
+    //      ordered by new distance (descending, ties by creation id); one thread per entered drivable. ----
+    const int n_mv = c.h->n_ent;
+    if (c.h->err) {   // mover list overflow / no slot left: keep the old state; the sticky flag reports it
         __syncthreads();
-        if (tid == 0) c.h->tick = tick + 1;
+        if (tid == 0) { c.h->tick = tick + 1; c.h->n_slots = n_slots; }      // (vehicles that did enter before the slots ran out stay listed)
         __syncthreads();
         return;
     }
-    // finished vehicles: statistics (A.8)
-    for (int i = tid; i < n_slots; i += NT) {
-        if ((c.nflag[i] & 10) == 10) {
-            int vt = __ldg(S.veh_tick + c.vid[i]);
+    for (int m = tid; m < n_mv; m += NT) {
+        const int i = c.mv_slot[m];
+        const int d = c.dn[i] & 0xFFFF;
+        const int ld = c.lead[i];
+        if (ld == (int) NONE16) {      // head of its drivable: hand the head over to the first vehicle that stays
+            int k = 0, v = i;
+            while (v != (int) NONE16 && (c.pj[v] & PJ_MOVER) && k < Y.Vcap) { ++k; v = c.foll[v]; }
+            c.head[d] = (u16) v;
+            if (v != (int) NONE16) c.lead[v] = (u16) NONE16; else c.tail[d] = (u16) NONE16;
+            if (k != (int) c.leave[d]) atomicOr(&c.h->err, ERR_ORDER);
+            c.cnt[d] = (u16) (c.cnt[d] - k);
+            c.leave[d] = 0;
+        } else if (!(c.pj[ld] & PJ_MOVER)) atomicOr(&c.h->err, ERR_ORDER);      // left although the vehicle ahead stays
+        if (c.mv_to[m] == NONE16) {    // finished: statistics (A.8); the slot becomes a hole
+            const int vt = __ldg(S.veh_tick + c.vid[i]);
             atomicAdd((unsigned long long *) &c.h->cum_tt, (unsigned long long) (tick - vt));
             atomicAdd((unsigned long long *) &c.h->fin_enter, (unsigned long long) vt);
             atomicAdd(&c.h->n_finished, 1);
             atomicSub(&c.h->n_running, 1);
+            c.vid[i] = -1; c.nblk[i] = -1;
         }
-    }
-    // scatter: kinematics come from the n* arrays into the (distinct) persistent columns.  The
-    // identity columns are permuted in place: every thread first pulls its vehicles' identities into
-    // registers, a barrier retires all reads, then they are stored at the new slots.  Replicas too
-    // large for that (Vcap > SCATTER_PER * NT) ping-pong between two copies instead, and so do
-    // replicas small enough to afford the second copy: it is the faster of the two (1.330 vs 1.343 ms).
-    if (STAGED) {
-        int r_vid[SCATTER_PER], r_ellt[SCATTER_PER];
-        u32 r_dn[SCATTER_PER];
-        u16 r_dst[SCATTER_PER];
-        u8 r_pj[SCATTER_PER];
-#pragma unroll
-        for (int k = 0; k < SCATTER_PER; ++k) {
-            const int i = tid + k * NT;
-            r_dst[k] = 0xFFFF;
-            if (i >= n_slots) continue;
-            const u16 dst = c.newslot[i];
-            if (dst == 0xFFFF) continue;
-            r_dst[k] = dst;
-            const u8 fl = c.nflag[i];
-            const int q = c.nrpos[i];
-            c.pos[dst] = c.npos[i]; c.spd[dst] = c.nspd[i]; c.rpos[dst] = q;
-            int bk = c.nblk[i];
-            if (bk >= 0) { u16 nb = c.newslot[bk]; bk = (nb == 0xFFFF) ? -1 : (int) nb; }
-            c.blk[dst] = (short) bk;
-            r_vid[k] = c.vid[i];
-            if (fl & 1) {
-                int dd = __ldg(S.route_seq + q);
-                r_dn[k] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
-                r_ellt[k] = dd >= L ? tick : INT_MAX;
-                r_pj[k] = (fl & 4) ? 1 : 0;
-            } else { r_dn[k] = c.dn[i]; r_ellt[k] = (int) (r_dn[k] & 0xFFFF) >= L ? c.ellt[i] : INT_MAX; r_pj[k] = c.pj[i]; }
-        }
-        __syncthreads();
-        for (int s = tid; s < S.n_spawn_lanes; s += NT) {
-            int l = c.sp_lane[s];
-            c.vid[noff[l + 1] - 1] = -1;         // the lane's spare slot (the last of its range) stays empty
-        }
-#pragma unroll
-        for (int k = 0; k < SCATTER_PER; ++k) {
-            const u16 dst = r_dst[k];
-            if (dst == 0xFFFF) continue;
-            c.vid[dst] = r_vid[k]; c.dn[dst] = r_dn[k]; c.ellt[dst] = r_ellt[k]; c.pj[dst] = r_pj[k];
-        }
-    } else {
-        for (int s = tid; s < S.n_spawn_lanes; s += NT) {
-            int l = c.sp_lane[s];
-            c.vid2[noff[l + 1] - 1] = -1;        // the lane's spare slot (the last of its range) stays empty
-        }
-        for (int i = tid; i < n_slots; i += NT) {
-            u16 dst = c.newslot[i];
-            if (dst == 0xFFFF) continue;
-            u8 fl = c.nflag[i];
-            int q = c.nrpos[i];
-            c.pos[dst] = c.npos[i]; c.spd[dst] = c.nspd[i]; c.rpos[dst] = q;
-            int bk = c.nblk[i];
-            if (bk >= 0) { u16 nb = c.newslot[bk]; bk = (nb == 0xFFFF) ? -1 : (int) nb; }
-            c.blk[dst] = (short) bk;
-            c.vid2[dst] = c.vid[i];
-            if (fl & 1) {
-                int dd = __ldg(S.route_seq + q);
-                c.dn2[dst] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
-                c.ellt2[dst] = dd >= L ? tick : INT_MAX;
-                c.pj2[dst] = (fl & 4) ? 1 : 0;
-            } else {
-                // enterLaneLinkTime is INT_MAX on every lane: only vehicles staying on a lane-link read the (cold) column
-                const u32 dnv = c.dn[i];
-                c.dn2[dst] = dnv; c.ellt2[dst] = (int) (dnv & 0xFFFF) >= L ? c.ellt[i] : INT_MAX; c.pj2[dst] = c.pj[i];
-            }
-        }
-        { int *t = c.vid; c.vid = c.vid2; c.vid2 = t; }
-        { int *t = c.ellt; c.ellt = c.ellt2; c.ellt2 = t; }
-        { u32 *t = c.dn; c.dn = c.dn2; c.dn2 = t; }
-        { u8 *t = c.pj; c.pj = c.pj2; c.pj2 = t; }
-    }
-    // new counts and offsets; move counters reset and non-empty drivables listed for the next tick
-    for (int d = tid; d < D; d += NT) {
-        const int n = c.ent[d];
-        c.cnt[d] = (u16) n; c.off[d] = noff[d];
-        c.leave[d] = 0; c.ent[d] = 0;
-        if (n > 0) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) d;
-    }
-    if (tid == 0) {
-        c.off[D] = noff[D]; c.h->n_slots = noff[D]; c.h->tick = tick + 1;
-        c.h->n_ent = 0; c.h->n_x = 0; c.h->n_a = 0; c.h->n_pairs = 0;      // scratch counters of the next tick
     }
     __syncthreads();
-    pt_mark(c, PT_SCATTER);
+    pt_mark(c, PT_LEAVE);
+    for (int m = tid; m < n_mv; m += NT) {
+        const int i = c.mv_slot[m];
+        const int dd = c.mv_to[m];
+        if (dd == (int) NONE16) { c.pj[i] = 0; continue; }
+        // the vehicle's own fields
+        const int q = c.mv_q[m];
+        c.rpos[i] = q;
+        c.dn[i] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
+        c.pj[i] = c.mv_pj[m];
+        if (dd >= L) c.ellt[i] = tick;      // enterLaneLinkTime is only read while the vehicle is on a lane-link
+        // the list of the drivable it enters
+        const int n_in = c.ent[dd];
+        if (n_in == 1) {
+            const int t = c.cnt[dd] > 0 ? (int) c.tail[dd] : (int) NONE16;
+            c.lead[i] = (u16) t; c.foll[i] = (u16) NONE16;
+            if (t != (int) NONE16) c.foll[t] = (u16) i; else c.head[dd] = (u16) i;
+            c.tail[dd] = (u16) i;
+            c.cnt[dd] = (u16) (c.cnt[dd] + 1);
+            c.ent[dd] = 0;
+        } else {
+            // several entrants: the one listed first appends them all, in order of new distance
+            bool first = true;
+            for (int k = 0; k < m; ++k) if (c.mv_to[k] == dd) { first = false; break; }
+            if (!first) continue;
+            int t = c.cnt[dd] > 0 ? (int) c.tail[dd] : (int) NONE16;
+            double last_x = 0.0;
+            int last_v = 0;
+            for (int r = 0; r < n_in; ++r) {      // selection in (distance desc, creation id asc) order
+                int best = -1;
+                double bx = 0.0;
+                int bv = 0;
+                for (int k = m; k < n_mv; ++k) {
+                    if (c.mv_to[k] != dd) continue;
+                    const int o = c.mv_slot[k];
+                    const double ox = c.npos[o];
+                    const int ov = c.vid[o];
+                    if (r > 0 && !(ox < last_x || (ox == last_x && ov > last_v))) continue;      // already placed
+                    if (best < 0 || ox > bx || (ox == bx && ov < bv)) { best = o; bx = ox; bv = ov; }
+                }
+                if (best < 0) break;
+                c.lead[best] = (u16) t; c.foll[best] = (u16) NONE16;
+                if (t != (int) NONE16) c.foll[t] = (u16) best; else c.head[dd] = (u16) best;
+                t = best; last_x = bx; last_v = bv;
+            }
+            c.tail[dd] = (u16) t;
+            c.cnt[dd] = (u16) (c.cnt[dd] + n_in);
+            c.ent[dd] = 0;
+        }
+    }
+    if (tid == 0) {
+        if (c.pt) atomicAdd(c.pt + PT_NENT, (unsigned long long) n_mv);
+        c.h->n_slots = n_slots; c.h->tick = tick + 1;
+        c.h->n_ent = 0; c.h->n_x = 0; c.h->n_a = 0;      // scratch counters of the next tick
+    }
+    // the next state becomes the current one
+    { double *t = c.pos; c.pos = c.npos; c.npos = t; }
+    { double *t = c.spd; c.spd = c.nspd; c.nspd = t; }
+    { short *t = c.blk; c.blk = c.nblk; c.nblk = t; }
+    __syncthreads();
+    pt_mark(c, PT_ENTER);
 }
 
 // ----------------------------------------------------------------------------
@@ -995,20 +945,21 @@ __device__ void lane_window(const DevScn &S, const Ctx &c, int l, bool tail, dou
     const double plen = __ldg(S.lane_pytsc_length + l);
     const double mspeed = __ldg(S.drv_max_speed + l);
     const int bins = (int) (plen / S.v_size);
-    const int n = c.cnt[l], base = c.off[l];
+    const int n = c.cnt[l];
     for (int k = 0; k < vis; ++k) w[k] = -1.0;
     if (bins > 0 && n > 0) {
         const int len = bins < vis ? vis : bins;     // padded length
         const int lo = tail ? len - vis : 0;         // window start in the padded list
         const double bin_size = plen / bins;
-        for (int k = 0; k < n; ++k) {
-            double p = round6(c.pos[base + k]);
+        int v = c.head[l];
+        for (int k = 0; k < n && v != (int) NONE16; ++k, v = c.foll[v]) {      // the lane's vehicles, front to back
+            double p = round6(c.pos[v]);
             if (p < 0) p = 0; else if (p > plen) p = plen;
             int bi = trunc_int_x86(py_floordiv(p, bin_size));
             if (bi >= bins) bi = bins - 1;
             const int wi = bi - lo;
             if (wi >= 0 && wi < vis) {
-                const double nsp = round6(c.spd[base + k]) / mspeed;
+                const double nsp = round6(c.spd[v]) / mspeed;
                 w[wi] += 1.0;
                 w[wi] += nsp;
             }
@@ -1177,31 +1128,28 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     const int tid = threadIdx.x;
     const int L = S.L, A = S.A;
     const tsc_outputs_t &O = a.out;
-    // scratch aliases (the n* arrays are free between ticks)
+    // scratch: the next-state kinematics pair (npos | nspd, contiguous, 16 bytes per laid-out slot) is free between ticks
     double *l_occ = c.npos;              // [L]
-    double *l_ms = c.npos + L;           // [L]
-    double *l_nms = c.npos + 2 * L;      // [L] mean speed / lane speed limit (metrics.py:113-135, traffic_signal.py:118)
-    double *s_loc = c.nspd;              // [A] local reward term
-    double *s_prs = c.nspd + A;          // [A] pressure
-    int *l_q = (int *) (c.nspd + 2 * A); // [L]
+    double *l_ms = l_occ + L;            // [L]
+    double *l_nms = l_ms + L;            // [L] mean speed / lane speed limit (metrics.py:113-135, traffic_signal.py:118)
+    double *s_loc = l_nms + L;           // [A] local reward term
+    double *s_prs = s_loc + A;           // [A] pressure
+    int *l_q = (int *) (s_prs + A);      // [L]
+    double *const r_tail = (double *) (l_q + ((L + 1) & ~1));      // what follows: position-matrix windows, or the host packet
     // registered host path: the replica's packet is assembled here, then stored to host memory in 16-byte pieces
-    unsigned char *const pkst = a.pk ? (unsigned char *) c.nrpos : nullptr;
+    unsigned char *const pkst = a.pk ? (unsigned char *) r_tail : nullptr;
 
     // --- Retriever._compute_lane_measurements (retriever.py:54-85) ---
     for (int l = tid; l < L; l += NT) {
-        int n = c.cnt[l], base = c.off[l];
+        const int n = c.cnt[l];
         int q = 0;
         double tot = 0.0;
-        int k = 0;
-        for (; k + 4 <= n; k += 4) {      // four loads in flight; the sum keeps the reference's front-to-back order
-            const double v0 = c.spd[base + k], v1 = c.spd[base + k + 1], v2 = c.spd[base + k + 2], v3 = c.spd[base + k + 3];
-            tot += v0; tot += v1; tot += v2; tot += v3;
-            q += (v0 < 0.1) + (v1 < 0.1) + (v2 < 0.1) + (v3 < 0.1);
-        }
-        for (; k < n; ++k) {
-            double v = c.spd[base + k];
-            tot += v;
-            q += v < 0.1;
+        int v = n > 0 ? (int) c.head[l] : (int) NONE16;
+        for (int k = 0; k < n && v != (int) NONE16; ++k) {      // front to back: the sum keeps the reference's order
+            const double sp = c.spd[v];
+            v = c.foll[v];
+            tot += sp;
+            q += sp < 0.1;
         }
         double ms = n ? div_pos(tot, (double) n) : 0.0;
         double occ = div_pos((double) n, __ldg(S.lane_cells + l));      // lane_cells = pytsc lane length / veh_size_min_gap
@@ -1233,7 +1181,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     // --- position-matrix windows (retriever.py:20-52, traffic_signal.py:124,135) ---
     const int vis = S.visibility;
     const bool need_pos = O.pos_in || O.pos_out || (O.obs && S.obs_type == TSC_OBS_POSITION_MATRIX);
-    double *win_in = (double *) c.nrpos;   // [n_in_total][vis] scratch (fp64), only when needed
+    double *win_in = r_tail;               // [n_in_total][vis] scratch (fp64), only when needed
     if (need_pos) {
         const int n_in = S.n_in_total, n_out = S.n_out_total;
         for (int e = tid; e < n_in + n_out; e += NT) {
@@ -1466,38 +1414,31 @@ __device__ __forceinline__ void copy16_async(void *dst_smem, const void *src, in
 __device__ __forceinline__ void copy16_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // CTL: the rule-based controllers are compiled in (kept out of the plain variant: their code costs the
-// hot path 2-3 % through register allocation alone).  STAGED: register-staged re-pack (see engine_tick).
+// hot path 2-3 % through register allocation alone).
 // GMEM: the replica's working set does not fit an SM's shared memory (a 16 x 16 grid needs ~1 MB): the
 // block works out of a global-memory workspace instead -- same layout, same code, L2-resident.
-template <int NT, int MINB, bool CTL, bool STAGED, bool GMEM, bool ONE_T, int HYB>
-__global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images,
-                                                      const u8 *is_spawn_lane, const StepArgs a) {
+template <int NT, int MINB, bool CTL, bool GMEM, bool ONE_T>
+__global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, const Layout Y, unsigned char *images, const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_block[];
     unsigned char *const smem = GMEM ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes + 255) & ~255) : smem_block;
-    // HYB >= 1: the cold buffers (D) live in this block's global workspace, the cold image column (B) stays
-    // in the image, and the shared-memory-only hot arrays (C) move down over the room (B) would have taken.
-    // HYB == 2 (replicas too large for three blocks per SM otherwise): the tick's decision buffers are in (D) too.
-    unsigned char *const hot = HYB ? smem - (Y.img_bytes - Y.o_img_cold) : smem;
-    unsigned char *const cold = HYB ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes - Y.o_cold + 255) & ~255) - Y.o_cold : smem;
     const int tid = threadIdx.x;
     Ctx c;
     c.h = (RepHeader *) smem;
-    c.cnt = (u16 *) (smem + Y.o_cnt); c.wq = (u16 *) (smem + Y.o_wq);
+    c.cnt = (u16 *) (smem + Y.o_cnt); c.head = (u16 *) (smem + Y.o_head); c.tail = (u16 *) (smem + Y.o_tail);
+    c.wq = (u16 *) (smem + Y.o_wq);
     c.sraw = smem + Y.o_sraw; c.scur = smem + Y.o_scur; c.schg = smem + Y.o_schg; c.stop = (int *) (smem + Y.o_stop);
-    c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd);
-    c.rpos = (int *) (smem + Y.o_rpos); c.blk = (short *) (smem + Y.o_blk);
-    c.newslot = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
-    unsigned char *const dec = HYB >= 2 ? cold : hot;      // decision buffers
-    c.npos = (double *) (dec + Y.o_npos); c.nspd = (double *) (dec + Y.o_nspd); c.nrpos = (int *) (dec + Y.o_nrpos);
-    c.nblk = (short *) (dec + Y.o_nblk); c.nflag = dec + Y.o_nflag; c.xlist = (u16 *) (hot + Y.o_xlist);
-    c.off = (u16 *) (hot + Y.o_off); c.leave = (u16 *) (hot + Y.o_leave); c.ent = (u16 *) (hot + Y.o_ent);
-    c.fresh = hot + Y.o_fresh; c.entlist = (u16 *) (hot + Y.o_entlist); c.entpos = (double *) (hot + Y.o_entpos);
-    c.entdrv = (u16 *) (hot + Y.o_entdrv); c.scan = (int *) (hot + Y.o_scan);
-    c.avail = (u32 *) (hot + Y.o_avail);
-    c.sp_lane = (int *) (hot + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
+    c.rpos = (int *) (smem + Y.o_rpos); c.vid = (int *) (smem + Y.o_vid);
+    c.lead = (u16 *) (smem + Y.o_lead); c.foll = (u16 *) (smem + Y.o_foll); c.pj = smem + Y.o_pj;
+    c.alist = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
+    c.dn = (u32 *) (smem + Y.o_dn); c.xlist = (u16 *) (smem + Y.o_xlist);
+    c.leave = (u16 *) (smem + Y.o_leave); c.ent = (u16 *) (smem + Y.o_ent); c.fresh = smem + Y.o_fresh;
+    c.mv_slot = (u16 *) (smem + Y.o_mvslot); c.mv_to = (u16 *) (smem + Y.o_mvto); c.mv_q = (int *) (smem + Y.o_mvq); c.mv_pj = smem + Y.o_mvpj;
+    c.scan = (int *) (smem + Y.o_scan);
+    c.avail = (u32 *) (smem + Y.o_avail);
+    c.sp_lane = (int *) (smem + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
     for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
     if (ONE_T || S.T <= SMEM_TEMPLATES) {
-        double *ts = (double *) (hot + Y.o_tmpl);
+        double *ts = (double *) (smem + Y.o_tmpl);
         for (int k = tid; k < S.T * TD_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
     } else c.tmpl = S.tmpl;
@@ -1506,11 +1447,11 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
 
     for (int b = a.b0 + blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
-        // the identity fields ping-pong between two buffers every tick: start from the primary ones
-        c.vid = (int *) (smem + Y.o_vid); c.dn = (u32 *) (hot + Y.o_dn); c.pj = smem + Y.o_pj;
-        c.vid2 = (int *) (hot + Y.o_vid2); c.dn2 = (u32 *) (hot + Y.o_dn2); c.pj2 = hot + Y.o_pj2;
-        c.ellt = (int *) ((HYB ? img : smem) + Y.o_ellt); c.ellt2 = (int *) (cold + Y.o_ellt2);
-        // ---- stage the replica image into shared memory ----
+        // the kinematics ping-pong between two buffers every tick: start from the ones that mirror the image
+        c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd); c.blk = (short *) (smem + Y.o_blk);
+        c.npos = (double *) (smem + Y.o_npos); c.nspd = (double *) (smem + Y.o_nspd); c.nblk = (short *) (smem + Y.o_nblk);
+        c.ellt = (int *) (img + Y.o_ellt);      // cold column: worked on in place
+        // ---- stage the replica image into the working set ----
         copy16(smem, img, Y.o_meta_end, tid, NT);
         __syncthreads();
         const int n_in = c.h->n_slots;
@@ -1522,7 +1463,8 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 copy16_async(smem + Y.o_spd, img + Y.o_spd, n8, tid, NT);
                 copy16_async(smem + Y.o_rpos, img + Y.o_rpos, n4, tid, NT);
                 copy16_async(smem + Y.o_vid, img + Y.o_vid, n4, tid, NT);
-                if (HYB == 0) copy16_async(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
+                copy16_async(smem + Y.o_lead, img + Y.o_lead, n2, tid, NT);
+                copy16_async(smem + Y.o_foll, img + Y.o_foll, n2, tid, NT);
                 copy16_async(smem + Y.o_blk, img + Y.o_blk, n2, tid, NT);
                 copy16_async(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
             } else {
@@ -1530,13 +1472,18 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 copy16(smem + Y.o_spd, img + Y.o_spd, n8, tid, NT);
                 copy16(smem + Y.o_rpos, img + Y.o_rpos, n4, tid, NT);
                 copy16(smem + Y.o_vid, img + Y.o_vid, n4, tid, NT);
-                if (HYB == 0) copy16(smem + Y.o_ellt, img + Y.o_ellt, n4, tid, NT);
+                copy16(smem + Y.o_lead, img + Y.o_lead, n2, tid, NT);
+                copy16(smem + Y.o_foll, img + Y.o_foll, n2, tid, NT);
                 copy16(smem + Y.o_blk, img + Y.o_blk, n2, tid, NT);
                 copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
             }
         }
-        for (int l = tid; l < S.L; l += NT) c.fresh[l] = 0;
-        if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_pairs = 0; }
+        {   // per-tick counters start from zero (the list surgery of every tick leaves them that way)
+            int4 *z = (int4 *) (smem + Y.o_leave);
+            const int nz = (Y.o_fresh - Y.o_leave + ((S.L + 15) & ~15)) / 16;      // leave, ent, fresh are adjacent
+            for (int k = tid; k < nz; k += NT) z[k] = make_int4(0, 0, 0, 0);
+        }
+        if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_new = n_in; }
         for (int s = tid; s < S.n_spawn_lanes; s += NT) {
             const int l = __ldg(S.spawn_lane + s);
             const int at = __ldg(c.lso + l) + c.wq[s];
@@ -1563,11 +1510,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 for (int o = tid * 128; o < Y.img_bytes; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nimg + o));
             }
         }
-        block_scan_counts<NT>(c.cnt, is_spawn_lane, S.L, c.off, S.D, c.scan);
-        for (int d = tid; d < S.D; d += NT) {      // what the end of a tick leaves for the next one
-            c.leave[d] = 0; c.ent[d] = 0;
-            if (c.cnt[d] > 0) c.xlist[atomicAdd(&c.h->n_h, 1)] = (u16) d;
-        }
+        __syncthreads();
         pt_mark(c, PT_STAGE_IN);
 
         int *decided = (int *) c.nspd;       // free between ticks
@@ -1588,23 +1531,25 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         }
         __syncthreads();
         pt_mark(c, PT_PROLOGUE);
-        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT, STAGED, ONE_T>(S, Y, c, is_spawn_lane);
+        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT, ONE_T>(S, Y, c);
         if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
         pt_mark(c, PT_RETRIEVE);
 
         // ---- write the image back ----
         if (!a.decide_only && (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0)) {
+            __syncthreads();      // retrieve's scratch lives in the next-state buffers; nothing below reads them
             copy16(img, smem, Y.o_meta_end, tid, NT);
             const int n = c.h->n_slots;
             const int n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
             if (a.n_ticks > 0) {
-                copy16(img + Y.o_pos, smem + Y.o_pos, n8, tid, NT);
-                copy16(img + Y.o_spd, smem + Y.o_spd, n8, tid, NT);
+                copy16(img + Y.o_pos, c.pos, n8, tid, NT);      // whichever buffer holds the current state
+                copy16(img + Y.o_spd, c.spd, n8, tid, NT);
+                copy16(img + Y.o_blk, c.blk, n2, tid, NT);
                 copy16(img + Y.o_rpos, smem + Y.o_rpos, n4, tid, NT);
-                copy16(img + Y.o_vid, c.vid, n4, tid, NT);
-                if ((unsigned char *) c.ellt != img + Y.o_ellt) copy16(img + Y.o_ellt, c.ellt, n4, tid, NT);
-                copy16(img + Y.o_blk, smem + Y.o_blk, n2, tid, NT);
-                copy16(img + Y.o_pj, c.pj, n1, tid, NT);
+                copy16(img + Y.o_vid, smem + Y.o_vid, n4, tid, NT);
+                copy16(img + Y.o_lead, smem + Y.o_lead, n2, tid, NT);
+                copy16(img + Y.o_foll, smem + Y.o_foll, n2, tid, NT);
+                copy16(img + Y.o_pj, smem + Y.o_pj, n1, tid, NT);
                 u32 *drv_pairs = (u32 *) (img + Y.o_drv);     // two u16 drivables per 32-bit store
                 for (int i = tid; i < (n + 1) / 2; i += NT) {
                     u32 lo = c.dn[2 * i] & 0xFFFFu;
@@ -1638,30 +1583,20 @@ static int fail(int code, const char *fmt, ...) {
             return fail(e__ == cudaErrorMemoryAllocation ? TSC_ENOMEM : TSC_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
     } while (0)
 
-// Kernel variants.  256 threads per replica block while at least two replicas fit an SM's shared memory
-// (launch bounds 3 -> 80 registers, 2 -> 128); one 512-thread block per SM for replicas larger than
-// that, register-staged when even one copy of the identity columns is too much; one 1024-thread block
-// per SM over a global-memory workspace for replicas that do not fit shared memory at all.
-typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const u8 *, const StepArgs);
-static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool staged, bool one_t, int hybrid, bool gmem) {
-    if (nt == 1024 && gmem) return tsc_step_kernel<1024, 1, true, false, true, false, 0>;
-    if (nt == 1024 && !staged && one_t) return tsc_step_kernel<1024, 1, true, false, false, true, 0>;    // shared memory, 32 warps, 64 registers
-    if (nt == 512 && !staged && one_t) return tsc_step_kernel<512, 1, true, false, false, true, 0>;
-    if (nt == 512 || nt == 1024) return staged ? tsc_step_kernel<512, 1, true, true, false, false, 0> : tsc_step_kernel<512, 1, true, false, false, false, 0>;
-    if (nt == 256 && one_t && hybrid == 2) {    // large replicas: decision buffers in the global workspace buy a block per SM
-        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true, 2> : tsc_step_kernel<256, 2, true, false, false, true, 2>;
-        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true, 2> : tsc_step_kernel<256, 2, false, false, false, true, 2>;
-    }
-    if (nt == 192 && one_t && hybrid)   // four 192-thread blocks per SM (80 registers), cold buffers in the global workspace
-        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, 1> : tsc_step_kernel<192, 4, false, false, false, true, 1>;
-    if (nt == 192 && one_t)             // the same with everything in shared memory (working set below 56 KB)
-        return ctl ? tsc_step_kernel<192, 4, true, false, false, true, 0> : tsc_step_kernel<192, 4, false, false, false, true, 0>;
-    if (one_t) {
-        if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, true, 0> : tsc_step_kernel<256, 2, true, false, false, true, 0>;
-        return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, true, 0> : tsc_step_kernel<256, 2, false, false, false, true, 0>;
-    }
-    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, false, false, 0> : tsc_step_kernel<256, 2, true, false, false, false, 0>;
-    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, false, false, 0> : tsc_step_kernel<256, 2, false, false, false, false, 0>;
+// Kernel variants, picked from how many replica working sets fit an SM's shared memory: four 192-thread
+// blocks per SM (80 registers) -- the bench workload --, three or two 256-thread blocks (80 / 128 registers),
+// one 512- or 1024-thread block, or one 1024-thread block over a global-memory workspace for replicas that do
+// not fit shared memory at all.  Scenarios with several vehicle templates run the generic (per-vehicle
+// template look-up) builds of the 256 x 2, 512 and global-memory variants.
+typedef void (*step_kernel_t)(const DevScn, const Layout, unsigned char *, const StepArgs);
+static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool one_t, bool gmem) {
+    if (gmem) return tsc_step_kernel<1024, 1, true, true, false>;
+    if (!one_t) return nt >= 512 ? tsc_step_kernel<512, 1, true, false, false> : tsc_step_kernel<256, 2, true, false, false>;
+    if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true>;      // 32 warps at 64 registers
+    if (nt == 512) return tsc_step_kernel<512, 1, true, false, true>;
+    if (nt == 192) return ctl ? tsc_step_kernel<192, 4, true, false, true> : tsc_step_kernel<192, 4, false, false, true>;
+    if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, true> : tsc_step_kernel<256, 2, true, false, true>;
+    return minb >= 3 ? tsc_step_kernel<256, 3, false, false, true> : tsc_step_kernel<256, 2, false, false, true>;
 }
 
 #define MAX_HOST_CHUNKS 16
@@ -1672,7 +1607,6 @@ struct tsc_engine {
     Layout Y{};
     std::vector<void *> dev_allocs;
     unsigned char *images = nullptr;
-    u8 *d_is_spawn_lane = nullptr;
     int *d_actions = nullptr;
     float *d_obs = nullptr, *d_reward = nullptr, *d_rg = nullptr;
     u8 *d_mask = nullptr;
@@ -1685,7 +1619,6 @@ struct tsc_engine {
     unsigned long long *d_phase_cycles = nullptr;   // debug phase timing buffer (tsc_debug_timing)
     unsigned char *workspace = nullptr;             // GMEM variant: grid working sets in global memory
     bool gmem = false;
-    int hybrid = 0;                                 // 0: everything in shared memory; 1: cold column in the global workspace; 2: decision buffers too
     int dyn_smem = 0;                               // dynamic shared memory per block of the chosen variant
     cudaStream_t host_compute = nullptr, host_compute2 = nullptr, host_copy = nullptr;   // tsc_env_step_host: step chunk k+1 while chunk k is copied out
     int host_streams = 1;               // compute streams the chunks alternate on (TSC_B200_HOST_STREAMS=2: measured slower, 1.58 vs 1.53 ms per B=4096 step)
@@ -1848,75 +1781,61 @@ static int upload(tsc_engine *E, const Tp *host, size_t n, const Tp **dev) {
 
 static int align16(int x) { return (x + 15) & ~15; }
 
-static void build_layout(Layout &Y, const DevScn &S, int Vcap, int staged, int cold_level = 0) {
+static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.Vcap = Vcap;
-    Y.staged = staged;
-    Y.cold_level = cold_level;
-    Y.pair_cap = staged ? 0 : Vcap;      // the list lives in the idle copy of the ping-pong identity columns
     // vehicles changing drivable in one tick (a lane hands over at most one or two per tick; the shipped
     // workloads stay far below a tenth of the running vehicles): a quarter of the slots, overflow is
     // reported (ERR_ENT_OVERFLOW)
     Y.ent_cap = Vcap / 4 < 64 ? 64 : (Vcap / 4 > 8192 ? 8192 : Vcap / 4);
-    // ---- (A) replica image, hot part: same byte offsets in HBM and in shared memory
+    // between ticks the next-state kinematics pair (16 bytes per slot, contiguous) is the scratch of retrieve /
+    // the controllers: lane sums, per-signal terms, then the position-matrix windows or the host packet
+    const int tailb = S.obs_type == TSC_OBS_POSITION_MATRIX ? std::max(S.n_in_total * S.visibility * 8, S.pk_bytes) : S.pk_bytes;
+    const int scratch = 24 * S.L + 16 * S.A + 4 * ((S.L + 1) & ~1) + tailb + 64;
+    int Vlay = Vcap;
+    if (16 * Vlay < scratch) Vlay = ((scratch + 15) / 16 + 7) & ~7;
+    Y.Vlay = Vlay;
+    // ---- replica image, hot part: same byte offsets in HBM and in the working set
     int o = sizeof(RepHeader);
     Y.o_cnt = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_head = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_tail = o; o = align16(o + 2 * (S.D + 2));
     Y.o_wq = o; o = align16(o + 2 * (S.n_spawn_lanes + 1));
     Y.o_sraw = o; o = align16(o + S.A);
     Y.o_scur = o; o = align16(o + S.A);
     Y.o_schg = o; o = align16(o + S.A);
     Y.o_stop = o; o = align16(o + 4 * S.A);
     Y.o_meta_end = o;
-    Y.o_pos = o; o = align16(o + 8 * Vcap);
-    Y.o_spd = o; o = align16(o + 8 * Vcap);
+    Y.o_pos = o; o = o + 8 * Vlay;              // pos | spd contiguous
+    Y.o_spd = o; o = align16(o + 8 * Vlay);
     Y.o_rpos = o; o = align16(o + 4 * Vcap);
     Y.o_vid = o; o = align16(o + 4 * Vcap);
-    Y.o_drv = o; o = align16(o + 2 * Vcap);     // HBM: u16 drivable; shared memory: the newslot scratch
+    Y.o_lead = o; o = align16(o + 2 * Vcap);
+    Y.o_foll = o; o = align16(o + 2 * Vcap);
+    Y.o_drv = o; o = align16(o + 2 * Vcap);     // HBM: u16 drivable; working set: the intersection-zone list
     Y.o_pj = o; o = align16(o + Vcap);
     Y.o_blk = o; o = align16(o + 2 * Vcap);
-    // ---- (B) replica image, cold part (enterLaneLinkTime: read by canPass tie-breaks only): the hybrid
-    //      variant leaves this column in the image and works on it in place
-    Y.o_img_cold = o;
-    Y.o_ellt = o; o = align16(o + 4 * Vcap);
-    Y.img_bytes = o;
-    // ---- (C) shared-memory-only hot arrays (the hybrid variant places them right after (A))
+    // ---- replica image, cold part (enterLaneLinkTime: read by canPass tie-breaks, written when a vehicle enters a
+    //      lane-link): stays in the image and is worked on in place
+    Y.o_ellt = o;
+    Y.img_bytes = align16(o + 4 * Vcap);
+    // ---- working-set-only arrays, from where the cold column starts
     Y.o_dn = o; o = align16(o + 4 * Vcap);
-    const int V2 = Y.staged ? 0 : Vcap;    // second copy of the identity columns: only for the ping-pong re-pack
-    Y.o_dn2 = o; o = align16(o + 4 * V2);
-    Y.o_vid2 = o; o = align16(o + 4 * V2);
-    Y.o_pj2 = o; o = align16(o + V2);
+    Y.o_npos = o; o = o + 8 * Vlay;             // npos | nspd contiguous
+    Y.o_nspd = o; o = align16(o + 8 * Vlay);
+    Y.o_nblk = o; o = align16(o + 2 * Vcap);
     Y.o_xlist = o; o = align16(o + 2 * Vcap);
-    Y.o_off = o; o = align16(o + 2 * (S.D + 2));
-    Y.o_leave = o; o = align16(o + 2 * (S.D + 2));
+    Y.o_leave = o; o = align16(o + 2 * (S.D + 2));      // leave | ent | fresh adjacent: zeroed together at stage-in
     Y.o_ent = o; o = align16(o + 2 * (S.D + 2));
     Y.o_fresh = o; o = align16(o + S.L);
-    Y.o_entlist = o; o = align16(o + 2 * Y.ent_cap);
-    Y.o_entdrv = o; o = align16(o + 2 * Y.ent_cap);
-    Y.o_entpos = o; o = align16(o + 8 * Y.ent_cap);
-    Y.o_scan = o; o = align16(o + 4 * 64 + 2 * (S.D + 2));
+    Y.o_mvslot = o; o = align16(o + 2 * Y.ent_cap);
+    Y.o_mvto = o; o = align16(o + 2 * Y.ent_cap);
+    Y.o_mvq = o; o = align16(o + 4 * Y.ent_cap);
+    Y.o_mvpj = o; o = align16(o + Y.ent_cap);
+    Y.o_scan = o; o = align16(o + 4 * 64);
     Y.o_avail = o; o = align16(o + 4 * ((S.K + 31) / 32 + 1));
     Y.o_tmpl = o; o = align16(o + 8 * TD_STRIDE * (S.T < SMEM_TEMPLATES ? S.T : SMEM_TEMPLATES));
     Y.o_spawn = o; o = align16(o + 12 * (S.n_spawn_lanes + 1));
-    // the tick's decision buffers; npos / nspd / nrpos double as retrieve scratch: make sure they are large enough
-    int need_np = 3 * S.L, need_ns = 2 * S.A + (S.L + 1) / 2 + 2;
-    int need_nr = S.obs_type == TSC_OBS_POSITION_MATRIX ? (S.n_in_total * S.visibility * 8 + 3) / 4 : (S.pk_bytes + 3) / 4;
-    auto decision_buffers = [&]() {
-        Y.o_npos = o; o = align16(o + 8 * (Vcap > need_np ? Vcap : need_np));
-        Y.o_nspd = o; o = align16(o + 8 * (Vcap > need_ns ? Vcap : need_ns));
-        Y.o_nrpos = o; o = align16(o + 4 * (Vcap > need_nr ? Vcap : need_nr));
-        Y.o_nblk = o; o = align16(o + 2 * Vcap);
-        Y.o_nflag = o; o = align16(o + Vcap);
-    };
-    if (cold_level < 2) decision_buffers();
-    // ---- (D) cold region: written once and read once per vehicle per tick, in slot order.  The hybrid
-    //      variants keep it in a per-block global-memory workspace (L2-resident) so that more replicas fit
-    //      an SM's shared memory.  Level 1: the idle copy of the cold column (8 bytes per slot with (B)) --
-    //      what lets the bench workload run four blocks per SM.  Level 2: the decision buffers as well
-    //      (29 more bytes per slot; costs ~20 % per block, taken only when it buys a block per SM).
-    Y.o_cold = o;
-    if (cold_level >= 2) decision_buffers();
-    Y.o_ellt2 = o; o = align16(o + 4 * V2);
     Y.smem_bytes = o;
-    Y.hybrid_smem_bytes = Y.o_cold - (Y.img_bytes - Y.o_img_cold);      // (A) + (C)
 }
 
 extern "C" {
@@ -2132,7 +2051,6 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
         for (int k = 0; k < E->n_spawn_lanes; ++k) idx[E->h_spawn_lane[k]] = (short) k;
         if ((rc = upload(E, idx.data(), (size_t) L, &S.lane_spawn_idx))) return rc;
     }
-    { const u8 *p; if ((rc = upload(E, E->h_is_spawn.data(), (size_t) L, &p))) return rc; E->d_is_spawn_lane = (u8 *) p; }
     const int H2 = S.horizon + 2;
     std::vector<int> ccnt((size_t) S.F * H2, 0);
     std::vector<long long> cent((size_t) S.F * H2, 0);
@@ -2155,87 +2073,39 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     E->h_veh_seq_start.assign(s->veh_seq_start, s->veh_seq_start + N);
 
     int Vcap = vehicle_capacity > 0 ? vehicle_capacity : 1024;
-    Vcap = (Vcap + E->n_spawn_lanes + 7) & ~7;
+    // room for the holes finished vehicles leave until the next compaction, on top of the running vehicles asked for
+    Vcap = (Vcap + HOLE_MAX + 7) & ~7;
     if (Vcap > 32767) { return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    // Pick the variant from what fits: 256-thread blocks (ping-pong re-pack) while >= 2 replicas fit an
-    // SM; else one 512-thread block per SM; register-staged (13 bytes less per vehicle slot) only when
-    // that is what makes the replica fit.  TSC_B200_THREADS / TSC_B200_STAGED / TSC_B200_MIN_BLOCKS override.
-    // (Two 512-thread blocks at 64 registers were measured too: 1.36 ms against 1.13 ms for three 256-thread blocks at 80.)
-    int staged = 0;
-    build_layout(E->Y, S, Vcap, 0);
-    E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
-    if (E->minb < 2) E->nt = 512;
-    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 256 || v == 512) E->nt = v; }
-    if (E->nt == 512 && (size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin && Vcap <= SCATTER_PER * 512) staged = 1;
-    if (const char *env = getenv("TSC_B200_STAGED")) { int v = atoi(env); if (v == 0 || (v == 1 && E->nt == 512 && Vcap <= SCATTER_PER * 512)) staged = v; }
-    if (staged) build_layout(E->Y, S, Vcap, 1);
-    if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) E->gmem = true;
-    if (const char *env = getenv("TSC_B200_GMEM")) E->gmem = atoi(env) != 0 || E->gmem;
-    if (E->gmem) {      // global-memory working sets: ping-pong layout, 1024 threads, one block per SM
-        E->nt = 1024;
-        build_layout(E->Y, S, Vcap, 0);
-    }
-    {   // the flat cross phase packs a cross's position in its link into 8 bits
-        int max_cross = 0;
-        for (int k = 0; k < K; ++k) max_cross = std::max(max_cross, s->ll_cross_off[k + 1] - s->ll_cross_off[k]);
-        if (max_cross > 255) E->Y.pair_cap = 0;
-        // measured on the bench workload (192 x 4): flat pair list 1.010 ms, groups of 32 / 16 / 8 lanes per vehicle
-        // 1.059 / 1.000 / 0.971 ms, width chosen per tick 0.923 ms (default); TSC_B200_FLAT_CROSS=1 selects the pair list
-        const char *flat = getenv("TSC_B200_FLAT_CROSS");
-        if (!flat || atoi(flat) == 0) E->Y.pair_cap = 0;
-        E->Y.cross_group = 0;      // adaptive
-        if (const char *env = getenv("TSC_B200_CROSS_GROUP")) { int v = atoi(env); if (v == 0 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) E->Y.cross_group = v; }
-        E->Y.async_stage = 1;      // 0.921 -> 0.912 ms
-        if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) E->Y.async_stage = atoi(env) != 0;
-        E->Y.prefetch_next = 1;
-        if (const char *env = getenv("TSC_B200_PREFETCH")) E->Y.prefetch_next = atoi(env) != 0;
-    }
-    // blocks per SM the shared-memory footprint allows decides the register budget (launch bounds variant);
-    // measured on B200 (Hangzhou, B = 4096): 4 blocks x 64 registers loses to 3 blocks x 80 (1.41 vs 1.34 ms)
-    E->minb = (int) (prop.sharedMemPerMultiprocessor / (size_t) (E->Y.smem_bytes + 1024));
-    if (E->minb < 1) E->minb = 1;
+    build_layout(E->Y, S, Vcap);
+    E->Y.cross_group = 0;      // adaptive (measured on the bench workload: 32 / 16 / 8 lanes per vehicle 1.059 / 1.000 / 0.971 ms, adaptive 0.923)
+    if (const char *env = getenv("TSC_B200_CROSS_GROUP")) { int v = atoi(env); if (v == 0 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) E->Y.cross_group = v; }
+    E->Y.async_stage = 1;
+    if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) E->Y.async_stage = atoi(env) != 0;
+    E->Y.prefetch_next = 1;
+    if (const char *env = getenv("TSC_B200_PREFETCH")) E->Y.prefetch_next = atoi(env) != 0;
+    // Pick the variant from how many working sets fit an SM's shared memory (the register budget follows from the
+    // launch bounds).  Measured on B200 (Hangzhou, B = 4096): four 192-thread blocks beat three 256-thread ones, which
+    // beat four blocks at 64 registers and two 512-thread blocks.  TSC_B200_THREADS / TSC_B200_MIN_BLOCKS / TSC_B200_GMEM override.
     bool one_t = S.T == 1;
     if (const char *env = getenv("TSC_B200_ONE_TEMPLATE")) one_t = one_t && atoi(env) != 0;
-    // Four 192-thread blocks per SM beat three 256-thread ones (1.00 vs 1.14 ms on the bench workload): taken
-    // whenever the working set allows it -- all of it in shared memory if that fits four times, else with the
-    // cold buffers in a global workspace (hybrid).  TSC_B200_THREADS=256 / TSC_B200_HYBRID=0 opt out.
-    bool small = one_t && !E->gmem && !staged && E->nt == 256;
-    if (const char *env = getenv("TSC_B200_THREADS")) small = small && atoi(env) == 192;      // (224 threads x 4 at 72 registers: 0.984 vs 0.970 ms)
-    const size_t per_sm = prop.sharedMemPerMultiprocessor;
-    const bool four_plain = small && per_sm / (size_t) (E->Y.smem_bytes + 1024) >= 4;
-    int hybrid = (small && !four_plain && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4) ? 1 : 0;
-    int hyb_env = 1;
-    if (const char *env = getenv("TSC_B200_HYBRID")) hyb_env = atoi(env);
-    if (hyb_env == 0) hybrid = 0;
-    if (hyb_env == 2 && small && per_sm / (size_t) (E->Y.hybrid_smem_bytes + 1024) >= 4) hybrid = 1;      // forced although everything would fit
-    const bool four_blocks = hybrid == 1 || four_plain;
-    if (E->minb > 3) E->minb = 3;
-    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 1 && v <= 3) E->minb = v; }
-    if (four_blocks) { E->nt = 192; E->minb = 4; }
-    if (!four_blocks && one_t && hyb_env != 0 && !getenv("TSC_B200_THREADS") && !getenv("TSC_B200_STAGED") && !getenv("TSC_B200_GMEM") &&
-        !getenv("TSC_B200_MIN_BLOCKS")) {
-        // larger replicas: does moving the decision buffers out as well buy a block per SM (up to three)?
-        const int plain_blocks = E->gmem ? 0 : (int) (per_sm / (size_t) (E->Y.smem_bytes + 1024));
-        Layout Y2 = E->Y;
-        build_layout(Y2, S, Vcap, 0, 2);
-        int b2 = (int) (per_sm / (size_t) (Y2.hybrid_smem_bytes + 1024));
-        if (b2 > 3) b2 = 3;
-        if (b2 >= 2 && b2 > plain_blocks && plain_blocks < 3) {
-            const int pc = E->Y.pair_cap, cg = E->Y.cross_group, pf = E->Y.prefetch_next;
-            E->Y = Y2;
-            E->Y.pair_cap = pc ? Y2.pair_cap : 0; E->Y.cross_group = cg; E->Y.prefetch_next = pf;
-            E->gmem = false; staged = 0;
-            E->nt = 256; E->minb = b2; hybrid = 2;
-        }
-    }
-    E->hybrid = hybrid;
-    if (E->nt == 512 && !E->gmem && !staged && one_t)      // one block per SM: TSC_B200_THREADS=1024 runs it with 32 warps at 64 registers
-        if (const char *env = getenv("TSC_B200_THREADS")) { if (atoi(env) == 1024) E->nt = 1024; }
-    E->kern = kernel_for(E->nt, E->minb, false, staged != 0, one_t, hybrid, E->gmem);
-    E->kern_ctl = kernel_for(E->nt, E->minb, true, staged != 0, one_t, hybrid, E->gmem);
-    const int dyn_smem = E->gmem ? 0 : (hybrid ? E->Y.hybrid_smem_bytes : E->Y.smem_bytes);
+    const size_t per_sm_bytes = prop.sharedMemPerMultiprocessor;
+    int fit = (int) (per_sm_bytes / (size_t) (E->Y.smem_bytes + 1024));
+    if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) fit = 0;
+    if (const char *env = getenv("TSC_B200_GMEM")) { if (atoi(env) != 0) fit = 0; }
+    int want_nt = 0;
+    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 192 || v == 256 || v == 512 || v == 1024) want_nt = v; }
+    if (fit == 0) { E->gmem = true; E->nt = 1024; E->minb = 1; }
+    else if (!one_t) { E->nt = fit >= 2 ? 256 : 512; E->minb = fit >= 2 ? 2 : 1; }
+    else if (fit >= 4 && (want_nt == 0 || want_nt == 192)) { E->nt = 192; E->minb = 4; }
+    else if (fit >= 2 && (want_nt == 0 || want_nt == 256 || want_nt == 192)) { E->nt = 256; E->minb = fit >= 3 ? 3 : 2; }
+    else { E->nt = want_nt == 1024 ? 1024 : 512; E->minb = 1; }
+    if (E->nt == 256)
+        if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 2 && v <= 3 && v <= fit) E->minb = v; }
+    E->kern = kernel_for(E->nt, E->minb, false, one_t, E->gmem);
+    E->kern_ctl = kernel_for(E->nt, E->minb, true, one_t, E->gmem);
+    const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;
     E->dyn_smem = dyn_smem;
     for (int k = 0; k < 2; ++k) {
         step_kernel_t kern = k ? E->kern_ctl : E->kern;
@@ -2251,21 +2121,24 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     CUDA_TRY(cudaFuncGetAttributes(&fa, E->kern));
     E->regs = fa.numRegs;
 
-    if (E->gmem || E->hybrid) {
+    if (E->gmem) {
         const int g = E->grid > E->grid_ctl ? E->grid : E->grid_ctl;
-        const size_t per_block = E->gmem ? (size_t) ((E->Y.smem_bytes + 255) & ~255) : (size_t) ((E->Y.smem_bytes - E->Y.o_cold + 255) & ~255);
-        CUDA_TRY(cudaMalloc((void **) &E->workspace, (size_t) g * per_block));
+        CUDA_TRY(cudaMalloc((void **) &E->workspace, (size_t) g * (size_t) ((E->Y.smem_bytes + 255) & ~255)));
     }
     CUDA_TRY(cudaMalloc((void **) &E->images, (size_t) (n_replicas + 1) * E->Y.img_bytes));      // + the tick-0 image (tsc_reset_replicas)
     // tick-0 image: empty network, one spare slot per spawn lane
     E->init_image.assign(E->Y.img_bytes, 0);
     {
         RepHeader *h = (RepHeader *) E->init_image.data();
-        h->n_slots = E->n_spawn_lanes;
+        h->n_slots = 0;
         int *vid = (int *) (E->init_image.data() + E->Y.o_vid);
         for (int i = 0; i < E->Y.Vcap; ++i) vid[i] = -1;
         short *blk = (short *) (E->init_image.data() + E->Y.o_blk);
         for (int i = 0; i < E->Y.Vcap; ++i) blk[i] = -1;
+        memset(E->init_image.data() + E->Y.o_head, 0xFF, 2 * (size_t) (D + 2));      // empty lists
+        memset(E->init_image.data() + E->Y.o_tail, 0xFF, 2 * (size_t) (D + 2));
+        memset(E->init_image.data() + E->Y.o_lead, 0xFF, 2 * (size_t) E->Y.Vcap);
+        memset(E->init_image.data() + E->Y.o_foll, 0xFF, 2 * (size_t) E->Y.Vcap);
         // the signal programs start on pytsc phase 0 (TSProgram.set_initial_phase, backends/cityflow/traffic_signal.py:26-32):
         // a caller that steps before its first tsc_init_program / action sees that light phase, not raw phase 0
         u8 *sraw = E->init_image.data() + E->Y.o_sraw;
@@ -2439,7 +2312,7 @@ static int launch(tsc_handle E, const StepArgs &a, void *stream) {
     int grid = ctl ? E->grid_ctl : E->grid;
     if (grid > a.B - a.b0) grid = a.B - a.b0;
     if (grid <= 0) return 0;
-    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->dyn_smem, (cudaStream_t) stream>>>(E->S, E->Y, E->images, E->d_is_spawn_lane, a);
+    (ctl ? E->kern_ctl : E->kern)<<<grid, E->nt, E->dyn_smem, (cudaStream_t) stream>>>(E->S, E->Y, E->images, a);
     E->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -2750,21 +2623,26 @@ int tsc_snapshot(tsc_handle E, int32_t b, int32_t cap, int32_t *vid, int32_t *dr
     const RepHeader *h = (const RepHeader *) img.data();
     const int *v = (const int *) (img.data() + Y.o_vid);
     const int *el = (const int *) (img.data() + Y.o_ellt);
-    const u16 *dr = (const u16 *) (img.data() + Y.o_drv);
+    const u16 *cnt = (const u16 *) (img.data() + Y.o_cnt), *head = (const u16 *) (img.data() + Y.o_head);
+    const u16 *foll = (const u16 *) (img.data() + Y.o_foll);
     const short *bl = (const short *) (img.data() + Y.o_blk);
     const double *ps = (const double *) (img.data() + Y.o_pos), *sp = (const double *) (img.data() + Y.o_spd);
+    // drivable-major, every drivable's list front to back
     int n = 0;
-    for (int i = 0; i < h->n_slots; ++i) {
-        if (v[i] < 0) continue;
-        if (n < cap) {
-            if (vid) vid[n] = v[i];
-            if (drivable) drivable[n] = dr[i];
-            if (distance) distance[n] = ps[i];
-            if (speed) speed[n] = sp[i];
-            if (blocker_vid) blocker_vid[n] = bl[i] >= 0 ? v[bl[i]] : -1;
-            if (enter_ll_time) enter_ll_time[n] = el[i];
+    for (int d = 0; d < E->S.D; ++d) {
+        int i = cnt[d] > 0 ? (int) head[d] : (int) NONE16;
+        for (int k = 0; k < (int) cnt[d] && i != (int) NONE16; ++k, i = foll[i]) {
+            if (i >= h->n_slots || v[i] < 0) return fail(TSC_EORDER, "replica %d: the list of drivable %d is corrupt", b, d);
+            if (n < cap) {
+                if (vid) vid[n] = v[i];
+                if (drivable) drivable[n] = d;
+                if (distance) distance[n] = ps[i];
+                if (speed) speed[n] = sp[i];
+                if (blocker_vid) blocker_vid[n] = (bl[i] >= 0 && bl[i] < h->n_slots) ? v[bl[i]] : -1;
+                if (enter_ll_time) enter_ll_time[n] = d >= E->S.L ? el[i] : INT_MAX;
+            }
+            ++n;
         }
-        ++n;
     }
     return n;
 }
@@ -2780,31 +2658,33 @@ int tsc_load_snapshot(tsc_handle E, int32_t b, int32_t n, const int32_t *vid, co
     std::vector<unsigned char> img(Y.img_bytes);
     CUDA_TRY(cudaMemcpy(img.data(), E->images + (size_t) b * Y.img_bytes, Y.img_bytes, cudaMemcpyDeviceToHost));
     RepHeader *h = (RepHeader *) img.data();
-    u16 *cnt = (u16 *) (img.data() + Y.o_cnt);
+    u16 *cnt = (u16 *) (img.data() + Y.o_cnt), *head = (u16 *) (img.data() + Y.o_head), *tail = (u16 *) (img.data() + Y.o_tail);
+    u16 *lead = (u16 *) (img.data() + Y.o_lead), *foll = (u16 *) (img.data() + Y.o_foll);
     int *v = (int *) (img.data() + Y.o_vid), *rp = (int *) (img.data() + Y.o_rpos), *el = (int *) (img.data() + Y.o_ellt);
     u16 *dr = (u16 *) (img.data() + Y.o_drv);
     short *bl = (short *) (img.data() + Y.o_blk);
     u8 *pj = img.data() + Y.o_pj;
     double *ps = (double *) (img.data() + Y.o_pos), *sp = (double *) (img.data() + Y.o_spd);
-    if (n + E->n_spawn_lanes > Y.Vcap) return fail(TSC_EOVERFLOW, "snapshot of %d vehicles exceeds vehicle_capacity", n);
-    for (int d = 0; d < D; ++d) cnt[d] = 0;
+    if (n > Y.Vcap - HOLE_MAX) return fail(TSC_EOVERFLOW, "snapshot of %d vehicles exceeds vehicle_capacity", n);
+    for (int d = 0; d < D; ++d) { cnt[d] = 0; head[d] = tail[d] = (u16) NONE16; }
     int prev = -1;
     for (int i = 0; i < n; ++i) {
         if (drivable[i] < prev || drivable[i] >= D || drivable[i] < 0) return fail(TSC_EINVAL, "snapshot must be drivable-major");
         prev = drivable[i];
-        cnt[drivable[i]] += 1;
     }
-    int slot = 0, k = 0;
-    for (int d = 0; d < D; ++d) {
-        for (int j = 0; j < cnt[d]; ++j, ++k, ++slot) {
-            v[slot] = vid ? vid[k] : k;
-            ps[slot] = distance[k]; sp[slot] = speed[k];
-            rp[slot] = route_pos ? route_pos[k] : 0;
-            el[slot] = d >= L ? 0 : INT_MAX; bl[slot] = -1; dr[slot] = (u16) d; pj[slot] = 0;
-        }
-        if (d < L && E->h_is_spawn[d]) { v[slot] = -1; ++slot; }
+    for (int i = 0; i < Y.Vcap; ++i) { v[i] = -1; bl[i] = -1; lead[i] = foll[i] = (u16) NONE16; }
+    for (int k = 0; k < n; ++k) {      // slot k = k-th vehicle: every drivable's vehicles front to back
+        const int d = drivable[k];
+        v[k] = vid ? vid[k] : k;
+        ps[k] = distance[k]; sp[k] = speed[k];
+        rp[k] = route_pos ? route_pos[k] : 0;
+        el[k] = d >= L ? 0 : INT_MAX; dr[k] = (u16) d; pj[k] = 0;
+        if (cnt[d] == 0) head[d] = (u16) k;
+        else { lead[k] = tail[d]; foll[tail[d]] = (u16) k; }
+        tail[d] = (u16) k;
+        cnt[d] += 1;
     }
-    h->n_slots = slot; h->n_running = n;
+    h->n_slots = n; h->n_running = n;
     CUDA_TRY(cudaMemcpy(E->images + (size_t) b * Y.img_bytes, img.data(), Y.img_bytes, cudaMemcpyHostToDevice));
     return 0;
 }
@@ -2873,8 +2753,8 @@ int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t
 
 int tsc_kernel_variant(tsc_handle E, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm) {
     if (!E) return fail(TSC_EINVAL, "null handle");
-    if (staged) *staged = E->Y.staged;
-    if (global_workspace) *global_workspace = E->gmem ? 1 : (E->hybrid ? 1 + E->hybrid : 0);      // 2: cold column only, 3: decision buffers too
+    if (staged) *staged = 0;
+    if (global_workspace) *global_workspace = E->gmem ? 1 : 0;
     if (blocks_per_sm) *blocks_per_sm = E->minb;
     return 0;
 }

@@ -254,22 +254,246 @@ class GridTripGenerator:
                 break
         return route
 
+    # ---- the arrival loop shared by the whole family (trip_generator.py:251-286 and its six variations):
+    #      per start edge, vehicles at Gaussian inter-arrival times; the subclasses change which edges start
+    #      vehicles, how the next gap is drawn, and how a route is picked ----
+    def _start_edges(self):
+        return self.incoming_edges
+
+    def _gap(self, edge, now):
+        return self.np_rng.normal(self.inter_mu, self.inter_sigma)
+
+    def _pick_route(self, edge):
+        route = [edge]
+        while len(route) <= 1 or len(route) > self.max_trip_length:
+            route = self._generate_route(edge)
+        return route
+
+    def _entry(self, route, t0):
+        return {"vehicle": self.vehicle_data, "route": route, "interval": 1.0, "startTime": t0, "endTime": t0}
+
+    def _arrivals(self, edge, now, until, flows):
+        """Vehicles entering on ``edge`` from ``now`` until ``until``; returns the time of the last one."""
+        while now < until:
+            t0 = int(now + max(0, self._gap(edge, now)))
+            if t0 >= until or t0 >= self.end_time:
+                break
+            flows.append(self._entry(self._pick_route(edge), t0))
+            now = t0
+        return now
+
     def generate(self):
         flows = []
-        for start_edge in self.incoming_edges:
-            now = self.start_time
-            while now < self.end_time:
-                gap = max(0, self.np_rng.normal(self.inter_mu, self.inter_sigma))
-                t0 = int(now + gap)
-                if t0 >= self.end_time:
-                    break
-                route = [start_edge]
-                while len(route) <= 1 or len(route) > self.max_trip_length:
-                    route = self._generate_route(start_edge)
-                flows.append({"vehicle": self.vehicle_data, "route": route, "interval": 1.0,
-                              "startTime": t0, "endTime": t0})
-                now = t0
+        for edge in self._start_edges():
+            self._arrivals(edge, self.start_time, self.end_time, flows)
         return sorted(flows, key=lambda f: f["startTime"])
+
+
+class LinkDisruptedTripGenerator(GridTripGenerator):
+    """``LinkDisruptedCityFlowTripGenerator`` (trip_generator.py:289-388): a share of the interior roads is closed
+    (``int(disruption_ratio * n_signals)`` of them, drawn by shuffling the non-fringe roads); routes avoid them."""
+
+    def __init__(self, roadnet, start_time, end_time, inter_mu, inter_sigma, disruption_ratio=0.1, **kw):
+        super().__init__(roadnet, start_time, end_time, inter_mu, inter_sigma, **kw)
+        self.disruption_ratio = disruption_ratio
+        n_signals = sum(1 for it in roadnet["intersections"] if not it["virtual"])
+        fringe = set(self.incoming_edges) | set(self.outgoing_edges)
+        interior = [r["id"] for r in roadnet["roads"] if r["id"] not in fringe]
+        self.py_rng.shuffle(interior)
+        self.disrupted_links = set(interior[: int(disruption_ratio * n_signals)])
+
+    def _choose_next_edge(self, cur):
+        if cur not in self.lane_connectivity_map:
+            return None
+        cands, weights = [], []
+        for i, direction in enumerate(self.turns):
+            nxt = self.lane_connectivity_map[cur].get(direction)
+            if nxt and nxt not in self.disrupted_links:
+                cands.append(nxt)
+                weights.append(self.turn_probabilities[i] * self.edge_weights.get(nxt, 1.0))
+        if not cands:
+            return None
+        total = sum(weights)
+        if total == 0:
+            return None
+        return self.py_rng.choices(cands, weights=[w / total for w in weights], k=1)[0]
+
+
+class FlowDisruptedTripGenerator(GridTripGenerator):
+    """``FlowDisruptedCityFlowTripGenerator`` (trip_generator.py:391-489): a share of the incoming fringe roads sees
+    a ten-minute burst (arrival rate x 4) starting at a random time within the first twenty minutes.
+
+    The reference draws the burst times while iterating a ``set`` of road ids, whose order follows Python's
+    per-process string hashing; here they are drawn in the order the roads were sampled (identical whenever
+    one road is disrupted, e.g. ``disruption_ratio`` 0.1 on a 3 x 3 grid)."""
+    burst_start_min, burst_start_max, burst_duration, burst_multiplier = 0, 20, 10, 4
+
+    def __init__(self, roadnet, start_time, end_time, inter_mu, inter_sigma, disruption_ratio=0.1, **kw):
+        super().__init__(roadnet, start_time, end_time, inter_mu, inter_sigma, **kw)
+        self.disruption_ratio = disruption_ratio
+        picked = self.py_rng.sample(self.incoming_edges, int(len(self.incoming_edges) * disruption_ratio))
+        self.disrupted_links = set(picked)
+        self.burst_timings = {}
+        for link in picked:
+            t0 = self.py_rng.randint(self.burst_start_min * 60, self.burst_start_max * 60)
+            self.burst_timings[link] = (t0, t0 + self.burst_duration * 60)
+
+    def _gap(self, edge, now):
+        b0, b1 = self.burst_timings.get(edge, (float("inf"), float("inf")))
+        if edge in self.disrupted_links and b0 <= now < b1:
+            return self.np_rng.normal(self.inter_mu / self.burst_multiplier, self.inter_sigma / self.burst_multiplier)
+        return self.np_rng.normal(self.inter_mu, self.inter_sigma)
+
+
+def weibull_flow_rates(np_rng, shape, scale, max_rate, num_segments):
+    """``generate_weibull_flow_rates`` (common/utils.py:136-155): a Gaussian-shaped profile of mean inter-arrival
+    times over the hour's segments, rolled to a random peak (the Weibull draws only advance the generator)."""
+    np_rng.weibull(shape, 1000)
+    peak = np_rng.randint(0, num_segments)
+    x = np.linspace(-2, 2, num_segments)
+    rates = np.exp(-(x ** 2))
+    return np.roll(rates / max(rates) * max_rate, peak)
+
+
+class IntervalTripGenerator(GridTripGenerator):
+    """``IntervalCityFlowTripGenerator`` (trip_generator.py:492-554): the mean inter-arrival time changes every
+    ``interval_duration`` seconds along a Weibull-placed profile."""
+
+    def generate(self, interval_duration=360, shape=1.5, scale=300):
+        self._segment_mean = weibull_flow_rates(self.np_rng, shape, scale, self.inter_mu, int(3600 / interval_duration))
+        flows = []
+        n_intervals = (self.end_time - self.start_time) // interval_duration
+        for edge in self._start_edges():
+            now = self.start_time
+            for k in range(n_intervals):
+                self._mean_now = self._segment_mean[k]
+                now = self._arrivals(edge, now, self.start_time + (k + 1) * interval_duration, flows)
+        return sorted(flows, key=lambda f: f["startTime"])
+
+    def _gap(self, edge, now):
+        return self.np_rng.normal(self._mean_now, self.inter_sigma)
+
+
+class VariableDemandTripGenerator(GridTripGenerator):
+    """``VariableDemandTripGenerator`` (trip_generator.py:557-666): per-edge mean / sigma of the inter-arrival time,
+    scaled by a ten-minute demand profile.  The reference does not seed: its ``random`` stream is the one
+    ``Config`` left (``random.seed(cityflow.seed)``), its numpy stream whatever the caller set -- ``config_seed`` and
+    ``seed`` here."""
+    demand_profile = [0.5, 0.6, 0.75, 1.0, 1.0, 0.5, 0.5, 0.3, 0.3, 1e-6]
+
+    def __init__(self, roadnet, start_time, end_time, inter_mus, inter_sigmas, edge_weights, turn_probs=(1 / 3, 1 / 3, 1 / 3),
+                 seed=None, config_seed=0):
+        super().__init__(roadnet, start_time, end_time, None, None, seed=seed, edge_weights=edge_weights, turn_probs=turn_probs)
+        self.py_rng = random.Random(config_seed)
+        self.inter_mus, self.inter_sigmas = inter_mus, inter_sigmas
+
+    def _start_edges(self):
+        return [e for e in self.incoming_edges if e in self.inter_mus]
+
+    def _gap(self, edge, now):
+        slot = (now % 3600) // 600
+        return self.np_rng.normal(self.inter_mus[edge] / self.demand_profile[slot], self.inter_sigmas[edge] / self.demand_profile[slot])
+
+
+class OneWayTripGenerator(GridTripGenerator):
+    """``CityFlowOneWayTripGenerator`` (trip_generator.py:669-802): one-way grids; north-south and east-west entry
+    roads have their own arrival rates, every vehicle goes straight."""
+
+    def __init__(self, roadnet, start_time, end_time, inter_mu_ns, inter_sigma_ns, inter_mu_ew, inter_sigma_ew,
+                 edge_weights=None, seed=0):
+        super().__init__(roadnet, start_time, end_time, inter_mu_ns, inter_sigma_ns, seed=seed, edge_weights=edge_weights,
+                         turn_probs=(0.0, 0.0, 1.0))
+        self.rates = {"ns": (inter_mu_ns, inter_sigma_ns), "ew": (inter_mu_ew, inter_sigma_ew)}
+        self._kind = {}
+        for r in roadnet["roads"]:
+            p0, p1 = r["points"][0], r["points"][-1]
+            if p0["x"] == p1["x"] and p0["y"] > p1["y"]:
+                self._kind[r["id"]] = "ns"
+            elif p0["y"] == p1["y"] and p0["x"] > p1["x"]:
+                self._kind[r["id"]] = "ew"
+
+    def _start_edges(self):      # all north-south entries first, then the east-west ones (roadnet order within each)
+        inc = set(self.incoming_edges)
+        roads = [r["id"] for r in self.net["roads"] if r["id"] in inc]
+        return [e for e in roads if self._kind.get(e) == "ns"] + [e for e in roads if self._kind.get(e) == "ew"]
+
+    def _gap(self, edge, now):
+        return self.np_rng.normal(*self.rates[self._kind[edge]])
+
+
+def turn_direction(prev_road, cur_road):
+    """``detect_turn_direction`` (trip_generator.py:26-42): from the second field of the road ids."""
+    a, b = prev_road.split("_")[1], cur_road.split("_")[1]
+    if a == b:
+        return "go_straight"
+    return "turn_right" if int(b) > int(a) else "turn_left"
+
+
+class RandomizedTripGenerator(GridTripGenerator):
+    """``CityFlowRandomizedTripGenerator`` (trip_generator.py:805-1027): re-samples an existing flow file -- per entry
+    road the observed inter-arrival statistics (scaled by ``flow_type``) and the observed routes with their
+    frequencies.  ``base_flows`` is that flow file's content.  Streams as for ``VariableDemandTripGenerator``."""
+
+    def __init__(self, roadnet, base_flows, start_time, end_time, seed=None, config_seed=0):
+        self.flow_info, self.stored_routes, self.route_proportions, turn_ratios = self._flow_statistics(base_flows)
+        super().__init__(roadnet, start_time, end_time, None, None, seed=seed,
+                         turn_probs=(turn_ratios["turn_left"], turn_ratios["turn_right"], turn_ratios["go_straight"]))
+        self.py_rng = random.Random(config_seed)
+        self.max_trip_length = max(v["max_route_length"] for v in self.flow_info.values())
+
+    @staticmethod
+    def _flow_statistics(base_flows):
+        counts, starts, lengths, routes, route_counts = {}, {}, {}, {}, {}
+        turns = {"go_straight": 0, "turn_right": 0, "turn_left": 0}
+        all_starts = []
+        for veh in base_flows:
+            route, t0 = veh["route"], veh["startTime"]
+            e = route[0]
+            routes.setdefault(e, [])
+            if route not in routes[e]:
+                routes[e].append(route)
+            rc = route_counts.setdefault(e, {})
+            rc[tuple(route)] = rc.get(tuple(route), 0) + 1
+            counts[e] = counts.get(e, 0) + 1
+            starts.setdefault(e, []).append(t0)
+            lengths.setdefault(e, []).append(len(route))
+            all_starts.append(t0)
+            for i in range(1, len(route)):
+                turns[turn_direction(route[i - 1], route[i])] += 1
+        proportions = {e: {r: n / sum(rc.values()) for r, n in rc.items()} for e, rc in route_counts.items()}
+        total_turns = sum(turns.values())
+        turns = {k: v / total_turns for k, v in turns.items()}
+        hours = (max(all_starts) - min(all_starts)) / 3600
+        info = {}
+        for e in counts:
+            d = np.diff(sorted(starts[e]))
+            info[e] = {"flow_rate": counts[e] / hours, "arrival_diff_mean": np.mean(d), "arrival_diff_std": np.std(d),
+                       "mean_route_length": np.mean(lengths[e]), "min_route_length": np.min(lengths[e]),
+                       "max_route_length": np.max(lengths[e])}
+        return info, routes, proportions, turns
+
+    def _start_edges(self):
+        return [e for e in self.incoming_edges if e in self.flow_info]
+
+    def _gap(self, edge, now):
+        m = self.flow_info[edge]["arrival_diff_mean"]
+        if self.flow_type == "low":
+            m = m + self.np_rng.uniform(-0.5, 0.0)
+        elif self.flow_type == "medium":
+            m = m * 0.75
+        elif self.flow_type == "high":
+            m = m * 0.5
+        else:
+            raise ValueError("Invalid flow type")
+        return self.np_rng.normal(m, self.flow_info[edge]["arrival_diff_std"])
+
+    def _pick_route(self, edge):
+        routes = self.stored_routes[edge]
+        return self.py_rng.choices(routes, weights=[self.route_proportions[edge][tuple(r)] for r in routes], k=1)[0]
+
+    def generate(self, flow_type="low"):
+        self.flow_type = flow_type
+        return super().generate()
 
 
 def synthetic_grid_scenario(rows, cols, vehicles_per_hour_per_road=900, horizon=3600, sigma=0.8, seed=0,

@@ -86,22 +86,19 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
 
 
 @pytest.mark.parametrize("env,capacity,variant", [
-    ({}, 600, (192, 2)),                                 # default at this size: four blocks per SM, cold buffers in the global workspace
-    ({}, 520, (192, 0)),                                 # small enough for four blocks with everything in shared memory
-    ({"TSC_B200_HYBRID": "2"}, 520, (192, 2)),
-    ({"TSC_B200_THREADS": "256"}, 600, (256, 0)),        # three 256-thread blocks per SM
-    ({"TSC_B200_FLAT_CROSS": "1"}, 600, (192, 2)),       # flat (vehicle, cross) pair list instead of lane groups per vehicle
-    ({"TSC_B200_CROSS_GROUP": "32"}, 600, (192, 2)),     # a whole warp per vehicle in the cross phase
-    ({"TSC_B200_CROSS_GROUP": "16"}, 600, (192, 2)),
-    ({"TSC_B200_CROSS_GROUP": "8"}, 600, (192, 2)),
-    ({"TSC_B200_CROSS_GROUP": "2"}, 600, (192, 2)),
-    ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0)),     # per-vehicle template look-up although the scenario has one template
-    ({"TSC_B200_PREFETCH": "0"}, 600, (192, 2)),
-    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (192, 2)),      # plain vector copies instead of cp.async for staging
-    ({"TSC_B200_HYBRID": "0"}, 600, (256, 0)),
-    ({}, 2000, (256, 3)),                                # large replica: decision buffers in the global workspace buy a second block per SM
-    ({"TSC_B200_THREADS": "512"}, 2000, (512, 0)),       # one block per SM, everything in shared memory
-    ({"TSC_B200_THREADS": "1024"}, 2000, (1024, 0)),     # the same with 32 warps at 64 registers
+    ({}, 600, (192, 0, 4)),                                 # default at this size: four 192-thread blocks per SM
+    ({"TSC_B200_THREADS": "256"}, 600, (256, 0, 3)),        # three 256-thread blocks per SM
+    ({}, 1200, (256, 0, 2)),                                # larger replica: two 256-thread blocks per SM (128 registers)
+    ({"TSC_B200_CROSS_GROUP": "32"}, 600, (192, 0, 4)),     # a whole warp per vehicle in the cross phase
+    ({"TSC_B200_CROSS_GROUP": "16"}, 600, (192, 0, 4)),
+    ({"TSC_B200_CROSS_GROUP": "8"}, 600, (192, 0, 4)),
+    ({"TSC_B200_CROSS_GROUP": "2"}, 600, (192, 0, 4)),
+    ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0, 2)),     # per-vehicle template look-up although the scenario has one template
+    ({"TSC_B200_PREFETCH": "0"}, 600, (192, 0, 4)),
+    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (192, 0, 4)),      # plain vector copies instead of cp.async for staging
+    ({}, 2000, (512, 0, 1)),                                # one 512-thread block per SM
+    ({"TSC_B200_THREADS": "1024"}, 2000, (1024, 0, 1)),     # the same with 32 warps at 64 registers
+    ({"TSC_B200_GMEM": "1"}, 600, (1024, 1, 1)),            # working set in a global-memory workspace
 ])
 def test_kernel_variants_agree_with_oracle(cuda_lib, env, capacity, variant, monkeypatch):
     """The code paths an environment switch (or an unusual scenario) selects at tsc_create produce the
@@ -114,7 +111,7 @@ def test_kernel_variants_agree_with_oracle(cuda_lib, env, capacity, variant, mon
     orc = oracle_engine(cfg)
     eng = Engine(cs, 2, 0, vehicle_capacity=capacity)
     info = eng.kernel_info()
-    assert (info["threads"], info["global_workspace"]) == variant, info
+    assert (info["threads"], info["global_workspace"], info["blocks_per_sm"]) == variant, info
     inter = signal_inter_indices(parser)
     rng = np.random.RandomState(7)
     raw = np.ones((2, eng.A), np.int32)

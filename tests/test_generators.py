@@ -78,3 +78,56 @@ def test_generated_grid_runs_on_the_oracle(tmp_path):
         eng.next_step()
     assert eng.get_vehicle_count() > 200
     assert eng.get_finished_vehicle_count() > 0
+
+
+# ---- the rest of the generator family (trip_generator.py:289-1027), each pinned to a flow list recorded from the
+#      reference's own class (tests/golden/make_trips_golden.py) ----
+def _family_generator(g):
+    from pytsc_b200 import generators as G
+    from pytsc_b200.backend.config import Config
+    scenario, cls = str(g["scenario"]), str(g["cls"])
+    kw, gen_kw = json.loads(str(g["args"])), json.loads(str(g["gen_args"]))
+    np_seed = int(g["np_seed"])
+    cfg = Config(scenario, cityflow=dict(flow_rate_type="constant"))
+    net = bundle.load_roadnet(cfg.cityflow_roadnet_file)
+    t0, t1 = kw.pop("start_time"), kw.pop("end_time")
+    if cls == "LinkDisruptedCityFlowTripGenerator":
+        gen = G.LinkDisruptedTripGenerator(net, t0, t1, kw["inter_mu"], kw["inter_sigma"], disruption_ratio=kw["disruption_ratio"], seed=kw["seed"])
+    elif cls == "FlowDisruptedCityFlowTripGenerator":
+        gen = G.FlowDisruptedTripGenerator(net, t0, t1, kw["inter_mu"], kw["inter_sigma"], disruption_ratio=kw["disruption_ratio"], seed=kw["seed"])
+    elif cls == "IntervalCityFlowTripGenerator":
+        gen = G.IntervalTripGenerator(net, t0, t1, kw["inter_mu"], kw["inter_sigma"], seed=kw["seed"])
+        gen_kw.pop("replicate_no")
+    elif cls == "VariableDemandTripGenerator":
+        gen = G.VariableDemandTripGenerator(net, t0, t1, kw["inter_mus"], kw["inter_sigmas"], kw["edge_weights"], seed=np_seed,
+                                            config_seed=cfg.simulator["seed"])
+    elif cls == "CityFlowOneWayTripGenerator":
+        gen = G.OneWayTripGenerator(net, t0, t1, kw["inter_mu_ns"], kw["inter_sigma_ns"], kw["inter_mu_ew"], kw["inter_sigma_ew"])
+    elif cls == "CityFlowRandomizedTripGenerator":
+        base = bundle.load_flow(cfg.resolve_flow_file(cfg.simulator["flow_file"]))
+        gen = G.RandomizedTripGenerator(net, base, t0, t1, seed=np_seed, config_seed=cfg.simulator["seed"])
+    else:
+        raise AssertionError(cls)
+    return net, gen, gen_kw
+
+
+@pytest.mark.parametrize("case", ["trips_link_disrupted_syn_3x3", "trips_flow_disrupted_syn_3x3", "trips_interval_syn_3x3",
+                                  "trips_variable_demand_syn_3x3", "trips_oneway_syn_5x5", "trips_randomized_hangzhou"])
+def test_generator_family_reproduces_reference(case):
+    with np.load(os.path.join(GOLDEN, case + ".npz")) as z:
+        g = {k: z[k] for k in z.files}
+    net, gen, gen_kw = _family_generator(g)
+    roads = [r["id"] for r in net["roads"]]
+    assert roads == [str(x) for x in g["roads"]]
+    assert gen.max_trip_length == int(g["max_trip_length"])
+    extra = json.loads(str(g["extra"]))
+    if "disrupted_links" in extra:
+        assert sorted(gen.disrupted_links) == json.loads(extra["disrupted_links"])
+    if "burst_timings" in extra:
+        assert {k: list(v) for k, v in gen.burst_timings.items()} == json.loads(extra["burst_timings"])
+    flows = gen.generate(**gen_kw)
+    assert len(flows) == len(g["start"])
+    assert [f["startTime"] for f in flows] == list(g["start"])
+    ridx = {r: i for i, r in enumerate(roads)}
+    assert np.array_equal(np.cumsum([0] + [len(f["route"]) for f in flows]), g["route_off"])
+    assert np.array_equal(np.asarray([ridx[r] for f in flows for r in f["route"]]), g["route"])

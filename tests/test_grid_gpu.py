@@ -69,15 +69,14 @@ def grid_6x6(tmp_path_factory):
     return write_grid_scenario(tmp_path_factory.mktemp("grids"), 6, 6, vehicles_per_hour_per_road=900, horizon=600, seed=2)
 
 
-@pytest.mark.parametrize("capacity,staged", [(2200, False), (2600, True)])
-def test_generated_6x6_grid_shared_memory(cuda_lib, grid_6x6, capacity, staged):
-    """One 512-thread block per SM: with the ping-pong re-pack while that fits, with the
-    register-staged one (13 bytes less per vehicle slot) when it is what makes the replica fit."""
+@pytest.mark.parametrize("capacity", [2200, 2600])
+def test_generated_6x6_grid_shared_memory(cuda_lib, grid_6x6, capacity):
+    """One 512-thread block per SM, everything in shared memory."""
     cfg, parser, cs = build_scenario(grid_6x6)
     assert cs.n_signals == 36
     info, n = _lockstep(cs, cfg, parser, 360, capacity)
     assert info["threads"] == 512 and n > 1500
-    assert bool(info["staged"]) == staged and not info["global_workspace"]
+    assert not info["global_workspace"]
 
 
 def test_generated_6x6_grid_gmem(cuda_lib, grid_6x6, gmem_forced):

@@ -11,13 +11,13 @@ run() {   # name, env assignments, args...
     echo "$tool $name rc=$rc :: $(grep -E 'sanitize_case ok' $log | head -1 | cut -c1-160) :: $(grep -E 'RACECHECK SUMMARY|ERROR SUMMARY' $log | tail -1)" >> $out/summary.txt
   done
 }
-run hyb1_192x4        "X=1" --capacity 600
-run plain_192x4       "X=1" --capacity 520
+run t192x4            "X=1" --capacity 600
 run t256x3            "TSC_B200_THREADS=256" --capacity 600
-run hyb2_256          "X=1" --capacity 2000
-run t512              "TSC_B200_THREADS=512" --capacity 2000
+run t256x2            "X=1" --capacity 1200
+run t512              "X=1" --capacity 2000
+run gmem1024          "TSC_B200_GMEM=1" --capacity 600
 run ctl_greedy        "X=1" --capacity 600 --controller greedy
 run ctl_max_pressure  "X=1" --capacity 600 --controller max_pressure --obs position_matrix
 run ctl_sotl          "X=1" --capacity 600 --controller sotl
-run flat_cross        "TSC_B200_FLAT_CROSS=1" --capacity 600
+run registered_host   "X=1" --capacity 600 --registered
 cat $out/summary.txt

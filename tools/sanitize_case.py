@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--controller", default="fixed_time")
     ap.add_argument("--scenario", default="hangzhou_4_4")
     ap.add_argument("--obs", default="lane_features")
+    ap.add_argument("--registered", action="store_true", help="step through the registered host path (packets + host threads)")
     args = ap.parse_args()
     import torch
     from helpers import build_scenario
@@ -31,8 +32,16 @@ def main():
     bufs = eng.alloc_outputs()
     eng.init_program(0)
     arg = 25 if args.controller == "fixed_time" else 3
+    if args.registered:
+        import numpy as np
+        d = eng.dims
+        eng.host_register(obs=np.empty((d["B"], d["A"], d["obs_dim"]), np.float32), reward=np.empty((d["B"], d["A"]), np.float32),
+                          mask=np.empty((d["B"], d["A"], d["n_actions"]), np.uint8), reward_global=np.empty((d["B"],), np.float32))
     for _ in range(args.ticks // 5):
-        eng.env_step(None, bufs, n_ticks=5, controller=CONTROLLERS[args.controller], controller_arg=arg)
+        if args.registered:
+            eng.env_step_registered(None, n_ticks=5, controller=CONTROLLERS[args.controller], controller_arg=arg)
+        else:
+            eng.env_step(None, bufs, n_ticks=5, controller=CONTROLLERS[args.controller], controller_arg=arg)
     torch.cuda.synchronize()
     eng.check()
     c = eng.counters()
