@@ -149,6 +149,9 @@ def _reference_python_worker(args):
 
     for _ in range(n_ff):          # untimed fast-forward into the loaded regime
         net.step(cheap_actions())
+    for _ in range(3):             # untimed: first calls of the getters (lazy properties, caches)
+        net.step(cheap_actions())
+        net.get_action_mask(); net.get_observations(); net.get_rewards()
     t0 = time.perf_counter()
     if mode == "evaluate":         # Evaluate.run itself (controllers/evaluate.py:71-95)
         ev.run((n_steps + 0.5) * ev.delta_time / 3600.0, output_folder=tempfile.mkdtemp(prefix="tsc_eval_"))

@@ -99,6 +99,7 @@ typedef struct tsc_scenario {
     int32_t max_phases;           /* P: row stride of the pytsc phase tables */
     int32_t n_in_total, n_out_total, n_nbr_total;
     int32_t n_ctl_total;          /* length of ctl_in_lane / ctl_out_lane */
+    int32_t n_dm_total;           /* length of dm_lane */
     int32_t n_flow_sets;          /* F >= 1: alternative flow files compiled into this scenario (pytsc's
                                      cityflow.flow_files with flow_rate_type random / sequential,
                                      backends/cityflow/config.py:63-76; DisruptedConfig :106-175).  Every replica
@@ -150,6 +151,11 @@ typedef struct tsc_scenario {
     const int32_t *ctl_off;           /* [A*P+1] */
     const int32_t *ctl_in_lane;       /* incoming lane of the entry */
     const int32_t *ctl_out_lane;      /* LAST outgoing lane listed for it (what controllers.py:165-169 ends up using), -1 = none */
+    /* network-level graph metrics (MetricsParser.density_map, backends/cityflow/metrics.py:170-199): the lanes leading
+     * from signal i to signal j (parsed_network.neighbors_lanes, agent order) = entries dm_off[i*A+j] .. dm_off[i*A+j+1] */
+    const int32_t *dm_off;            /* [A*A+1] */
+    const int32_t *dm_lane;
+    const double  *dm_adjacency;      /* [A][A] parsed_network.adjacency_matrix as the reference adds it (its own, sorted-id, order) */
 
     /* --- options --- */
     int32_t reward_type, obs_type, action_space, round_robin;
@@ -185,6 +191,8 @@ typedef struct tsc_outputs {
     double  *sim;               /* [B][4] n_vehicles, average_travel_time, time_step, n_finished (retriever.py:101-112) */
     double  *metrics;           /* [B][8] n_queued, mean_speed, mean_delay, density, pressure, network_flow,
                                           flickering_signal, norm_mean_speed  (backends/cityflow/metrics.py:221-232) */
+    double  *density_map;       /* [B][A][A] MetricsParser.density_map: clip(mean occupancy of the lanes i -> j, 0, 1), symmetrised,
+                                       + 1e-6 * adjacency  (backends/cityflow/metrics.py:170-199) */
     int32_t *err;               /* [B] sticky error bits of the replica (0 = healthy; 1 | 4 vehicle capacity exceeded,
                                        2 FIFO order lost, 8 bad light phase): a replica with a bit set is frozen and its
                                        rows are stale -- the same bits tsc_check reports, readable without a sync */
@@ -306,6 +314,13 @@ int  tsc_snapshot(tsc_handle h, int32_t replica, int32_t cap, int32_t *vid, int3
  * vehicles given drivable-major front to back.  Syncs. */
 int  tsc_load_snapshot(tsc_handle h, int32_t replica, int32_t n, const int32_t *vid, const int32_t *drivable,
                        const double *distance, const double *speed, const int32_t *route_pos);
+
+/* MetricsParser.mst (backends/cityflow/metrics.py:202-209; common/utils.py:158-161): the maximum spanning tree
+ * (forest, if the signal graph is not connected) of every replica's density map.  density_map: device double
+ * [B][A][A] as tsc_retrieve writes it (symmetric; 0 = no edge); out: device double [B][A][A], -w at [min(u,v)][max(u,v)]
+ * for every tree edge {u, v} of weight w (the sign scipy's minimum_spanning_tree(-density_map) leaves), 0 elsewhere.
+ * Prim's algorithm, one thread block per replica; among equal weights the lower vertex index wins. */
+int  tsc_max_spanning_tree(tsc_handle h, const double *density_map, double *out, void *stream);
 
 /* Synchronise and report sticky device-side error flags: returns 0 or the most
  * severe TSC_E* code; *first_bad_replica (may be NULL) gets the replica index. */

@@ -48,25 +48,16 @@ class MetricsParser:
 
     @property
     def density_map(self):
-        """metrics.py:170-199."""
-        nl = self.parsed_network.neighbors_lanes
-        ids = list(self.traffic_signals.keys())
-        lanes = self.simulator.step_measurements["lane"]
-        dm = np.zeros((len(ids), len(ids)))
-        for i, ts in enumerate(ids):
-            if not nl[ts]:
-                continue
-            for j, other in enumerate(ids):
-                if other in nl[ts]:
-                    ls = nl[ts][other]
-                    dm[i, j] = np.clip(sum(lanes[l]["occupancy"] for l in ls) / len(ls), 0, 1).item()
-        return (dm + dm.T) / 2 + 1e-6 * self.parsed_network.adjacency_matrix
+        """metrics.py:170-199 -- computed by the retrieve kernel (``density_map`` output) for every replica; this is
+        the view replica's matrix."""
+        return np.array(self.simulator.view["density_map"], dtype=np.float64)
 
     @property
     def mst(self):
-        """metrics.py:202-209 / common/utils.py compute_max_spanning_tree."""
-        from scipy.sparse.csgraph import minimum_spanning_tree
-        return minimum_spanning_tree(-1 * self.density_map).toarray()
+        """metrics.py:202-209 / common/utils.py compute_max_spanning_tree -- ``tsc_max_spanning_tree`` on the device
+        (Prim per replica).  Same tree weight as scipy's; among equally heavy edges the choice may differ."""
+        sim = self.simulator
+        return sim.engine.max_spanning_tree(sim._bufs["density_map"])[sim.view_replica].cpu().numpy()
 
     def get_step_stats(self):
         """metrics.py:221-260."""

@@ -19,7 +19,7 @@ from ..binding import Engine
 from ..scenario import compile_scenario
 from .retriever import Retriever
 
-VIEW_OUTPUTS = ("lane_count", "lane_queued", "lane_meas64", "pos_in", "pos_out", "sig_stats64", "sim", "metrics")
+VIEW_OUTPUTS = ("lane_count", "lane_queued", "lane_meas64", "pos_in", "pos_out", "sig_stats64", "sim", "metrics", "density_map")
 
 
 class Simulator:

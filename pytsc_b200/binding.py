@@ -24,7 +24,7 @@ SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "ts
            "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
            "tsc_debug_timing", "tsc_controller_act", "tsc_kernel_variant", "tsc_reset_replicas", "tsc_state_bytes",
            "tsc_save_state", "tsc_load_state", "tsc_reset_flows", "tsc_reset_replicas_flows", "tsc_host_register",
-           "tsc_host_unregister", "tsc_env_step_registered", "tsc_host_packet_bytes")
+           "tsc_host_unregister", "tsc_env_step_registered", "tsc_host_packet_bytes", "tsc_max_spanning_tree")
 
 # tsc_env_step / tsc_controller_act controller codes (include/tsc_b200.h)
 CONTROLLERS = {"external": 0, "fixed_time": 1, "phase_index": 2, "greedy": 3, "max_pressure": 4, "sotl": 5, "random": 6}
@@ -39,7 +39,7 @@ def sotl_arg(theta=3, mu=4, phi_min=5):
 class tsc_outputs_t(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed", "lane_meas64", "pos_in", "pos_out",
-        "sig_stats64", "obs", "state", "reward", "reward_global", "mask", "sim", "metrics", "err")]
+        "sig_stats64", "obs", "state", "reward", "reward_global", "mask", "sim", "metrics", "density_map", "err")]
 
 
 class TscError(RuntimeError):
@@ -74,6 +74,7 @@ def load_library(path=None):
     L.tsc_env_step_registered.argtypes = [vp, vp, i32, i32, i32]
     L.tsc_host_packet_bytes.argtypes = [vp]
     L.tsc_host_packet_bytes.restype = C.c_int64
+    L.tsc_max_spanning_tree.argtypes = [vp, vp, vp, vp]
     L.tsc_state_bytes.argtypes = [vp]
     L.tsc_state_bytes.restype = C.c_int64
     L.tsc_save_state.argtypes = [vp, vp, C.c_int64, vp]
@@ -125,6 +126,7 @@ OUTPUT_SPECS = {   # name -> (shape builder, torch dtype name)
     "mask": (lambda d: (d["B"], d["A"], d["n_actions"]), "uint8"),
     "sim": (lambda d: (d["B"], 4), "float64"),
     "metrics": (lambda d: (d["B"], 8), "float64"),
+    "density_map": (lambda d: (d["B"], d["A"], d["A"]), "float64"),
     "err": (lambda d: (d["B"],), "int32"),
 }
 
@@ -276,6 +278,15 @@ class Engine:
         if actions is not None:
             assert actions.dtype == np.int32 and actions.shape == (self.B, self.A) and actions.flags["C_CONTIGUOUS"]
         self._check(self.lib.tsc_env_step_registered(self.h, _np_ptr(actions), controller, controller_arg, n_ticks))
+
+    def max_spanning_tree(self, density_map):
+        """``MetricsParser.mst`` for every replica: float64 [B, A, A] device tensor in (as the ``density_map`` output), the
+        tree's edges out (-weight in the upper triangle, scipy's sign convention)."""
+        torch = self.torch
+        assert density_map.dtype == torch.float64 and tuple(density_map.shape) == (self.B, self.A, self.A) and density_map.is_contiguous()
+        out = torch.empty_like(density_map)
+        self._check(self.lib.tsc_max_spanning_tree(self.h, _ptr(density_map), _ptr(out), self._stream()))
+        return out
 
     def host_packet_bytes(self):
         return int(self.lib.tsc_host_packet_bytes(self.h))

@@ -88,6 +88,8 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     const int *nbr_off, *nbr_idx;
     const double *nbr_weight;
     const int *ctl_off, *ctl_in_lane, *ctl_out_lane;   // rule-based controllers: lanes served by every pytsc phase
+    const int *dm_off, *dm_lane;                       // density map: lanes leading from signal i to signal j
+    const double *dm_adjacency;
     const u32 *obs_code;      // [A * state_dim] lane-feature row recipe: 0 = static, else kind | truncate << 3 | argument << 4
     const float *obs_static;  // [A * state_dim] the static values (lane features as the reference stores them, -1 padding)
     int reward_type, obs_type, action_space, round_robin, visibility, yellow_time;
@@ -206,6 +208,18 @@ enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1A, PT_PHASE1, PT_PHASE1C
        PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_NENT, PT_N };
 __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
     if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
+}
+
+// Append to a per-tick work list from whichever lanes of the warp are here together: one atomic per warp
+// instead of one per lane (the counters live in shared memory; a hundred serialised atomics per phase showed up
+// as thousands of cycles per tick).  Returns the caller's position in the list.
+__device__ __forceinline__ int warp_append(int *counter) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
 }
 
 // Device-side vehicle template row: the ABI's TSC_T_STRIDE doubles followed by constants derived on
@@ -494,7 +508,7 @@ __device__ void compact_slots(const DevScn &S, const Layout &Y, Ctx &c) {
         u8 pjv = 0;
         if (dst != (int) NONE16) {
             p = c.pos[i]; s = c.spd[i]; rp = c.rpos[i]; vd = c.vid[i]; dnv = c.dn[i]; pjv = c.pj[i];
-            el = (int) (dnv & 0xFFFF) >= S.L ? c.ellt[i] : INT_MAX;
+            el = c.ellt[i];
             ld = c.lead[i]; fo = c.foll[i];
             if (ld != NONE16) ld = map[ld];
             if (fo != NONE16) fo = map[fo];
@@ -505,7 +519,7 @@ __device__ void compact_slots(const DevScn &S, const Layout &Y, Ctx &c) {
         __syncthreads();
         if (dst != (int) NONE16) {
             c.pos[dst] = p; c.spd[dst] = s; c.rpos[dst] = rp; c.vid[dst] = vd; c.dn[dst] = dnv; c.pj[dst] = pjv;
-            if ((int) (dnv & 0xFFFF) >= S.L) c.ellt[dst] = el;
+            c.ellt[dst] = el;
             c.lead[dst] = ld; c.foll[dst] = fo; c.blk[dst] = bk;
         }
     }
@@ -603,7 +617,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         if (tid == 0) { c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned; }
     }
     for (int i = tid; i < n_old; i += NT)      // the heads among the vehicles that were here before this tick
-        if (c.vid[i] >= 0 && c.lead[i] == NONE16) hlist[atomicAdd(&c.h->n_h, 1)] = (u16) i;
+        if (c.vid[i] >= 0 && c.lead[i] == NONE16) hlist[warp_append(&c.h->n_h)] = (u16) i;
     __syncthreads();
     pt_mark(c, PT_SPAWN);
     const int n_slots = c.h->n_new;
@@ -689,7 +703,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         ns = min2(ns, cf);
         if (d >= L || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {   // intersection related speed applies (A.5)
             c.nspd[i] = ns;
-            alist[atomicAdd(&c.h->n_a, 1)] = (u16) i;
+            alist[warp_append(&c.h->n_a)] = (u16) i;
             continue;
         }
         finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
@@ -728,7 +742,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         }
         if (!done) {   // phase 2 examines the crosses of the lane-link
             c.npos[i] = vi;
-            c.xlist[atomicAdd(&c.h->n_x, 1)] = (u16) i;
+            c.xlist[warp_append(&c.h->n_x)] = (u16) i;
             continue;
         }
         ns = min2(ns, vi);
@@ -838,7 +852,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         c.rpos[i] = q;
         c.dn[i] = (u32) dd | ((u32) (__ldg(S.route_seq + q + 1) & 0xFFFF) << 16);
         c.pj[i] = c.mv_pj[m];
-        if (dd >= L) c.ellt[i] = tick;      // enterLaneLinkTime is only read while the vehicle is on a lane-link
+        c.ellt[i] = dd >= L ? tick : INT_MAX;      // enterLaneLinkTime: the tick a lane-link was entered, "never" on a lane
         // the list of the drivable it enters
         const int n_in = c.ent[dd];
         if (n_in == 1) {
@@ -1135,7 +1149,8 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
     double *s_loc = l_nms + L;           // [A] local reward term
     double *s_prs = s_loc + A;           // [A] pressure
     int *l_q = (int *) (s_prs + A);      // [L]
-    double *const r_tail = (double *) (l_q + ((L + 1) & ~1));      // what follows: position-matrix windows, or the host packet
+    // what follows, 16-byte aligned: position-matrix windows, or the host packet
+    double *const r_tail = (double *) ((unsigned char *) c.npos + ((24 * L + 16 * A + 4 * L + 15) & ~15));
     // registered host path: the replica's packet is assembled here, then stored to host memory in 16-byte pieces
     unsigned char *const pkst = a.pk ? (unsigned char *) r_tail : nullptr;
 
@@ -1175,6 +1190,23 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
                 float *f = (float *) pkst + 3 * i;
                 f[0] = (float) l_q[l]; f[1] = ref_trunc(l_occ[l], tr); f[2] = ref_trunc(l_ms[l], tr);
             }
+        }
+    }
+
+    // --- MetricsParser.density_map (backends/cityflow/metrics.py:170-199): thread per signal pair ---
+    if (O.density_map) {
+        auto directed = [&](int i, int j) -> double {
+            const int e0 = __ldg(S.dm_off + i * A + j), e1 = __ldg(S.dm_off + i * A + j + 1);
+            if (e1 == e0) return 0.0;
+            double tot = 0.0;
+            for (int e = e0; e < e1; ++e) tot += l_occ[__ldg(S.dm_lane + e)];
+            const double m = tot / (double) (e1 - e0);
+            return m < 0.0 ? 0.0 : (m > 1.0 ? 1.0 : m);
+        };
+        double *dm = O.density_map + (size_t) b * A * A;
+        for (int p = tid; p < A * A; p += NT) {
+            const int i = p / A, j = p - i * A;
+            dm[p] = (directed(i, j) + directed(j, i)) / 2 + 1e-6 * __ldg(S.dm_adjacency + p);
         }
     }
 
@@ -1564,6 +1596,57 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
 }
 
 // ----------------------------------------------------------------------------
+// MetricsParser.mst: maximum spanning forest of a replica's density map (Prim, one block per replica)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tsc_mst_kernel(const double *dm, double *out, int A) {
+    extern __shared__ __align__(16) unsigned char mst_smem[];
+    double *key = (double *) mst_smem;            // [A] heaviest edge from the tree to the vertex (0 = none yet)
+    int *parent = (int *) (key + A);              // [A]
+    int *in_tree = parent + A;                    // [A]
+    __shared__ double red_w[8];
+    __shared__ int red_v[8];
+    __shared__ int pick;
+    const double *W = dm + (size_t) blockIdx.x * A * A;
+    double *O = out + (size_t) blockIdx.x * A * A;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int p = tid; p < A * A; p += 256) O[p] = 0.0;
+    for (int v = tid; v < A; v += 256) { key[v] = 0.0; parent[v] = -1; in_tree[v] = 0; }
+    __syncthreads();
+    for (int it = 0; it < A; ++it) {
+        // the vertex outside the tree with the heaviest edge into it; none reachable: the lowest outsider (a new component)
+        double bw = -1.0;
+        int bv = INT_MAX;
+        for (int v = tid; v < A; v += 256)
+            if (!in_tree[v] && (key[v] > bw || (key[v] == bw && v < bv))) { bw = key[v]; bv = v; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
+            const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            if (ow > bw || (ow == bw && ov < bv)) { bw = ow; bv = ov; }
+        }
+        if (lane == 0) { red_w[w] = bw; red_v[w] = bv; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < 8; ++k)
+                if (red_w[k] > bw || (red_w[k] == bw && red_v[k] < bv)) { bw = red_w[k]; bv = red_v[k]; }
+            pick = bv;
+            in_tree[bv] = 1;
+            if (bw > 0.0) {
+                const int p = parent[bv];
+                O[(size_t) min(p, bv) * A + max(p, bv)] = -bw;
+            }
+        }
+        __syncthreads();
+        const int u = pick;
+        for (int v = tid; v < A; v += 256) {
+            const double wt = W[(size_t) u * A + v];
+            if (!in_tree[v] && wt > key[v]) { key[v] = wt; parent[v] = u; }
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------
 // Host side: handle, tables, C ABI
 // ----------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -1858,6 +1941,9 @@ int tsc_create(const tsc_scenario_t *s, int32_t n_replicas, int32_t device, int3
     for (int e = 0; e < s->n_ctl_total; ++e)
         if (s->ctl_in_lane[e] < 0 || s->ctl_in_lane[e] >= s->n_lanes || s->ctl_out_lane[e] >= s->n_lanes)
             return fail(TSC_EINVAL, "controller table entry %d: bad lane index", e);
+    if (!s->dm_off || s->dm_off[(size_t) s->n_signals * s->n_signals] != s->n_dm_total) return fail(TSC_EINVAL, "dm_off does not end at n_dm_total");
+    for (int e = 0; e < s->n_dm_total; ++e)
+        if (s->dm_lane[e] < 0 || s->dm_lane[e] >= s->n_lanes) return fail(TSC_EINVAL, "density-map table entry %d: bad lane index", e);
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(TSC_EINVAL, "device %d not available (%d devices)", device, ndev);
@@ -1903,6 +1989,7 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     UP(sig_phase_green, A * s->max_phases) UP(sig_min_time, A * s->max_phases) UP(sig_max_time, A * s->max_phases)
     UP(nbr_off, A + 1) UP(nbr_idx, s->n_nbr_total) UP(nbr_weight, s->n_nbr_total)
     UP(ctl_off, A * s->max_phases + 1) UP(ctl_in_lane, s->n_ctl_total) UP(ctl_out_lane, s->n_ctl_total)
+    UP(dm_off, (size_t) A * A + 1) UP(dm_lane, s->n_dm_total) UP(dm_adjacency, (size_t) A * A)
 #undef UP
     {   // pytsc's lane length in vehicle cells (retriever.py:73), the same IEEE division the kernel used to repeat per lane
         std::vector<double> cells(L > 0 ? L : 1, 1.0);
@@ -2686,6 +2773,16 @@ int tsc_load_snapshot(tsc_handle E, int32_t b, int32_t n, const int32_t *vid, co
     }
     h->n_slots = n; h->n_running = n;
     CUDA_TRY(cudaMemcpy(E->images + (size_t) b * Y.img_bytes, img.data(), Y.img_bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int tsc_max_spanning_tree(tsc_handle E, const double *density_map, double *out, void *stream) {
+    if (!E || !density_map || !out) return fail(TSC_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(E->device));
+    const int A = E->S.A;
+    tsc_mst_kernel<<<E->B, 256, (size_t) A * 16, (cudaStream_t) stream>>>(density_map, out, A);
+    E->launches += 1;
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

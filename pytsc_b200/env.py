@@ -47,33 +47,6 @@ def reduce_episode_metrics(vec, group=None):
             "mean_global_reward": v[3] / steps, "mean_n_queued": v[4] / steps, "replicas": int(v[6])}
 
 
-def density_map_operator(parsed_network):
-    """The linear part of ``MetricsParser.density_map`` (backends/cityflow/metrics.py:170-199) as a
-    matrix: row ``i * A + j`` averages the occupancies of the lanes leading from signal i to its
-    neighbour j.  Returns (W float64 [A*A, L], adjacency float64 [A, A]) as numpy arrays."""
-    import numpy as np
-    ids = list(parsed_network.traffic_signals.keys())
-    lane_index = {l: k for k, l in enumerate(parsed_network.lanes)}
-    A, L = len(ids), len(parsed_network.lanes)
-    W = np.zeros((A * A, L))
-    nl = parsed_network.neighbors_lanes
-    for i, ts in enumerate(ids):
-        for j, other in enumerate(ids):
-            lanes = (nl.get(ts) or {}).get(other)
-            if lanes:
-                for l in lanes:
-                    W[i * A + j, lane_index[l]] += 1.0 / len(lanes)
-    return W, np.asarray(parsed_network.adjacency_matrix, np.float64)
-
-
-def batched_density_map(lane_occupancy, W, adjacency):
-    """``MetricsParser.density_map`` for every replica: lane_occupancy [B, L] -> [B, A, A] (torch, any device):
-    clip(mean occupancy of the connecting lanes, 0, 1), symmetrised, + 1e-6 * adjacency."""
-    A = adjacency.shape[0]
-    dm = (lane_occupancy.to(W.dtype) @ W.T).clamp_(0.0, 1.0).view(-1, A, A)
-    return (dm + dm.transpose(1, 2)) / 2 + 1e-6 * adjacency
-
-
 STEP_OUTPUTS = ("obs", "state", "reward", "reward_global", "mask", "sim", "metrics", "err")
 LANE_OUTPUTS = ("lane_count", "lane_queued", "lane_occupancy", "lane_mean_speed")
 
@@ -250,19 +223,17 @@ class BatchedTrafficSignalNetwork:
         return self.out["reward"]
 
     def get_density_map(self):
-        """``MetricsParser.density_map`` (backends/cityflow/metrics.py:170-199) per replica: [B, A, A] on the
-        device.  Needs ``lane_outputs=True``."""
-        if "lane_occupancy" not in self.out:
-            raise RuntimeError("get_density_map needs BatchedTrafficSignalNetwork(..., lane_outputs=True)")
+        """``MetricsParser.density_map`` (backends/cityflow/metrics.py:170-199) per replica: float64 [B, A, A] on the
+        device, computed by the retrieve kernel from the current state."""
         if not hasattr(self, "_dm"):
-            W, adj = density_map_operator(self.parsed_network)
-            self._dm = (self.torch.from_numpy(W).to(self.device), self.torch.from_numpy(adj).to(self.device))
-        return batched_density_map(self.out["lane_occupancy"], *self._dm)
+            self._dm = self.engine.alloc_outputs(["density_map"])
+        self.engine.retrieve(self._dm)
+        return self._dm["density_map"]
 
-    def get_mst(self, replica=0):
-        """``MetricsParser.mst`` (metrics.py:202-209; common/utils.py:145-165) for one replica (host, scipy)."""
-        from scipy.sparse.csgraph import minimum_spanning_tree
-        return minimum_spanning_tree(-1 * self.get_density_map()[replica].cpu().numpy()).toarray()
+    def get_mst(self):
+        """``MetricsParser.mst`` (metrics.py:202-209; common/utils.py:158-161) per replica: float64 [B, A, A] on the device,
+        the maximum spanning tree of the density map (``tsc_max_spanning_tree``)."""
+        return self.engine.max_spanning_tree(self.get_density_map())
 
     def get_env_info(self):
         """Per-replica step statistics (backends/cityflow/metrics.py:221-232) as tensors."""

@@ -40,7 +40,7 @@ class tsc_scenario_t(C.Structure):
         ("abi_version", _i), ("n_lanes", _i), ("n_lanelinks", _i), ("n_signals", _i), ("n_vehicles", _i),
         ("n_templates", _i), ("n_route_seq", _i), ("n_cross_entries", _i), ("horizon_ticks", _i),
         ("max_raw_phases", _i), ("max_phases", _i), ("n_in_total", _i), ("n_out_total", _i), ("n_nbr_total", _i),
-        ("n_ctl_total", _i), ("n_flow_sets", _i),
+        ("n_ctl_total", _i), ("n_dm_total", _i), ("n_flow_sets", _i),
         ("drv_length", _pd), ("drv_max_speed", _pd), ("lane_ll_off", _pi), ("lane_ll", _pi),
         ("lane_spawn_off", _pi), ("lane_spawn_vid", _pi), ("ll_start_lane", _pi), ("ll_end_lane", _pi),
         ("ll_signal", _pi), ("ll_roadlink", _pi), ("ll_type", _pi), ("ll_cross_off", _pi),
@@ -52,6 +52,7 @@ class tsc_scenario_t(C.Structure):
         ("sig_phase_green", _pu8), ("sig_min_time", _pi), ("sig_max_time", _pi),
         ("nbr_off", _pi), ("nbr_idx", _pi), ("nbr_weight", _pd),
         ("ctl_off", _pi), ("ctl_in_lane", _pi), ("ctl_out_lane", _pi),
+        ("dm_off", _pi), ("dm_lane", _pi), ("dm_adjacency", _pd),
         ("reward_type", _i), ("obs_type", _i), ("action_space", _i), ("round_robin", _i), ("visibility", _i),
         ("yellow_time", _i), ("obs_dim", _i), ("state_dim", _i), ("n_actions", _i), ("reference_exact", _i),
         ("max_lanes_per_signal", _i), ("max_obs_phases", _i),
@@ -326,6 +327,13 @@ def compile_scenario(config, parser, flows=None, flow_file=None, flow_sets=None)
     a["ctl_off"], a["ctl_in_lane"] = _csr(ctl_in)
     _, a["ctl_out_lane"] = _csr(ctl_out)
 
+    # MetricsParser.density_map (backends/cityflow/metrics.py:170-199): lanes from signal i to signal j in agent order,
+    # and the adjacency matrix exactly as the reference adds it (its rows follow the SORTED ids: SURVEY B5)
+    nl = parser.neighbors_lanes
+    a["dm_off"], a["dm_lane"] = _csr([[lane_idx[l] for l in ((nl.get(ti) or {}).get(tj) or [])]
+                                      for ti in signal_ids for tj in signal_ids])
+    a["dm_adjacency"] = np.asarray(parser.adjacency_matrix, f64).reshape(-1)
+
     vis = int(sig["visibility"])
     obs_type = OBS_TYPES[sig["observation_space"]]
     state_dim = MAX_N_CONTROLLED_LANES * 12 + MAX_PHASES
@@ -335,7 +343,7 @@ def compile_scenario(config, parser, flows=None, flow_file=None, flow_sets=None)
              n_templates=len(sp["templates"]) or 1, n_route_seq=len(seq), n_cross_entries=len(xs),
              horizon_ticks=horizon, max_raw_phases=max_raw, max_phases=P,
              n_in_total=int(a["sig_in_off"][-1]), n_out_total=int(a["sig_out_off"][-1]),
-             n_nbr_total=int(a["nbr_off"][-1]), n_ctl_total=int(a["ctl_off"][-1]), n_flow_sets=F,
+             n_nbr_total=int(a["nbr_off"][-1]), n_ctl_total=int(a["ctl_off"][-1]), n_dm_total=int(a["dm_off"][-1]), n_flow_sets=F,
              reward_type=REWARD_TYPES[sig["reward_function"]], obs_type=obs_type, action_space=act,
              round_robin=int(bool(sig["round_robin"])), visibility=vis, yellow_time=int(sig["yellow_time"]),
              obs_dim=obs_dim, state_dim=state_dim, n_actions=(P if act == 0 else 2),

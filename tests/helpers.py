@@ -178,6 +178,16 @@ class FakeDeviceEngine:
             "sig_stats64": [[s.n_queued, s.occupancy, s.mean_speed, s.mean_delay, s.outgoing_occupancy, s.pressure,
                              s.norm_time_on_phase, s.current_phase_index] for s in sig],
         }
+        ids = list(p.signals.keys())      # MetricsParser.density_map (backends/cityflow/metrics.py:170-199), written out
+        nl = p.parser.neighbors_lanes if hasattr(p, "parser") else p.parsed_network.neighbors_lanes
+        dm = np.zeros((len(ids), len(ids)))
+        for i, ti in enumerate(ids):
+            for j, tj in enumerate(ids):
+                ls = (nl.get(ti) or {}).get(tj)
+                if ls:
+                    dm[i, j] = np.clip(sum(lm[l]["occupancy"] for l in ls) / len(ls), 0, 1)
+        adj = np.asarray((p.parser if hasattr(p, "parser") else p.parsed_network).adjacency_matrix, np.float64)
+        vals["density_map"] = (dm + dm.T) / 2 + 1e-6 * adj
         sm = p.step_measurements["sim"]
         vals["sim"] = [sm["n_vehicles"], sm["average_travel_time"], sm["time_step"], p.engine.get_finished_vehicle_count()]
         st = p.step_stats()

@@ -85,27 +85,20 @@ def test_rule_based_controller_and_wrapper(fake_engine):
     assert len(step_out) == 5 and len(step_out[0]) == info["n_agents"]
 
 
-def test_batched_density_map_matches_metrics_parser():
-    """env.batched_density_map (torch, [B, L] -> [B, A, A]) against the formula MetricsParser.density_map
-    applies lane by lane (backends/cityflow/metrics.py:170-199), random occupancies incl. values above 1."""
+def test_density_map_tables_follow_neighbors_lanes():
+    """The compiled density-map tables (dm_off / dm_lane / dm_adjacency) hold parsed_network.neighbors_lanes in agent
+    order and the adjacency matrix as the reference adds it (backends/cityflow/metrics.py:170-199)."""
     import numpy as np
-    import torch
     from helpers import build_scenario
-    from pytsc_b200.env import batched_density_map, density_map_operator
-    for name in ("hangzhou_4_4", "jinan_3_4", "syn_1x1"):
+    for name in ("hangzhou_4_4", "jinan_3_4", "manhattan_16_3", "syn_1x1"):
         cfg, parser, cs = build_scenario(name)
-        W, adj = density_map_operator(parser)
-        rng = np.random.RandomState(5)
-        occ = rng.uniform(0, 1.6, size=(3, len(parser.lanes)))
-        got = batched_density_map(torch.from_numpy(occ), torch.from_numpy(W), torch.from_numpy(adj)).numpy()
         ids = list(parser.traffic_signals.keys())
-        for b in range(3):
-            lanes = {l: {"occupancy": occ[b, k]} for k, l in enumerate(parser.lanes)}
-            dm = np.zeros((len(ids), len(ids)))
-            for i, ts in enumerate(ids):
-                for j, other in enumerate(ids):
-                    if parser.neighbors_lanes[ts] and other in parser.neighbors_lanes[ts]:
-                        ls = parser.neighbors_lanes[ts][other]
-                        dm[i, j] = np.clip(sum(lanes[l]["occupancy"] for l in ls) / len(ls), 0, 1)
-            want = (dm + dm.T) / 2 + 1e-6 * adj
-            assert np.allclose(got[b], want, rtol=1e-12, atol=1e-15), name
+        A = len(ids)
+        off, lanes = np.asarray(cs.dm_off), np.asarray(cs.dm_lane)
+        assert off[-1] == cs.n_dm_total and len(off) == A * A + 1
+        for i, ti in enumerate(ids):
+            for j, tj in enumerate(ids):
+                want = (parser.neighbors_lanes.get(ti) or {}).get(tj) or []
+                got = [cs.lane_ids[l] for l in lanes[off[i * A + j]:off[i * A + j + 1]]]
+                assert got == list(want), (name, ti, tj)
+        assert np.array_equal(np.asarray(cs.dm_adjacency).reshape(A, A), np.asarray(parser.adjacency_matrix, np.float64))

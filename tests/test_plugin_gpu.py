@@ -150,3 +150,82 @@ def test_batched_env_rule_based_controllers(cuda_lib):
             assert torch.equal(a.get_action_mask(), b.get_action_mask()), (name, t)
         a.check(); b.check()
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("scenario", ["hangzhou_4_4", "jinan_3_4", "manhattan_16_3"])
+def test_graph_metrics_against_reference_metrics_parser(cuda_lib, scenario):
+    """density_map (retrieve kernel) and mst (tsc_max_spanning_tree) through the unmodified reference facade on the gpu
+    backend, against the reference's own MetricsParser (backends/cityflow/metrics.py:170-209) running its CityFlow
+    backend over the oracle engine, in lock-step under the same actions."""
+    import random
+    from scipy.sparse.csgraph import connected_components
+    pytsc = reference_pytsc()
+    if pytsc is None:
+        pytest.skip("reference pytsc not importable on this machine")
+    import sys
+    from pytsc_b200 import compat
+    from oracle.engine import Engine as OracleEngine
+    import pytsc.backends.cityflow.simulator as cf_sim
+    cf_sim.cityflow.Engine = OracleEngine if getattr(sys.modules.get("cityflow"), "__pytsc_b200_stub__", False) else cf_sim.cityflow.Engine
+    from bench import materialise_reference_scenario
+    import tempfile
+    import pytsc.backends.cityflow.config as cf_config
+    import pytsc.common.config as base_config
+    kw = dict(cityflow=dict(flow_rate_type="constant"), signal=dict(observation_space="lane_features", reward_function="queue_length",
+                                                                   action_space="phase_selection", round_robin=False))
+    root = tempfile.mkdtemp(prefix="tsc_refscn_")
+    name = materialise_reference_scenario(dict(scenario=scenario, kw=kw), root)
+    old = (base_config.CONFIG_DIR, cf_config.CONFIG_DIR)
+    base_config.CONFIG_DIR, cf_config.CONFIG_DIR = root, root + "/cityflow"
+    try:
+        ref = pytsc.TrafficSignalNetwork(name, "cityflow", **kw)
+    finally:
+        base_config.CONFIG_DIR, cf_config.CONFIG_DIR = old
+    gkw = dict(kw, gpu=dict(n_replicas=2, view_replica=1, vehicle_capacity=1600))
+    net = pytsc.TrafficSignalNetwork(scenario, "gpu", **gkw)
+    rng = random.Random(4)
+    for t in range(60):
+        mask = ref.get_action_mask()
+        acts = [rng.choice([k for k, m in enumerate(row) if m]) for row in mask]
+        ref.step(acts)
+        net.step(acts)
+        if t % 6 == 5:
+            want, got = np.asarray(ref.metrics.density_map), np.asarray(net.metrics.density_map)
+            assert want.shape == got.shape and want.max() > 1e-3
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15)
+            tw, tg = np.asarray(ref.metrics.mst), np.asarray(net.metrics.mst)
+            sym = lambda m: np.triu(m + m.T - np.diag(np.diag(m)))
+            assert tw.sum() == pytest.approx(tg.sum(), rel=1e-12)                      # same (maximum) tree weight
+            assert np.count_nonzero(sym(tg)) == np.count_nonzero(sym(tw))              # same number of edges
+            assert ((sym(tg) != 0) <= (np.triu(want + want.T) != 0)).all()             # edges of the signal graph only
+            n_comp, _ = connected_components(sym(tg) != 0, directed=False)
+            assert n_comp == len(tg) - np.count_nonzero(sym(tg))                       # a forest
+    net.simulator.close_simulator()
+
+
+def test_batched_env_graph_metrics(cuda_lib):
+    """BatchedTrafficSignalNetwork.get_density_map / get_mst: every replica, device tensors; equal to the plugin view."""
+    import torch
+    from pytsc_b200 import BatchedTrafficSignalNetwork
+    kw = dict(signal=dict(observation_space="lane_features", reward_function="queue_length",
+                          action_space="phase_selection", round_robin=False), gpu=dict(vehicle_capacity=1200))
+    env = BatchedTrafficSignalNetwork("jinan_3_4", n_replicas=5, lane_outputs=True, **kw)
+    for _ in range(50):
+        env.step(controller="fixed_time", green_time=25)
+    dm, mst = env.get_density_map(), env.get_mst()
+    assert dm.shape == (5, 12, 12) and mst.shape == (5, 12, 12) and dm.dtype == torch.float64
+    assert torch.equal(dm, dm.transpose(1, 2)) and torch.equal(dm[0], dm[4]) and torch.equal(mst[0], mst[3])
+    occ = env.out["lane_occupancy"][0].double().cpu().numpy()
+    ids = list(env.parsed_network.traffic_signals.keys())
+    nl, lanes = env.parsed_network.neighbors_lanes, env.scenario.lane_ids
+    want = np.zeros((12, 12))
+    for i, ti in enumerate(ids):
+        for j, tj in enumerate(ids):
+            ls = (nl.get(ti) or {}).get(tj)
+            if ls:
+                want[i, j] = np.clip(sum(occ[lanes.index(l)] for l in ls) / len(ls), 0, 1)
+    want = (want + want.T) / 2 + 1e-6 * np.asarray(env.parsed_network.adjacency_matrix)
+    np.testing.assert_allclose(dm[0].cpu().numpy(), want, rtol=1e-6)      # lane_occupancy output is fp32
+    m = mst[0].cpu().numpy()
+    assert np.count_nonzero(m) == 11 and (m <= 0).all()
+    env.close()

@@ -1,0 +1,19 @@
+#!/bin/bash
+# GPU visit 4: slot-stable kernel after the ellt / alignment fixes and warp-aggregated list appends
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_engine_gpu.py tests/test_episode_gpu.py -m gpu -x -q > gpurun_out/pytest_engine.log 2>&1; tail -15 gpurun_out/pytest_engine.log
+timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_engine_gpu.py --deselect tests/test_episode_gpu.py > gpurun_out/pytest_gpu.log 2>&1; tail -25 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_short.json 2> gpurun_out/bench_short.err; python - <<'PY'
+import json
+try:
+    d=json.load(open("gpurun_out/bench_short.json"))
+    print("bench short: dev ms %.4f  e2e ms %.4f  policy %.3f  V %.1f  frac %.4f  match %s  kernel %s" % (d["ms_per_step"], d["e2e"]["ms_per_step"], d["e2e"]["host_policy_ms_per_step"], d["config"]["mean_running_vehicles"], d["roofline"]["frac"], d["e2e"]["matches_device_leg"], d["config"]["kernel"]))
+except Exception as e:
+    print("bench short failed", e); print(open("gpurun_out/bench_short.err").read()[-3000:])
+PY
+python tools/phase_timing.py 640 > gpurun_out/phase_timing.txt 2>&1; cat gpurun_out/phase_timing.txt
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 900 gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tsc_step -s 372 -c 1 -f -o gpurun_out/prof \
+    python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out
