@@ -60,6 +60,20 @@ class Simulator:
         self._raw0 = np.asarray(self.scenario.sig_phase_raw).reshape(self.engine.A, -1)
         self.retriever = Retriever(self)
         self.cityflow_retriever = self.retriever          # the name the reference uses (simulator.py:75)
+        # cityflow.save_replay (backends/cityflow/config.py:88-99): CityFlow-format replay of the view replica
+        self._replay = None
+        self._raw_now = self._raw0[:, 0].copy()
+        if self.config.simulator.get("save_replay", False):
+            import os
+            from ..replay import ReplayWriter
+            out_dir = gpu.get("replay_dir") or self.config.dir
+            path = lambda name: os.path.join(out_dir, name)
+            for name in (self.config.simulator.get("replay_log_file", "replay_log_file.txt"),
+                         self.config.simulator.get("roadnet_log_file", "roadnet_log_file.json")):
+                os.makedirs(os.path.dirname(path(name)) or ".", exist_ok=True)
+            self._replay = ReplayWriter(self.scenario, self.parsed_network.net,
+                                        path(self.config.simulator.get("replay_log_file", "replay_log_file.txt")),
+                                        path(self.config.simulator.get("roadnet_log_file", "roadnet_log_file.json")))
         wait = int(self.config.simulator["initial_wait_time"])
         if wait:
             self.engine.step(wait)
@@ -68,6 +82,9 @@ class Simulator:
 
     def close_simulator(self):
         """simulator.py:91-95 (engine.reset())."""
+        if getattr(self, "_replay", None) is not None:
+            self._replay.close()
+            self._replay = None
         if self.engine is not None:
             self.engine.close()
             self.engine = None
@@ -99,13 +116,30 @@ class Simulator:
                 raise RuntimeError("gpu backend: every signal must be given a phase before simulator_step")
             torch = self.engine.torch
             act = torch.from_numpy(np.repeat(self._pending[None], self.n_replicas, 0)).to(self.engine.device)
-            self.engine.env_step(act, self._bufs, n_ticks=int(n_steps), controller=2)
+            self._raw_now = self._raw0[np.arange(self.engine.A), self._pending].copy()
+            if self._replay is None:
+                self.engine.env_step(act, self._bufs, n_ticks=int(n_steps), controller=2)
+            else:                         # one tick per launch so that every tick can be logged (same trajectory)
+                self.engine.env_step(act, None, n_ticks=1, controller=2)
+                self._log_replay()
+                for _ in range(int(n_steps) - 1):
+                    self.engine.step(1)
+                    self._log_replay()
+                self.engine.retrieve(self._bufs)
             self._pending = None
+        elif self._replay is not None:
+            for _ in range(int(n_steps)):
+                self.engine.step(1)
+                self._log_replay()
+            self.engine.retrieve(self._bufs)
         else:
             self.engine.step(int(n_steps))
             self.engine.retrieve(self._bufs)
         self._tick += int(n_steps)
         self._publish()
+
+    def _log_replay(self):
+        self._replay.log_step(self.engine.snapshot(self.view_replica), self._raw_now)
 
     def retrieve_step_measurements(self):
         """simulator.py:52-62."""

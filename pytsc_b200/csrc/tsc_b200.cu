@@ -73,6 +73,7 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     const u32 *sig_phase_mask;
     const int *sig_n_raw;            // [A] raw light phases per signal
     const int *route_seq, *veh_tick, *veh_seq_start, *veh_tmpl, *veh_priority;
+    const int4 *spawn_rec;           // [N] in lane_spawn_vid order: {vehicle, creation tick, route cursor, second drivable}
     const double *tmpl;
     const int *created_cnt;          // [F][horizon+2] vehicles of flow set f created before tick t
     const long long *created_enter;  // [F][horizon+2] sum of their creation ticks
@@ -127,9 +128,9 @@ struct Layout {
     int Vcap;              // vehicle slots (running vehicles + holes)
     int Vlay;              // slots the columns are laid out for (>= Vcap: the retrieve scratch lives in a pos/spd pair)
     int ent_cap;           // vehicles that may change drivable in one tick
+    int wl_cap;            // entries of a warp's private head-vehicle list
     int async_stage;       // 1: cp.async staging of the image columns (TSC_B200_ASYNC_STAGE)
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
-    int cross_group;       // lanes per vehicle in the cross phase: 32, 16, 8, 4, 2, or 0 = chosen per tick from the list length
     // persistent part: identical byte offsets in the HBM image and in the working set
     int o_cnt, o_head, o_tail, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
     int o_pos, o_spd, o_rpos, o_vid, o_lead, o_foll, o_drv, o_pj, o_blk;
@@ -180,11 +181,13 @@ __device__ __forceinline__ int trunc_int_x86(double x) {
 struct Ctx {
     RepHeader *h;
     // per drivable: vehicle count and the ends of its list (front = head, back = tail)
-    u16 *cnt, *head, *tail, *wq, *leave, *ent;
+    u16 *cnt, *head, *tail, *wq;
+    u8 *leave, *ent;      // per drivable: vehicles leaving / entering this tick (bytes, counted four to an atomic word)
     // per vehicle slot.  Slots are STABLE: a vehicle keeps its slot from spawn to finish; order on a drivable is
     // the doubly linked list lead (vehicle ahead) / foll (vehicle behind).
     u16 *lead, *foll;
-    u16 *xlist, *alist;   // per-tick work lists (heads / cross phase share one, intersection zone the other)
+    u16 *xlist;           // the warps' private head-vehicle lists (wl_cap entries each); the slot map of a compaction
+    u16 *clist;           // the block's list of vehicles that go through the cross phase this tick
     u16 *mv_slot, *mv_to; // this tick's movers: slot, new drivable (NONE16 = route ends)
     int *mv_q;            // ... new route cursor
     u8 *mv_pj;            // ... skipped a whole drivable
@@ -193,7 +196,9 @@ struct Ctx {
     const double *tmpl;   // vehicle templates (shared-memory copy when they fit)
     u8 *sraw, *scur, *schg, *pj, *fresh;
     int *stop, *rpos, *vid, *ellt, *scan;
-    int *sp_lane, *sp_vid, *sp_tick;   // head of every spawn lane's waiting buffer
+    int *sp_lane;                      // [S] the spawn lanes
+    int *sp_rec;                       // [S] int4: head of every spawn lane's waiting buffer (vehicle, creation tick, route cursor, second drivable)
+    int *sp_base;                      // [2S] this replica's flow set: first / one-past-last spawn record of every spawn lane
     const int *lso;                    // this replica's flow set: row of lane_spawn_off
     // kinematics ping-pong: every tick reads pos / spd / blk and writes npos / nspd / nblk, then they swap
     short *blk, *nblk;
@@ -441,8 +446,8 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
     c.npos[i] = nx; c.nspd[i] = ns; c.nblk[i] = (short) blocker;
     if (hops > 0 || end) {           // leaves its drivable: the list surgery at the end of the tick moves it
         c.pj[i] |= PJ_MOVER;
-        atomicAdd((unsigned *) &c.leave[d & ~1], (d & 1) ? 0x10000u : 1u);
-        if (!end) atomicAdd((unsigned *) &c.ent[dd & ~1], (dd & 1) ? 0x10000u : 1u);
+        atomicAdd((unsigned *) (c.leave + (d & ~3)), 1u << (8 * (d & 3)));
+        if (!end) atomicAdd((unsigned *) (c.ent + (dd & ~3)), 1u << (8 * (dd & 3)));
         const int k = atomicAdd(&c.h->n_ent, 1);
         if (k < Y.ent_cap) {
             c.mv_slot[k] = (u16) i; c.mv_to[k] = end ? (u16) NONE16 : (u16) dd; c.mv_q[k] = q; c.mv_pj[k] = hops > 1 ? 1 : 0;
@@ -554,34 +559,27 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
     const int n_old = c.h->n_slots;
 
     // ---- handleWaiting: at most one vehicle per lane leaves its waiting buffer.  The head of every
-    //      buffer (lane, vehicle, creation tick) is cached in the working set, so a tick without an arrival
-    //      costs one compare per spawn lane.  The first warp serves the spawn lanes 32 at a time: a new
-    //      vehicle's slot is n_slots + its rank among the lanes that spawn (ballot), so slot numbers do
-    //      not depend on thread timing.  Meanwhile every thread lists the head vehicles (no vehicle ahead on
-    //      their drivable) for sub-phase 1a.
-    //      getAction is split so that every sub-phase runs the same code in all its lanes:
-    //      1a  head vehicles: look-ahead leader + gap
-    //      1b  every vehicle: car following; vehicles in an intersection zone go on a list
-    //      1c  listed vehicles: red light / blocked exit / turn speed; those that must examine
-    //          the crosses of a lane-link go on a second list
-    //      2   a group of lanes per vehicle of the second list, one lane per cross ----
-    u16 *hlist = c.xlist;      // dead before 1c fills xlist
-    u16 *alist = c.alist;
+    //      buffer (vehicle, creation tick, route cursor, second drivable) is cached in the working set, so a
+    //      tick without an arrival costs one compare per spawn lane and an arrival needs no table look-up
+    //      before the vehicle is in place; the cache is refilled with ONE 16-byte load whose latency the rest
+    //      of the work hides.  The first warp serves the spawn lanes 32 at a time: a new vehicle's slot is
+    //      n_slots + its rank among the lanes that spawn (ballot), so slot numbers do not depend on timing. ----
     if (tid < 32) {
         int base = n_old, spawned = 0;
         for (int s0 = 0; s0 < S.n_spawn_lanes; s0 += 32) {
             const int s = s0 + tid;
             bool want = false;
-            int l = 0, v = 0, n = 0;
+            int l = 0, n = 0;
+            int4 rec = make_int4(0, INT_MAX, 0, 0);      // vehicle, creation tick, route cursor, second drivable
             if (s < S.n_spawn_lanes) {
                 l = c.sp_lane[s];
-                if (c.sp_tick[s] <= tick) {
-                    v = c.sp_vid[s];
+                rec = ((const int4 *) c.sp_rec)[s];
+                if (rec.y <= tick) {
                     n = c.cnt[l];
                     want = true;
                     if (n > 0) {
                         const int t = c.tail[l];
-                        want = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, v)[TSC_T_MIN_GAP];
+                        want = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + tmpl_of<ONE_T>(S, c, rec.x)[TSC_T_MIN_GAP];
                     }
                 }
             }
@@ -589,25 +587,23 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
             const int slot = base + __popc(m & ((1u << tid) - 1u));
             if (want && slot >= Y.Vcap) { atomicOr(&c.h->err, ERR_OVERFLOW); want = false; }
             if (want) {
-                const int rp0 = __ldg(S.veh_seq_start + v);
+                const int hd = c.wq[s] + 1;
+                const int at = c.sp_base[s] + hd;
+                int4 nxt = make_int4(-1, INT_MAX, 0, 0);
+                if (at < c.sp_base[s + S.n_spawn_lanes]) nxt = __ldg(S.spawn_rec + at);      // issued now, needed last
                 c.pos[slot] = 0.0; c.spd[slot] = 0.0;
-                c.rpos[slot] = rp0;
-                c.vid[slot] = v; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
-                c.dn[slot] = (u32) l | ((u32) (__ldg(S.route_seq + rp0 + 1) & 0xFFFF) << 16);
+                c.rpos[slot] = rec.z;
+                c.vid[slot] = rec.x; c.ellt[slot] = INT_MAX; c.blk[slot] = -1;
+                c.dn[slot] = (u32) l | ((u32) (rec.w & 0xFFFF) << 16);
                 c.pj[slot] = 0;
                 c.foll[slot] = (u16) NONE16;
                 if (n > 0) { const int t = c.tail[l]; c.lead[slot] = (u16) t; c.foll[t] = (u16) slot; }
-                else { c.lead[slot] = (u16) NONE16; c.head[l] = (u16) slot; hlist[atomicAdd(&c.h->n_h, 1)] = (u16) slot; }
+                else { c.lead[slot] = (u16) NONE16; c.head[l] = (u16) slot; }
                 c.tail[l] = (u16) slot;
                 c.cnt[l] = (u16) (n + 1);
-                const int hd = c.wq[s] + 1;
                 c.wq[s] = (u16) hd;
-                const int at = __ldg(c.lso + l) + hd;
-                if (at < __ldg(c.lso + l + 1)) {
-                    const int nv = __ldg(S.lane_spawn_vid + at);
-                    c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
-                } else c.sp_tick[s] = INT_MAX;
                 ++spawned;
+                ((int4 *) c.sp_rec)[s] = nxt;
             }
             if (s < S.n_spawn_lanes) c.fresh[l] = want ? 1 : 0;
             base += __popc(m);
@@ -616,155 +612,163 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         for (int o = 16; o > 0; o >>= 1) spawned += __shfl_xor_sync(0xffffffffu, spawned, o);
         if (tid == 0) { c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned; }
     }
-    for (int i = tid; i < n_old; i += NT)      // the heads among the vehicles that were here before this tick
-        if (c.vid[i] >= 0 && c.lead[i] == NONE16) hlist[warp_append(&c.h->n_h)] = (u16) i;
     __syncthreads();
     pt_mark(c, PT_SPAWN);
     const int n_slots = c.h->n_new;
 
-    // 1a: leader and gap of head vehicles as of the end of the previous tick (A.7): vehicles that
-    // entered from the waiting buffer this tick are not yet visible to others
-    for (int e = tid, n_h = c.h->n_h; e < n_h; e += NT) {
-        const int i = hlist[e];
-        const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
-        const u32 dnv = c.dn[i];
-        const int d = dnv & 0xFFFF;
-        const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
-        const int rp = c.rpos[i];
-        int leader = -1;
-        double gap = 0.0;
-        double dist = __ldg(S.drv_length + d) - c.pos[i];
-        const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
-        for (int j = 1;; ++j) {
-            int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
-            if (nd < 0) break;
-            if (nd >= L) {
-                const int sl = (j == 1 && d < L) ? d : __ldg(&S.llinfo[nd - L].start_lane);   // the link after lane d starts at d
-                // all lane-links leaving that lane, in roadnet order: one packed load for up to three of them
-                const int4 sib = __ldg(S.lane_sib + sl);
-                auto consider = [&](int dl) {
-                    if (c.cnt[dl] > 0) {
-                        int cand = c.tail[dl];
-                        double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
-                        if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
+    // ---- getAction.  Every decision reads only the state the tick started from (positions, lists, blockers) and
+    //      writes the vehicle's own entries of the next-state buffers, so the whole of it runs without a block-wide
+    //      barrier: each WARP owns the slots of its 32-slot chunks and takes them through
+    //        a  head vehicles (no vehicle ahead on their drivable), gathered warp-locally: look-ahead leader + gap (A.7)
+    //        b  every vehicle, a lane each: car following (A.4); red light / blocked exit / turn speed (A.5 i-ii)
+    //      and commits them (finish_vehicle); the few vehicles that must examine the crosses of a lane-link (A.5 iii) are
+    //      listed for the cross phase, which spreads each of them over a group of lanes. ----
+    {
+        const int lane = tid & 31, w = tid >> 5, NW = NT / 32;
+        const unsigned lt = (1u << lane) - 1u;
+        const int n_chunks = (n_slots + 31) >> 5;
+        // a: this warp's head vehicles
+        u16 *wl = c.xlist + w * Y.wl_cap;
+        int nh = 0;
+        for (int ch = w; ch < n_chunks; ch += NW) {
+            const int i = (ch << 5) + lane;
+            const bool hd = i < n_slots && c.vid[i] >= 0 && c.lead[i] == NONE16;
+            const unsigned m = __ballot_sync(0xffffffffu, hd);
+            if (hd) wl[nh + __popc(m & lt)] = (u16) i;
+            nh += __popc(m);
+        }
+        __syncwarp();
+        for (int e = lane; e < nh; e += 32) {
+            const int i = wl[e];
+            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
+            const u32 dnv = c.dn[i];
+            const int d = dnv & 0xFFFF;
+            const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
+            const int rp = c.rpos[i];
+            int leader = -1;
+            double gap = 0.0;
+            double dist = __ldg(S.drv_length + d) - c.pos[i];
+            const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
+            for (int j = 1;; ++j) {
+                int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
+                if (nd < 0) break;
+                if (nd >= L) {
+                    const int sl = (j == 1 && d < L) ? d : __ldg(&S.llinfo[nd - L].start_lane);   // the link after lane d starts at d
+                    // all lane-links leaving that lane, in roadnet order: one packed load for up to three of them
+                    const int4 sib = __ldg(S.lane_sib + sl);
+                    auto consider = [&](int dl) {
+                        if (c.cnt[dl] > 0) {
+                            int cand = c.tail[dl];
+                            double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
+                            if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
+                        }
+                    };
+                    if (sib.x >= 0) {
+                        if (sib.x > 0) consider(sib.y);
+                        if (sib.x > 1) consider(sib.z);
+                        if (sib.x > 2) consider(sib.w);
+                    } else {
+                        int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
+                        for (int q = e0; q < e1; ++q) consider(L + __ldg(S.lane_ll + q));
                     }
-                };
-                if (sib.x >= 0) {
-                    if (sib.x > 0) consider(sib.y);
-                    if (sib.x > 1) consider(sib.z);
-                    if (sib.x > 2) consider(sib.w);
+                    if (leader >= 0) break;
                 } else {
-                    int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
-                    for (int q = e0; q < e1; ++q) consider(L + __ldg(S.lane_ll + q));
+                    const int n = c.cnt[nd] - c.fresh[nd];
+                    if (n > 0) {      // the lane's last vehicle, not counting one that left the waiting buffer this tick
+                        int t = c.tail[nd];
+                        if (c.fresh[nd]) t = c.lead[t];
+                        leader = t;
+                        gap = dist + c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN];
+                        break;
+                    }
                 }
-                if (leader >= 0) break;
-            } else {
-                const int n = c.cnt[nd] - c.fresh[nd];
-                if (n > 0) {      // the lane's last vehicle, not counting one that left the waiting buffer this tick
-                    int t = c.tail[nd];
-                    if (c.fresh[nd]) t = c.lead[t];
-                    leader = t;
-                    gap = dist + c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN];
-                    break;
+                dist += __ldg(S.drv_length + nd);
+                if (dist > horizon) break;
+            }
+            c.nblk[i] = (short) leader; c.npos[i] = gap;
+        }
+        __syncwarp();
+        // b, c: chunk by chunk
+        for (int ch = w; ch < n_chunks; ch += NW) {
+            const int i = (ch << 5) + lane;
+            const bool valid = i < n_slots && c.vid[i] >= 0;
+            const double *T = c.tmpl;
+            u32 dnv = 0;
+            int d = 0;
+            double x = 0.0, v = 0.0, dlen = 0.0, ns = 0.0, vi = 0.0;
+            bool zone = false, needx = false;
+            if (valid) {
+                T = tmpl_of<ONE_T>(S, c, c.vid[i]);
+                dnv = c.dn[i];
+                d = dnv & 0xFFFF;
+                const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
+                x = c.pos[i]; v = c.spd[i];
+                const double2 lm = __ldg(S.drv_lm + d);       // length, speed limit: one 16-byte load
+                dlen = lm.x;
+                int leader = c.lead[i];
+                double gap;
+                if (leader != (int) NONE16) gap = c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN] - x;
+                else { leader = c.nblk[i]; gap = c.npos[i]; }
+                ns = T[TSC_T_MAX_SPEED];
+                ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
+                ns = min2(ns, lm.y);
+                double cf = T[TSC_T_MAX_SPEED];
+                if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
+                ns = min2(ns, cf);
+                zone = d >= L || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST]);   // intersection related speed applies (A.5)
+                if (zone) {
+                    vi = T[TSC_T_MAX_SPEED];
+                    needx = true;
+                    if (d < L) {
+                        const int ll = nd1 - L;
+                        const int el = __ldg(&S.llinfo[ll].end_lane);
+                        bool enter = true;
+                        if (c.cnt[el] > 0) {
+                            int t = c.tail[el];
+                            enter = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
+                        }
+                        if (!ll_available(c, ll) || !enter) {
+                            if (DIV_POS_HOT(0.5 * v * v, T[TSC_T_MAX_NEG_ACC]) > dlen - x) {
+                                // cannot stop before the line any more
+                            } else {
+                                vi = min2(vi, stop_before_speed(T, v, dlen - x));
+                                needx = false;      // stops at the line: the crosses are not examined
+                            }
+                        }
+                        if (needx && __ldg(&S.llinfo[ll].type) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
+                    }
                 }
             }
-            dist += __ldg(S.drv_length + nd);
-            if (dist > horizon) break;
+            // vehicles that must examine the crosses of a lane-link (A.5 iii) go on the block's list: one ballot and
+            // one atomic per warp; their car-following speed and the speed limit found so far wait in the next-state buffers
+            const unsigned mx = __ballot_sync(0xffffffffu, needx);
+            if (mx) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&c.h->n_x, __popc(mx));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (needx) { c.clist[base + __popc(mx & lt)] = (u16) i; c.nspd[i] = ns; c.npos[i] = vi; }
+            }
+            if (valid && !needx) {
+                if (zone) ns = min2(ns, vi);
+                finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
+            }
         }
-        c.nblk[i] = (short) leader; c.npos[i] = gap;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (c.pt) atomicAdd(c.pt + PT_NH, (unsigned long long) c.h->n_h);
-        c.h->n_h = 0;       // every thread has read it
-    }
-    pt_mark(c, PT_PHASE1A);
-
-    // 1b: next speed from acceleration, speed limits and the car-following law (A.4)
-    for (int i = tid; i < n_slots; i += NT) {
-        int vid = c.vid[i];
-        if (vid < 0) continue;
-        const double *T = tmpl_of<ONE_T>(S, c, vid);
-        const u32 dnv = c.dn[i];
-        const int d = dnv & 0xFFFF;
-        const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
-        const double x = c.pos[i], v = c.spd[i];
-        const double2 lm = __ldg(S.drv_lm + d);       // length, speed limit: one 16-byte load
-        const double dlen = lm.x;
-        int leader = c.lead[i];
-        double gap;
-        if (leader != (int) NONE16) gap = c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN] - x;
-        else { leader = c.nblk[i]; gap = c.npos[i]; }
-        double ns = T[TSC_T_MAX_SPEED];
-        ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
-        ns = min2(ns, lm.y);
-        double cf = T[TSC_T_MAX_SPEED];
-        if (leader >= 0) cf = car_follow_speed(T, v, gap, c.spd[leader], tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_MAX_NEG_ACC]);
-        ns = min2(ns, cf);
-        if (d >= L || (nd1 >= L && dlen - x <= T[TSC_T_APPROACH_DIST])) {   // intersection related speed applies (A.5)
-            c.nspd[i] = ns;
-            alist[warp_append(&c.h->n_a)] = (u16) i;
-            continue;
-        }
-        finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
     }
     __syncthreads();
     pt_mark(c, PT_PHASE1);
 
-    // 1c: intersection related speed, part (i)-(ii) of A.5
-    for (int e = tid, n_a = c.h->n_a; e < n_a; e += NT) {
-        const int i = alist[e];
-        const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
-        const u32 dnv = c.dn[i];
-        const int d = dnv & 0xFFFF;
-        const double x = c.pos[i], v = c.spd[i];
-        const double dlen = __ldg(S.drv_length + d);
-        double ns = c.nspd[i];
-        double vi = T[TSC_T_MAX_SPEED];
-        bool done = false;
-        if (d < L) {
-            const int ll = (int) (dnv >> 16) - L;
-            const int el = __ldg(&S.llinfo[ll].end_lane);
-            bool enter = true;
-            if (c.cnt[el] > 0) {
-                int t = c.tail[el];
-                enter = c.pos[t] > tmpl_of<ONE_T>(S, c, c.vid[t])[TSC_T_LEN] + T[TSC_T_LEN] || c.spd[t] >= 2;
-            }
-            if (!ll_available(c, ll) || !enter) {
-                if (DIV_POS_HOT(0.5 * v * v, T[TSC_T_MAX_NEG_ACC]) > dlen - x) {
-                    // cannot stop before the line any more
-                } else {
-                    vi = min2(vi, stop_before_speed(T, v, dlen - x));
-                    done = true;
-                }
-            }
-            if (!done && __ldg(&S.llinfo[ll].type) != 3) vi = min2(vi, T[TSC_T_TURN_SPEED]);
-        }
-        if (!done) {   // phase 2 examines the crosses of the lane-link
-            c.npos[i] = vi;
-            c.xlist[warp_append(&c.h->n_x)] = (u16) i;
-            continue;
-        }
-        ns = min2(ns, vi);
-        finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, -1);
-    }
-    __syncthreads();
-    if (c.pt && tid == 0) { atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x); atomicAdd(c.pt + PT_NA, (unsigned long long) c.h->n_a); }
-    pt_mark(c, PT_PHASE1C);
-
-    // ---- getAction, phase 2: Cross::canPass for every cross ahead of every deferred vehicle.  canPass
-    //      has no side effects, so all crosses are evaluated at once and the first refusal in link order
-    //      is the sequential scan of A.5(iii): a group of G lanes (a whole warp, or a half / quarter of one:
-    //      links rarely have more than a dozen crosses) per vehicle, one lane per cross; cross_group = 0
-    //      (default): the widest group that still gives every listed vehicle its own group in one round ----
+    // ---- getAction, cross phase: Cross::canPass for every cross ahead of every listed vehicle.  canPass has no side
+    //      effects, so all crosses are evaluated at once and the first refusal in link order is the sequential scan of
+    //      A.5(iii): a group of G lanes (half / quarter / eighth of a warp: links rarely have more than a dozen crosses)
+    //      per vehicle, one lane per cross, all listed vehicles at once; G = the widest group that still gives every
+    //      listed vehicle its own group in one round ----
     {
         const int n_x = c.h->n_x;
-        int G = Y.cross_group;
-        if (G == 0) G = n_x * 16 <= NT ? 16 : (n_x * 8 <= NT ? 8 : (n_x * 4 <= NT ? 4 : 2));
+        const int G = n_x * 16 <= NT ? 16 : (n_x * 8 <= NT ? 8 : (n_x * 4 <= NT ? 4 : 2));
         const int lane = tid & 31, sl = lane & (G - 1);
-        const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
+        const unsigned gm = ((1u << G) - 1u) << (lane & ~(G - 1));
         for (int e = tid / G; e < n_x; e += NT / G) {
-            const int i = c.xlist[e];
+            const int i = c.clist[e];
             const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
             const u32 dnv = c.dn[i];
             const int d = dnv & 0xFFFF;
@@ -805,6 +809,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         }
     }
     __syncthreads();
+    if (c.pt && tid == 0) atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x);
     pt_mark(c, PT_PHASE2);
 
     // ---- updateLocation.  Slots are stable, so there is nothing to re-pack: every vehicle's next state is
@@ -1461,13 +1466,13 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     c.sraw = smem + Y.o_sraw; c.scur = smem + Y.o_scur; c.schg = smem + Y.o_schg; c.stop = (int *) (smem + Y.o_stop);
     c.rpos = (int *) (smem + Y.o_rpos); c.vid = (int *) (smem + Y.o_vid);
     c.lead = (u16 *) (smem + Y.o_lead); c.foll = (u16 *) (smem + Y.o_foll); c.pj = smem + Y.o_pj;
-    c.alist = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
     c.dn = (u32 *) (smem + Y.o_dn); c.xlist = (u16 *) (smem + Y.o_xlist);
-    c.leave = (u16 *) (smem + Y.o_leave); c.ent = (u16 *) (smem + Y.o_ent); c.fresh = smem + Y.o_fresh;
+    c.clist = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
+    c.leave = smem + Y.o_leave; c.ent = smem + Y.o_ent; c.fresh = smem + Y.o_fresh;
     c.mv_slot = (u16 *) (smem + Y.o_mvslot); c.mv_to = (u16 *) (smem + Y.o_mvto); c.mv_q = (int *) (smem + Y.o_mvq); c.mv_pj = smem + Y.o_mvpj;
     c.scan = (int *) (smem + Y.o_scan);
     c.avail = (u32 *) (smem + Y.o_avail);
-    c.sp_lane = (int *) (smem + Y.o_spawn); c.sp_vid = c.sp_lane + S.n_spawn_lanes; c.sp_tick = c.sp_vid + S.n_spawn_lanes;
+    c.sp_rec = (int *) (smem + Y.o_spawn); c.sp_lane = c.sp_rec + 4 * S.n_spawn_lanes; c.sp_base = c.sp_lane + S.n_spawn_lanes;
     for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
     if (ONE_T || S.T <= SMEM_TEMPLATES) {
         double *ts = (double *) (smem + Y.o_tmpl);
@@ -1516,13 +1521,12 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             for (int k = tid; k < nz; k += NT) z[k] = make_int4(0, 0, 0, 0);
         }
         if (tid == 0) { c.h->n_ent = 0; c.h->n_x = 0; c.h->n_h = 0; c.h->n_a = 0; c.h->n_new = n_in; }
-        for (int s = tid; s < S.n_spawn_lanes; s += NT) {
+        for (int s = tid; s < S.n_spawn_lanes; s += NT) {      // the head of every waiting buffer, in this replica's flow set
             const int l = __ldg(S.spawn_lane + s);
-            const int at = __ldg(c.lso + l) + c.wq[s];
-            if (at < __ldg(c.lso + l + 1)) {
-                const int nv = __ldg(S.lane_spawn_vid + at);
-                c.sp_vid[s] = nv; c.sp_tick[s] = __ldg(S.veh_tick + nv);
-            } else { c.sp_vid[s] = -1; c.sp_tick[s] = INT_MAX; }
+            const int b0 = __ldg(c.lso + l), b1 = __ldg(c.lso + l + 1);
+            c.sp_base[s] = b0; c.sp_base[s + S.n_spawn_lanes] = b1;
+            const int at = b0 + c.wq[s];
+            ((int4 *) c.sp_rec)[s] = at < b1 ? __ldg(S.spawn_rec + at) : make_int4(-1, INT_MAX, 0, 0);
         }
         if (!GMEM && Y.async_stage) copy16_async_wait();      // this thread's requests; the barrier publishes everybody's
         __syncthreads();
@@ -1677,7 +1681,10 @@ static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool one_t, bool gme
     if (!one_t) return nt >= 512 ? tsc_step_kernel<512, 1, true, false, false> : tsc_step_kernel<256, 2, true, false, false>;
     if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true>;      // 32 warps at 64 registers
     if (nt == 512) return tsc_step_kernel<512, 1, true, false, true>;
+    if (nt == 160) return ctl ? tsc_step_kernel<160, 5, true, false, true> : tsc_step_kernel<160, 5, false, false, true>;
+    if (nt == 192 && minb >= 5) return ctl ? tsc_step_kernel<192, 5, true, false, true> : tsc_step_kernel<192, 5, false, false, true>;
     if (nt == 192) return ctl ? tsc_step_kernel<192, 4, true, false, true> : tsc_step_kernel<192, 4, false, false, true>;
+    if (nt == 256 && minb >= 4) return ctl ? tsc_step_kernel<256, 4, true, false, true> : tsc_step_kernel<256, 4, false, false, true>;
     if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, true> : tsc_step_kernel<256, 2, true, false, true>;
     return minb >= 3 ? tsc_step_kernel<256, 3, false, false, true> : tsc_step_kernel<256, 2, false, false, true>;
 }
@@ -1864,12 +1871,12 @@ static int upload(tsc_engine *E, const Tp *host, size_t n, const Tp **dev) {
 
 static int align16(int x) { return (x + 15) & ~15; }
 
-static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
+static void build_layout(Layout &Y, const DevScn &S, int Vcap, int n_warps) {
     Y.Vcap = Vcap;
     // vehicles changing drivable in one tick (a lane hands over at most one or two per tick; the shipped
-    // workloads stay far below a tenth of the running vehicles): a quarter of the slots, overflow is
+    // workloads stay below a twentieth of the running vehicles): an eighth of the slots, overflow is
     // reported (ERR_ENT_OVERFLOW)
-    Y.ent_cap = Vcap / 4 < 64 ? 64 : (Vcap / 4 > 8192 ? 8192 : Vcap / 4);
+    Y.ent_cap = Vcap / 8 < 64 ? 64 : (Vcap / 8 > 8192 ? 8192 : Vcap / 8);
     // between ticks the next-state kinematics pair (16 bytes per slot, contiguous) is the scratch of retrieve /
     // the controllers: lane sums, per-signal terms, then the position-matrix windows or the host packet
     const int tailb = S.obs_type == TSC_OBS_POSITION_MATRIX ? std::max(S.n_in_total * S.visibility * 8, S.pk_bytes) : S.pk_bytes;
@@ -1906,9 +1913,10 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.o_npos = o; o = o + 8 * Vlay;             // npos | nspd contiguous
     Y.o_nspd = o; o = align16(o + 8 * Vlay);
     Y.o_nblk = o; o = align16(o + 2 * Vcap);
-    Y.o_xlist = o; o = align16(o + 2 * Vcap);
-    Y.o_leave = o; o = align16(o + 2 * (S.D + 2));      // leave | ent | fresh adjacent: zeroed together at stage-in
-    Y.o_ent = o; o = align16(o + 2 * (S.D + 2));
+    Y.wl_cap = (((Vcap + 31) / 32 + n_warps - 1) / n_warps) * 32;      // a warp owns every n_warps-th chunk of 32 slots
+    Y.o_xlist = o; o = align16(o + 2 * std::max(Vcap, n_warps * Y.wl_cap));
+    Y.o_leave = o; o = align16(o + S.D + 4);      // leave | ent | fresh adjacent: zeroed together at stage-in
+    Y.o_ent = o; o = align16(o + S.D + 4);
     Y.o_fresh = o; o = align16(o + S.L);
     Y.o_mvslot = o; o = align16(o + 2 * Y.ent_cap);
     Y.o_mvto = o; o = align16(o + 2 * Y.ent_cap);
@@ -1917,7 +1925,7 @@ static void build_layout(Layout &Y, const DevScn &S, int Vcap) {
     Y.o_scan = o; o = align16(o + 4 * 64);
     Y.o_avail = o; o = align16(o + 4 * ((S.K + 31) / 32 + 1));
     Y.o_tmpl = o; o = align16(o + 8 * TD_STRIDE * (S.T < SMEM_TEMPLATES ? S.T : SMEM_TEMPLATES));
-    Y.o_spawn = o; o = align16(o + 12 * (S.n_spawn_lanes + 1));
+    Y.o_spawn = o; o = align16(o + 28 * (S.n_spawn_lanes + 1));      // 16-byte records first, then the lanes and the record ranges
     Y.smem_bytes = o;
 }
 
@@ -2156,6 +2164,16 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     }
     if ((rc = upload(E, ccnt.data(), ccnt.size(), &S.created_cnt))) return rc;
     if ((rc = upload(E, cent.data(), cent.size(), &S.created_enter))) return rc;
+    {   // one 16-byte record per spawn-list entry: what handleWaiting needs to put the vehicle on its first lane
+        std::vector<int4> rec(N > 0 ? N : 1, make_int4(-1, INT_MAX, 0, 0));
+        for (int at = 0; at < s->lane_spawn_off[(size_t) S.F * (L + 1) - 1]; ++at) {
+            const int v = s->lane_spawn_vid[at];
+            const int rp0 = s->veh_seq_start[v];
+            if (rp0 < 1 || rp0 + 1 >= s->n_route_seq) return fail(TSC_EINVAL, "vehicle %d: route cursor out of range", v);
+            rec[at] = make_int4(v, s->veh_tick[v], rp0, s->route_seq[rp0 + 1] & 0xFFFF);
+        }
+        if ((rc = upload(E, rec.data(), rec.size(), &S.spawn_rec))) return rc;
+    }
     E->h_route_seq.assign(s->route_seq, s->route_seq + s->n_route_seq);
     E->h_veh_seq_start.assign(s->veh_seq_start, s->veh_seq_start + N);
 
@@ -2165,31 +2183,41 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     if (Vcap > 32767) { return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    build_layout(E->Y, S, Vcap);
-    E->Y.cross_group = 0;      // adaptive (measured on the bench workload: 32 / 16 / 8 lanes per vehicle 1.059 / 1.000 / 0.971 ms, adaptive 0.923)
-    if (const char *env = getenv("TSC_B200_CROSS_GROUP")) { int v = atoi(env); if (v == 0 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) E->Y.cross_group = v; }
-    E->Y.async_stage = 1;
-    if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) E->Y.async_stage = atoi(env) != 0;
-    E->Y.prefetch_next = 1;
-    if (const char *env = getenv("TSC_B200_PREFETCH")) E->Y.prefetch_next = atoi(env) != 0;
+    int async_stage = 1, prefetch_next = 1;
+    if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) async_stage = atoi(env) != 0;
+    if (const char *env = getenv("TSC_B200_PREFETCH")) prefetch_next = atoi(env) != 0;
     // Pick the variant from how many working sets fit an SM's shared memory (the register budget follows from the
-    // launch bounds).  Measured on B200 (Hangzhou, B = 4096): four 192-thread blocks beat three 256-thread ones, which
-    // beat four blocks at 64 registers and two 512-thread blocks.  TSC_B200_THREADS / TSC_B200_MIN_BLOCKS / TSC_B200_GMEM override.
+    // launch bounds): the first of (192 threads x 4 blocks per SM), (256 x 3), (256 x 2), (512 x 1) that fits, else the
+    // global-memory workspace.  Measured on B200 (Hangzhou, B = 4096): four 192-thread blocks beat three 256-thread
+    // ones, which beat four blocks at 64 registers and two 512-thread blocks.  TSC_B200_THREADS / TSC_B200_MIN_BLOCKS /
+    // TSC_B200_GMEM override.
     bool one_t = S.T == 1;
     if (const char *env = getenv("TSC_B200_ONE_TEMPLATE")) one_t = one_t && atoi(env) != 0;
     const size_t per_sm_bytes = prop.sharedMemPerMultiprocessor;
-    int fit = (int) (per_sm_bytes / (size_t) (E->Y.smem_bytes + 1024));
-    if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) fit = 0;
-    if (const char *env = getenv("TSC_B200_GMEM")) { if (atoi(env) != 0) fit = 0; }
-    int want_nt = 0;
-    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 192 || v == 256 || v == 512 || v == 1024) want_nt = v; }
-    if (fit == 0) { E->gmem = true; E->nt = 1024; E->minb = 1; }
-    else if (!one_t) { E->nt = fit >= 2 ? 256 : 512; E->minb = fit >= 2 ? 2 : 1; }
-    else if (fit >= 4 && (want_nt == 0 || want_nt == 192)) { E->nt = 192; E->minb = 4; }
-    else if (fit >= 2 && (want_nt == 0 || want_nt == 256 || want_nt == 192)) { E->nt = 256; E->minb = fit >= 3 ? 3 : 2; }
-    else { E->nt = want_nt == 1024 ? 1024 : 512; E->minb = 1; }
-    if (E->nt == 256)
-        if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 2 && v <= 3 && v <= fit) E->minb = v; }
+    int want_nt = 0, want_minb = 0;
+    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 160 || v == 192 || v == 256 || v == 512 || v == 1024) want_nt = v; }
+    if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 2 && v <= 5) want_minb = v; }
+    bool force_gmem = false;
+    if (const char *env = getenv("TSC_B200_GMEM")) force_gmem = atoi(env) != 0;
+    const int cand[8][2] = {{160, 5}, {192, 5}, {192, 4}, {256, 4}, {256, 3}, {256, 2}, {512, 1}, {1024, 1}};
+    bool chosen = false;
+    for (int k = 0; k < 8 && !force_gmem && !chosen; ++k) {
+        const int nt = cand[k][0], minb = cand[k][1];
+        if (want_nt && nt != want_nt) continue;
+        if (want_minb && (nt == 256 || nt == 192) && minb != want_minb) continue;
+        // on request only (TSC_B200_THREADS / TSC_B200_MIN_BLOCKS): 32 warps at 64 registers, five 160-thread blocks,
+        // five 192-thread or four 256-thread blocks at 64 registers
+        if (!want_nt && (nt == 1024 || nt == 160)) continue;
+        if (!want_minb && ((nt == 192 && minb == 5) || (nt == 256 && minb == 4))) continue;
+        if (!one_t && !((nt == 256 && minb == 2) || nt == 512)) continue;      // generic-template builds
+        if (nt == 160 && !one_t) continue;
+        build_layout(E->Y, S, Vcap, nt / 32);
+        if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) continue;
+        if ((int) (per_sm_bytes / (size_t) (E->Y.smem_bytes + 1024)) < minb) continue;
+        E->nt = nt; E->minb = minb; chosen = true;
+    }
+    if (!chosen) { E->gmem = true; E->nt = 1024; E->minb = 1; build_layout(E->Y, S, Vcap, 32); }
+    E->Y.async_stage = async_stage; E->Y.prefetch_next = prefetch_next;
     E->kern = kernel_for(E->nt, E->minb, false, one_t, E->gmem);
     E->kern_ctl = kernel_for(E->nt, E->minb, true, one_t, E->gmem);
     const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;

@@ -89,10 +89,6 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({}, 600, (192, 0, 4)),                                 # default at this size: four 192-thread blocks per SM
     ({"TSC_B200_THREADS": "256"}, 600, (256, 0, 3)),        # three 256-thread blocks per SM
     ({}, 1200, (256, 0, 2)),                                # larger replica: two 256-thread blocks per SM (128 registers)
-    ({"TSC_B200_CROSS_GROUP": "32"}, 600, (192, 0, 4)),     # a whole warp per vehicle in the cross phase
-    ({"TSC_B200_CROSS_GROUP": "16"}, 600, (192, 0, 4)),
-    ({"TSC_B200_CROSS_GROUP": "8"}, 600, (192, 0, 4)),
-    ({"TSC_B200_CROSS_GROUP": "2"}, 600, (192, 0, 4)),
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0, 2)),     # per-vehicle template look-up although the scenario has one template
     ({"TSC_B200_PREFETCH": "0"}, 600, (192, 0, 4)),
     ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (192, 0, 4)),      # plain vector copies instead of cp.async for staging

@@ -191,7 +191,9 @@ def test_graph_metrics_against_reference_metrics_parser(cuda_lib, scenario):
         net.step(acts)
         if t % 6 == 5:
             want, got = np.asarray(ref.metrics.density_map), np.asarray(net.metrics.density_map)
-            assert want.shape == got.shape and want.max() > 1e-3
+            assert want.shape == got.shape
+            if t == 59:
+                assert want.max() > 1e-3      # vehicles on the connecting roads by now: not just the 1e-6 adjacency term
             np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15)
             tw, tg = np.asarray(ref.metrics.mst), np.asarray(net.metrics.mst)
             sym = lambda m: np.triu(m + m.T - np.diag(np.diag(m)))
