@@ -62,6 +62,7 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     const CrossEntry *cross;
     int L, K, D, A, N, T, F, horizon, max_raw, P;
     int n_in_total, n_out_total, n_spawn_lanes;
+    int spawn_pure;                  // 1: no spawn lane is the end lane of a lane-link (handleWaiting and the look-ahead touch disjoint drivables)
     const double *drv_length, *drv_max_speed;
     const double2 *drv_lm;      // [D] (length, max speed) packed for the per-vehicle pass
     const int *lane_ll_off, *lane_ll, *lane_spawn_off, *lane_spawn_vid, *spawn_lane;
@@ -537,6 +538,60 @@ __device__ void compact_slots(const DevScn &S, const Layout &Y, Ctx &c) {
 // ----------------------------------------------------------------------------
 // One engine tick for the replica held in the working set (A.2)
 // ----------------------------------------------------------------------------
+// Leader and gap of a head vehicle (no vehicle ahead on its drivable) as of the end of the previous tick (A.7): the
+// last vehicle of the drivables ahead on its route, as far as it looks; vehicles that left a waiting buffer this tick
+// are not yet visible.
+template <bool ONE_T>
+__device__ __forceinline__ void head_look_ahead(const DevScn &S, const Ctx &c, int i, int *leader_out, double *gap_out) {
+    const int L = S.L;
+    const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
+    const u32 dnv = c.dn[i];
+    const int d = dnv & 0xFFFF;
+    const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
+    const int rp = c.rpos[i];
+    int leader = -1;
+    double gap = 0.0;
+    double dist = __ldg(S.drv_length + d) - c.pos[i];
+    const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
+    for (int j = 1;; ++j) {
+        int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
+        if (nd < 0) break;
+        if (nd >= L) {
+            const int sl = (j == 1 && d < L) ? d : __ldg(&S.llinfo[nd - L].start_lane);   // the link after lane d starts at d
+            // all lane-links leaving that lane, in roadnet order: one packed load for up to three of them
+            const int4 sib = __ldg(S.lane_sib + sl);
+            auto consider = [&](int dl) {
+                if (c.cnt[dl] > 0) {
+                    int cand = c.tail[dl];
+                    double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
+                    if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
+                }
+            };
+            if (sib.x >= 0) {
+                if (sib.x > 0) consider(sib.y);
+                if (sib.x > 1) consider(sib.z);
+                if (sib.x > 2) consider(sib.w);
+            } else {
+                int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
+                for (int q = e0; q < e1; ++q) consider(L + __ldg(S.lane_ll + q));
+            }
+            if (leader >= 0) break;
+        } else {
+            const int n = c.cnt[nd] - c.fresh[nd];
+            if (n > 0) {      // the lane's last vehicle, not counting one that left the waiting buffer this tick
+                int t = c.tail[nd];
+                if (c.fresh[nd]) t = c.lead[t];
+                leader = t;
+                gap = dist + c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN];
+                break;
+            }
+        }
+        dist += __ldg(S.drv_length + nd);
+        if (dist > horizon) break;
+    }
+    *leader_out = leader; *gap_out = gap;
+}
+
 template <int NT, bool ONE_T>
 __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
     const int tid = threadIdx.x;
@@ -612,27 +667,21 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         for (int o = 16; o > 0; o >>= 1) spawned += __shfl_xor_sync(0xffffffffu, spawned, o);
         if (tid == 0) { c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned; }
     }
-    __syncthreads();
-    pt_mark(c, PT_SPAWN);
-    const int n_slots = c.h->n_new;
-
-    // ---- getAction.  Every decision reads only the state the tick started from (positions, lists, blockers) and
-    //      writes the vehicle's own entries of the next-state buffers, so the whole of it runs without a block-wide
-    //      barrier: each WARP owns the slots of its 32-slot chunks and takes them through
-    //        a  head vehicles (no vehicle ahead on their drivable), gathered warp-locally: look-ahead leader + gap (A.7)
-    //        b  every vehicle, a lane each: car following (A.4); red light / blocked exit / turn speed (A.5 i-ii)
-    //      and commits them (finish_vehicle); the few vehicles that must examine the crosses of a lane-link (A.5 iii) are
-    //      listed for the cross phase, which spreads each of them over a group of lanes. ----
+    // ---- head vehicles (no vehicle ahead on their drivable) of the vehicles that were here before this tick, gathered
+    //      warp-locally: look-ahead leader + gap (A.7).  Each WARP owns the slots of its 32-slot chunks.  When no spawn
+    //      lane is fed by a lane-link (every shipped roadnet: vehicles start on roads that leave the network's rim), what
+    //      the look-ahead reads -- the drivables AHEAD of a vehicle -- is never a lane handleWaiting touches, so it runs
+    //      beside it; otherwise after a barrier. ----
+    if (!S.spawn_pure) __syncthreads();
     {
         const int lane = tid & 31, w = tid >> 5, NW = NT / 32;
         const unsigned lt = (1u << lane) - 1u;
-        const int n_chunks = (n_slots + 31) >> 5;
-        // a: this warp's head vehicles
+        const int n_chunks = (n_old + 31) >> 5;
         u16 *wl = c.xlist + w * Y.wl_cap;
         int nh = 0;
         for (int ch = w; ch < n_chunks; ch += NW) {
             const int i = (ch << 5) + lane;
-            const bool hd = i < n_slots && c.vid[i] >= 0 && c.lead[i] == NONE16;
+            const bool hd = i < n_old && c.vid[i] >= 0 && c.lead[i] == NONE16;
             const unsigned m = __ballot_sync(0xffffffffu, hd);
             if (hd) wl[nh + __popc(m & lt)] = (u16) i;
             nh += __popc(m);
@@ -640,55 +689,26 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         __syncwarp();
         for (int e = lane; e < nh; e += 32) {
             const int i = wl[e];
-            const double *T = tmpl_of<ONE_T>(S, c, c.vid[i]);
-            const u32 dnv = c.dn[i];
-            const int d = dnv & 0xFFFF;
-            const int nd1 = (dnv >> 16) == 0xFFFFu ? -1 : (int) (dnv >> 16);
-            const int rp = c.rpos[i];
-            int leader = -1;
-            double gap = 0.0;
-            double dist = __ldg(S.drv_length + d) - c.pos[i];
-            const double horizon = T[TSC_T_APPROACH_DIST];   // maxSpeed^2 / usualNegAcc / 2 + maxSpeed * interval * 2
-            for (int j = 1;; ++j) {
-                int nd = j == 1 ? nd1 : __ldg(S.route_seq + rp + j);
-                if (nd < 0) break;
-                if (nd >= L) {
-                    const int sl = (j == 1 && d < L) ? d : __ldg(&S.llinfo[nd - L].start_lane);   // the link after lane d starts at d
-                    // all lane-links leaving that lane, in roadnet order: one packed load for up to three of them
-                    const int4 sib = __ldg(S.lane_sib + sl);
-                    auto consider = [&](int dl) {
-                        if (c.cnt[dl] > 0) {
-                            int cand = c.tail[dl];
-                            double cg = dist + c.pos[cand] - tmpl_of<ONE_T>(S, c, c.vid[cand])[TSC_T_LEN];
-                            if (leader < 0 || cg < gap) { leader = cand; gap = cg; }
-                        }
-                    };
-                    if (sib.x >= 0) {
-                        if (sib.x > 0) consider(sib.y);
-                        if (sib.x > 1) consider(sib.z);
-                        if (sib.x > 2) consider(sib.w);
-                    } else {
-                        int e0 = __ldg(S.lane_ll_off + sl), e1 = __ldg(S.lane_ll_off + sl + 1);
-                        for (int q = e0; q < e1; ++q) consider(L + __ldg(S.lane_ll + q));
-                    }
-                    if (leader >= 0) break;
-                } else {
-                    const int n = c.cnt[nd] - c.fresh[nd];
-                    if (n > 0) {      // the lane's last vehicle, not counting one that left the waiting buffer this tick
-                        int t = c.tail[nd];
-                        if (c.fresh[nd]) t = c.lead[t];
-                        leader = t;
-                        gap = dist + c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN];
-                        break;
-                    }
-                }
-                dist += __ldg(S.drv_length + nd);
-                if (dist > horizon) break;
-            }
+            int leader;
+            double gap;
+            head_look_ahead<ONE_T>(S, c, i, &leader, &gap);
             c.nblk[i] = (short) leader; c.npos[i] = gap;
         }
-        __syncwarp();
-        // b, c: chunk by chunk
+    }
+    __syncthreads();
+    pt_mark(c, PT_SPAWN);
+    const int n_slots = c.h->n_new;
+
+    // ---- getAction.  Every decision reads only the state the tick started from (positions, lists, blockers) and
+    //      writes the vehicle's own entries of the next-state buffers, so the whole of it runs without a block-wide
+    //      barrier: every vehicle, a lane each: car following (A.4); red light / blocked exit / turn speed (A.5 i-ii);
+    //      then commit (finish_vehicle); the few vehicles that must examine the crosses of a lane-link (A.5 iii) are
+    //      listed for the cross phase, which spreads each of them over a group of lanes. ----
+    {
+        const int lane = tid & 31, w = tid >> 5, NW = NT / 32;
+        const unsigned lt = (1u << lane) - 1u;
+        const int n_chunks = (n_slots + 31) >> 5;
+        // (a vehicle that left a waiting buffer onto an empty lane this tick is a head too: its look-ahead runs here)
         for (int ch = w; ch < n_chunks; ch += NW) {
             const int i = (ch << 5) + lane;
             const bool valid = i < n_slots && c.vid[i] >= 0;
@@ -708,6 +728,7 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
                 int leader = c.lead[i];
                 double gap;
                 if (leader != (int) NONE16) gap = c.pos[leader] - tmpl_of<ONE_T>(S, c, c.vid[leader])[TSC_T_LEN] - x;
+                else if (i >= n_old) head_look_ahead<ONE_T>(S, c, i, &leader, &gap);
                 else { leader = c.nblk[i]; gap = c.npos[i]; }
                 ns = T[TSC_T_MAX_SPEED];
                 ns = min2(ns, v + T[TSC_T_MAX_POS_ACC] * dt);
@@ -1684,6 +1705,7 @@ static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool one_t, bool gme
     if (nt == 160) return ctl ? tsc_step_kernel<160, 5, true, false, true> : tsc_step_kernel<160, 5, false, false, true>;
     if (nt == 192 && minb >= 5) return ctl ? tsc_step_kernel<192, 5, true, false, true> : tsc_step_kernel<192, 5, false, false, true>;
     if (nt == 192) return ctl ? tsc_step_kernel<192, 4, true, false, true> : tsc_step_kernel<192, 4, false, false, true>;
+    if (nt == 384) return ctl ? tsc_step_kernel<384, 2, true, false, true> : tsc_step_kernel<384, 2, false, false, true>;
     if (nt == 256 && minb >= 4) return ctl ? tsc_step_kernel<256, 4, true, false, true> : tsc_step_kernel<256, 4, false, false, true>;
     if (ctl) return minb >= 3 ? tsc_step_kernel<256, 3, true, false, true> : tsc_step_kernel<256, 2, true, false, true>;
     return minb >= 3 ? tsc_step_kernel<256, 3, false, false, true> : tsc_step_kernel<256, 2, false, false, true>;
@@ -2139,6 +2161,9 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
         if (any) { E->h_spawn_lane.push_back(l); E->h_is_spawn[l] = 1; }
     }
     S.n_spawn_lanes = E->n_spawn_lanes = (int) E->h_spawn_lane.size();
+    S.spawn_pure = 1;
+    for (int k = 0; k < K; ++k) if (E->h_is_spawn[s->ll_end_lane[k]]) S.spawn_pure = 0;
+    if (const char *env = getenv("TSC_B200_SPAWN_OVERLAP")) { if (atoi(env) == 0) S.spawn_pure = 0; }
     if ((rc = upload(E, E->h_spawn_lane.data(), E->h_spawn_lane.size(), &S.spawn_lane))) return rc;
     {
         if (E->n_spawn_lanes > 32767) { return fail(TSC_EINVAL, "more than 32767 spawn lanes"); }
@@ -2187,28 +2212,28 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) async_stage = atoi(env) != 0;
     if (const char *env = getenv("TSC_B200_PREFETCH")) prefetch_next = atoi(env) != 0;
     // Pick the variant from how many working sets fit an SM's shared memory (the register budget follows from the
-    // launch bounds): the first of (192 threads x 4 blocks per SM), (256 x 3), (256 x 2), (512 x 1) that fits, else the
-    // global-memory workspace.  Measured on B200 (Hangzhou, B = 4096): four 192-thread blocks beat three 256-thread
-    // ones, which beat four blocks at 64 registers and two 512-thread blocks.  TSC_B200_THREADS / TSC_B200_MIN_BLOCKS /
-    // TSC_B200_GMEM override.
+    // launch bounds): the first of (256 threads x 4 blocks per SM, 64 registers), (192 x 4, 80), (256 x 3, 80), (384 x 2, 80),
+    // (256 x 2, 128), (512 x 1) that fits, else the global-memory workspace.  Measured on B200 with this kernel (Hangzhou,
+    // B = 4096, profiles/r02e_variant_sweep.txt): 256 x 4 0.749 ms, 192 x 5 (64 registers) 0.754, 192 x 4 0.769, 160 x 5
+    // 0.773, 256 x 3 0.859.  TSC_B200_THREADS / TSC_B200_MIN_BLOCKS / TSC_B200_GMEM override.
     bool one_t = S.T == 1;
     if (const char *env = getenv("TSC_B200_ONE_TEMPLATE")) one_t = one_t && atoi(env) != 0;
     const size_t per_sm_bytes = prop.sharedMemPerMultiprocessor;
     int want_nt = 0, want_minb = 0;
-    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 160 || v == 192 || v == 256 || v == 512 || v == 1024) want_nt = v; }
+    if (const char *env = getenv("TSC_B200_THREADS")) { int v = atoi(env); if (v == 160 || v == 192 || v == 256 || v == 384 || v == 512 || v == 1024) want_nt = v; }
     if (const char *env = getenv("TSC_B200_MIN_BLOCKS")) { int v = atoi(env); if (v >= 2 && v <= 5) want_minb = v; }
     bool force_gmem = false;
     if (const char *env = getenv("TSC_B200_GMEM")) force_gmem = atoi(env) != 0;
-    const int cand[8][2] = {{160, 5}, {192, 5}, {192, 4}, {256, 4}, {256, 3}, {256, 2}, {512, 1}, {1024, 1}};
+    const int cand[9][2] = {{160, 5}, {192, 5}, {256, 4}, {192, 4}, {256, 3}, {384, 2}, {256, 2}, {512, 1}, {1024, 1}};
     bool chosen = false;
-    for (int k = 0; k < 8 && !force_gmem && !chosen; ++k) {
+    for (int k = 0; k < 9 && !force_gmem && !chosen; ++k) {
         const int nt = cand[k][0], minb = cand[k][1];
         if (want_nt && nt != want_nt) continue;
         if (want_minb && (nt == 256 || nt == 192) && minb != want_minb) continue;
         // on request only (TSC_B200_THREADS / TSC_B200_MIN_BLOCKS): 32 warps at 64 registers, five 160-thread blocks,
-        // five 192-thread or four 256-thread blocks at 64 registers
+        // five 192-thread blocks at 64 registers
         if (!want_nt && (nt == 1024 || nt == 160)) continue;
-        if (!want_minb && ((nt == 192 && minb == 5) || (nt == 256 && minb == 4))) continue;
+        if (!want_minb && nt == 192 && minb == 5) continue;
         if (!one_t && !((nt == 256 && minb == 2) || nt == 512)) continue;      // generic-template builds
         if (nt == 160 && !one_t) continue;
         build_layout(E->Y, S, Vcap, nt / 32);

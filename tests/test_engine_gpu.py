@@ -86,12 +86,17 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
 
 
 @pytest.mark.parametrize("env,capacity,variant", [
-    ({}, 600, (192, 0, 4)),                                 # default at this size: four 192-thread blocks per SM
-    ({"TSC_B200_THREADS": "256"}, 600, (256, 0, 3)),        # three 256-thread blocks per SM
-    ({}, 1200, (256, 0, 2)),                                # larger replica: two 256-thread blocks per SM (128 registers)
+    ({}, 600, (256, 0, 4)),                                 # default at this size: four 256-thread blocks per SM (64 registers)
+    ({"TSC_B200_THREADS": "192"}, 600, (192, 0, 4)),        # four 192-thread blocks per SM (80 registers)
+    ({"TSC_B200_THREADS": "192", "TSC_B200_MIN_BLOCKS": "5"}, 560, (192, 0, 5)),
+    ({"TSC_B200_THREADS": "160"}, 560, (160, 0, 5)),
+    ({"TSC_B200_THREADS": "256", "TSC_B200_MIN_BLOCKS": "3"}, 600, (256, 0, 3)),        # three 256-thread blocks per SM (80 registers)
+    ({}, 1100, (256, 0, 3)),                                # larger replica: three 256-thread blocks per SM (80 registers)
+    ({}, 1560, (384, 0, 2)),                                # two 384-thread blocks per SM (80 registers)
+    ({"TSC_B200_THREADS": "256"}, 1560, (256, 0, 2)),       # two 256-thread blocks per SM (128 registers)
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0, 2)),     # per-vehicle template look-up although the scenario has one template
-    ({"TSC_B200_PREFETCH": "0"}, 600, (192, 0, 4)),
-    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (192, 0, 4)),      # plain vector copies instead of cp.async for staging
+    ({"TSC_B200_PREFETCH": "0"}, 600, (256, 0, 4)),
+    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (256, 0, 4)),      # plain vector copies instead of cp.async for staging
     ({}, 2000, (512, 0, 1)),                                # one 512-thread block per SM
     ({"TSC_B200_THREADS": "1024"}, 2000, (1024, 0, 1)),     # the same with 32 warps at 64 registers
     ({"TSC_B200_GMEM": "1"}, 600, (1024, 1, 1)),            # working set in a global-memory workspace

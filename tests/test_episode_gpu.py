@@ -90,9 +90,9 @@ def _episode(name, kw, capacity, B, replicas, ticks=3600, snap_every=50, expect_
 
 
 def test_bench_config_full_hour(cuda_lib):
-    """bench.py's kernel variant (capacity 640 -> four 192-thread blocks per SM) over the whole simulated hour."""
+    """bench.py's kernel variant (capacity 640 -> four 256-thread blocks per SM) over the whole simulated hour."""
     _episode("hangzhou_4_4", dict(signal=dict(observation_space="lane_features", reward_function="max_pressure")),
-             capacity=640, B=8, replicas=(0, 7), expect_variant=(192, 0), min_peak=500)
+             capacity=640, B=8, replicas=(0, 7), expect_variant=(256, 0), min_peak=500)
 
 
 @pytest.mark.parametrize("name,kw,capacity,min_peak", [
@@ -109,4 +109,4 @@ def test_loaded_scenarios_full_hour(cuda_lib, name, kw, capacity, min_peak):
 def test_full_batch_full_hour(cuda_lib):
     """B = 4096 (bench batch): first replica, both sides of the first grid wave's edge, last replica."""
     _episode("hangzhou_4_4", dict(signal=dict(observation_space="lane_features", reward_function="max_pressure")),
-             capacity=640, B=4096, replicas=(0, 591, 592, 4095), snap_every=300, expect_variant=(192, 0))
+             capacity=640, B=4096, replicas=(0, 591, 592, 4095), snap_every=300, expect_variant=(256, 0))
