@@ -460,6 +460,9 @@ def run_gpu_arm(args):
     act_np = act_pinned.numpy()
     state = {"step": 0}
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()      # started before the fast-forward: nvidia-smi needs a few hundred ms before its first sample
     # ---- untimed fast-forward into the loaded regime; the state (and the host policy's) is kept for both legs ----------
     eng.reset()
     eng.init_program(0)
@@ -497,9 +500,6 @@ def run_gpu_arm(args):
 
     # ---- device-resident leg ----------------------------------------------------------
     restart(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     for _ in range(args.warmup):
         one_step()
         flush.zero_()
