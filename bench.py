@@ -64,7 +64,7 @@ CONFIGS = {
                   replicas=2048, capacity=1150, api="BatchedEPyMARLTrafficSignalNetwork"),
     "manhattan": dict(scenario="manhattan_16_3", label="BASELINE.json configs[4]: 3600 s horizon",
                       kw=dict(cityflow=dict(flow_rate_type="constant", episode_limit=3600), signal=dict(LF, reward_function="queue_length")),
-                      replicas=4096, capacity=1560, api="BatchedTrafficSignalNetwork"),
+                      replicas=4096, capacity=1530, api="BatchedTrafficSignalNetwork"),
     "grid16": dict(scenario=None, label="BASELINE.json configs[3]: 16x16 grid, 900 veh/h/road, B = 1024 over 8 GPUs = 128 per GPU",
                    kw=dict(cityflow=dict(flow_rate_type="constant"), signal=dict(LF, reward_function="max_pressure")),
                    replicas=128, capacity=24000, api="BatchedTrafficSignalNetwork"),
