@@ -85,6 +85,7 @@ struct DevScn {   // device copies of tsc_scenario_t tables
     // pytsc tables
     const double *lane_pytsc_length, *lane_feat, *lane_cells;
     const int *sig_in_off, *sig_in_lane, *sig_out_off, *sig_out_lane;
+    const int *in_sig;               // [n_in_total] the signal an incoming-lane entry belongs to
     const int *sig_n_phases, *sig_phase_raw, *sig_min_time, *sig_max_time;
     const u8 *sig_phase_green;
     const int *nbr_off, *nbr_idx;
@@ -130,7 +131,7 @@ struct Layout {
     int Vlay;              // slots the columns are laid out for (>= Vcap: the retrieve scratch lives in a pos/spd pair)
     int ent_cap;           // vehicles that may change drivable in one tick
     int wl_cap;            // entries of a warp's private head-vehicle list
-    int async_stage;       // 1: cp.async staging of the image columns (TSC_B200_ASYNC_STAGE)
+    int async_stage;       // staging of the image columns (TSC_B200_ASYNC_STAGE): 2 bulk asynchronous copies + mbarrier, 1 cp.async, 0 plain
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
     // persistent part: identical byte offsets in the HBM image and in the working set
     int o_cnt, o_head, o_tail, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
@@ -592,17 +593,19 @@ __device__ __forceinline__ void head_look_ahead(const DevScn &S, const Ctx &c, i
     *leader_out = leader; *gap_out = gap;
 }
 
+// `frozen`: the replica carries a sticky error (the same answer in every thread: it comes out of a barrier).  Returns
+// that answer as of the end of the tick.
 template <int NT, bool ONE_T>
-__device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
+__device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool frozen) {
     const int tid = threadIdx.x;
     const int tick = c.h->tick;
     const double dt = DT;
     const int L = S.L;
-    if (c.h->err) {   // a replica that overflowed or lost its order is frozen: its result is reported invalid by tsc_check
+    if (frozen) {   // a replica that overflowed or lost its order is frozen: its result is reported invalid by tsc_check
         __syncthreads();
         if (tid == 0) c.h->tick = tick + 1;
         __syncthreads();
-        return;
+        return true;
     }
     {   // holes left by finished vehicles are squeezed out now and then (uniform decision: every thread reads the same header)
         const int ns = c.h->n_slots, holes = ns - c.h->n_running;
@@ -665,7 +668,10 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) spawned += __shfl_xor_sync(0xffffffffu, spawned, o);
-        if (tid == 0) { c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned; }
+        if (tid == 0) {
+            c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned;
+            c.h->n_ent = 0; c.h->n_x = 0;      // this tick's list counters (nobody touches them before the barrier below)
+        }
     }
     // ---- head vehicles (no vehicle ahead on their drivable) of the vehicles that were here before this tick, gathered
     //      warp-locally: look-ahead leader + gap (A.7).  Each WARP owns the slots of its 32-slot chunks.  When no spawn
@@ -831,7 +837,8 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
             if (sl == 0) finish_vehicle(S, Y, c, i, T, d, c.rpos[i], x, v, dlen, ns, blocker);
         }
     }
-    __syncthreads();
+    // (the barrier also tells every thread, uniformly, whether any decision raised a sticky error)
+    const bool bail = __syncthreads_or(c.h->err != 0) != 0;
     if (c.pt && tid == 0) atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x);
     pt_mark(c, PT_PHASE2);
 
@@ -840,12 +847,12 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
     //      Leaving: movers are a prefix of their drivable's list (FIFO); the mover at its head walks the prefix
     //      and hands the head over.  Entering (after a barrier): entrants go behind the vehicles that stay,
     //      ordered by new distance (descending, ties by creation id); one thread per entered drivable. ----
-    const int n_mv = c.h->n_ent;
-    if (c.h->err) {   // mover list overflow / no slot left: keep the old state; the sticky flag reports it
+    const int n_mv = c.h->n_ent;      // (stable until the next tick's first phase resets it)
+    if (bail) {   // mover list overflow / no slot left: keep the old state; the sticky flag reports it
         __syncthreads();
         if (tid == 0) { c.h->tick = tick + 1; c.h->n_slots = n_slots; }      // (vehicles that did enter before the slots ran out stay listed)
         __syncthreads();
-        return;
+        return true;
     }
     for (int m = tid; m < n_mv; m += NT) {
         const int i = c.mv_slot[m];
@@ -925,14 +932,14 @@ __device__ void engine_tick(const DevScn &S, const Layout &Y, Ctx &c) {
     if (tid == 0) {
         if (c.pt) atomicAdd(c.pt + PT_NENT, (unsigned long long) n_mv);
         c.h->n_slots = n_slots; c.h->tick = tick + 1;
-        c.h->n_ent = 0; c.h->n_x = 0; c.h->n_a = 0;      // scratch counters of the next tick
     }
     // the next state becomes the current one
     { double *t = c.pos; c.pos = c.npos; c.npos = t; }
     { double *t = c.spd; c.spd = c.nspd; c.nspd = t; }
     { short *t = c.blk; c.blk = c.nblk; c.nblk = t; }
-    __syncthreads();
+    const bool err_now = __syncthreads_or(c.h->err != 0) != 0;      // (the list surgery may have found a FIFO violation)
     pt_mark(c, PT_ENTER);
+    return err_now;
 }
 
 // ----------------------------------------------------------------------------
@@ -1291,30 +1298,6 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         s_loc[s] = -S.flick * chg - metric - 1e-6;
         s_prs[s] = pressure;
 
-        if (O.obs && S.obs_type == TSC_OBS_POSITION_MATRIX) {
-            // variable-length rows (observations.py:72-88 drops entries <= 0): one thread per signal
-            const int ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
-            const bool ex = S.reference_exact != 0;
-            float *dst = O.obs + ((size_t) b * A + s) * S.obs_dim;
-            const int body = ML * (vis + 9);
-            int total = 0;   // pad_list truncates only if it pads
-            for (int e = i0; e < i1; ++e) {
-                total += 9;
-                for (int k = 0; k < vis; ++k) total += win_in[e * vis + k] > 0;
-            }
-            bool tr = ex && total < body;
-            int k = 0;
-            for (int e = i0; e < i1; ++e) {
-                int l = __ldg(S.sig_in_lane + e);
-                for (int f = 0; f < 9 && k < body; ++f) dst[k++] = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
-                for (int j = 0; j < vis; ++j) {
-                    double val = win_in[e * vis + j];
-                    if (val > 0 && k < body) dst[k++] = ref_trunc(val > 1.0 ? 1.0 : val, tr);   // np.clip(val + 0, 0, 1)
-                }
-            }
-            for (; k < body; ++k) dst[k] = -1.0f;
-            for (int p = 0; p < MP; ++p) dst[k++] = p < P ? (p == cur ? 1.0f : 0.0f) : -1.0f;
-        }
         // action mask (common/traffic_signal.py:329-361, 375-404; actions.py:119-131, 169-188)
         if (O.mask || pkst) {
             const u32 allow = allowable_phases(S, c, s);
@@ -1329,6 +1312,42 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         }
     }
     __syncthreads();
+
+    // --- position-matrix observation rows (observations.py:140-160; :72-88 drops window entries <= 0, so a lane's block has
+    //     variable length and later lanes shift left): a thread per incoming lane.  Each counts the entries of the lanes
+    //     before it in its signal's row (at most 15 short sums), then writes its own block; a thread per signal pads the row
+    //     and appends the phase one-hot. ---
+    if (O.obs && S.obs_type == TSC_OBS_POSITION_MATRIX) {
+        const int ML = S.max_lanes_per_signal, MP = S.max_obs_phases;
+        const bool ex = S.reference_exact != 0;
+        const int body = ML * (vis + 9);
+        auto lane_entries = [&](int e) { int n = 9; for (int k = 0; k < vis; ++k) n += win_in[e * vis + k] > 0; return n; };
+        for (int e = tid; e < S.n_in_total; e += NT) {
+            const int sg = __ldg(S.in_sig + e);
+            const int i0 = __ldg(S.sig_in_off + sg), i1 = __ldg(S.sig_in_off + sg + 1);
+            int before = 0, total = 0;
+            for (int q = i0; q < i1; ++q) { const int n = lane_entries(q); total += n; if (q < e) before += n; }
+            const bool tr = ex && total < body;      // pad_list truncates only if it pads
+            float *dst = O.obs + ((size_t) b * A + sg) * S.obs_dim;
+            const int l = __ldg(S.sig_in_lane + e);
+            int k = before;
+            for (int f = 0; f < 9 && k < body; ++f) dst[k++] = ref_trunc(__ldg(S.lane_feat + l * 9 + f), tr);
+            for (int j = 0; j < vis; ++j) {
+                const double val = win_in[e * vis + j];
+                if (val > 0 && k < body) dst[k++] = ref_trunc(val > 1.0 ? 1.0 : val, tr);   // np.clip(val + 0, 0, 1)
+            }
+        }
+        for (int sg = tid; sg < A; sg += NT) {
+            const int i0 = __ldg(S.sig_in_off + sg), i1 = __ldg(S.sig_in_off + sg + 1);
+            int k = 0;
+            for (int q = i0; q < i1; ++q) k += lane_entries(q);
+            float *dst = O.obs + ((size_t) b * A + sg) * S.obs_dim;
+            if (k > body) k = body;
+            for (; k < body; ++k) dst[k] = -1.0f;
+            const int cur = c.scur[sg], P = __ldg(S.sig_n_phases + sg);
+            for (int p = 0; p < MP; ++p) dst[k++] = p < P ? (p == cur ? 1.0f : 0.0f) : -1.0f;
+        }
+    }
 
     // --- local rewards with spatially discounted neighbours (reward.py:81-88 | 129-136) ---
     if (O.reward || pkst) {
@@ -1475,6 +1494,40 @@ __device__ __forceinline__ void copy16_async(void *dst_smem, const void *src, in
 }
 __device__ __forceinline__ void copy16_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
+// ---- bulk asynchronous copies (the TMA engine's 1-D form): ONE thread issues a whole image column per instruction; an
+//      mbarrier in shared memory counts the bytes that have landed.  Sizes and addresses are multiples of 16 bytes. ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+    if (bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
+                     "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, unsigned bytes) {
+    if (bytes) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // CTL: the rule-based controllers are compiled in (kept out of the plain variant: their code costs the
 // hot path 2-3 % through register allocation alone).
 // GMEM: the replica's working set does not fit an SM's shared memory (a 16 x 16 grid needs ~1 MB): the
@@ -1506,6 +1559,14 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     } else c.tmpl = S.tmpl;
     c.pt = a.phase_cycles;
     c.pt_last = clock64();
+    // async_stage 2 (default): the image travels as bulk asynchronous copies (TMA, 1-D) issued by one thread, one per column
+    __shared__ __align__(8) unsigned long long stage_bar;
+    const bool bulk = !GMEM && Y.async_stage == 2;
+    unsigned stage_parity = 0;
+    if (bulk) {
+        if (tid == 0) { mbar_init(&stage_bar, 1); fence_proxy_async(); }
+        __syncthreads();
+    }
 
     for (int b = a.b0 + blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
@@ -1514,11 +1575,36 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         c.npos = (double *) (smem + Y.o_npos); c.nspd = (double *) (smem + Y.o_nspd); c.nblk = (short *) (smem + Y.o_nblk);
         c.ellt = (int *) (img + Y.o_ellt);      // cold column: worked on in place
         // ---- stage the replica image into the working set ----
-        copy16(smem, img, Y.o_meta_end, tid, NT);
-        __syncthreads();
+        if (bulk) {
+            if (tid == 0) {      // how many slots are in use is in the image's header: every column is one bulk copy of just that much
+                const int n0 = *(const volatile int *) img;      // RepHeader::n_slots
+                const unsigned n8 = (n0 * 8 + 15) & ~15, n4 = (n0 * 4 + 15) & ~15, n2 = (n0 * 2 + 15) & ~15, n1 = (n0 + 15) & ~15;
+                fence_proxy_async();      // whatever the block read or wrote here before, ahead of the copy engine's writes
+                mbar_expect_tx(&stage_bar, (unsigned) Y.o_meta_end + 2 * n8 + 2 * n4 + 3 * n2 + n1);
+                bulk_g2s(smem, img, (unsigned) Y.o_meta_end, &stage_bar);
+                bulk_g2s(smem + Y.o_pos, img + Y.o_pos, n8, &stage_bar);
+                bulk_g2s(smem + Y.o_spd, img + Y.o_spd, n8, &stage_bar);
+                bulk_g2s(smem + Y.o_rpos, img + Y.o_rpos, n4, &stage_bar);
+                bulk_g2s(smem + Y.o_vid, img + Y.o_vid, n4, &stage_bar);
+                bulk_g2s(smem + Y.o_lead, img + Y.o_lead, n2, &stage_bar);
+                bulk_g2s(smem + Y.o_foll, img + Y.o_foll, n2, &stage_bar);
+                bulk_g2s(smem + Y.o_blk, img + Y.o_blk, n2, &stage_bar);
+                bulk_g2s(smem + Y.o_pj, img + Y.o_pj, n1, &stage_bar);
+            }
+            {   // meanwhile: per-tick counters start from zero (the list surgery of every tick leaves them that way)
+                int4 *z = (int4 *) (smem + Y.o_leave);
+                const int nz = (Y.o_fresh - Y.o_leave + ((S.L + 15) & ~15)) / 16;      // leave, ent, fresh are adjacent
+                for (int k = tid; k < nz; k += NT) z[k] = make_int4(0, 0, 0, 0);
+            }
+            mbar_wait(&stage_bar, stage_parity);
+            stage_parity ^= 1u;
+        } else {
+            copy16(smem, img, Y.o_meta_end, tid, NT);
+            __syncthreads();
+        }
         const int n_in = c.h->n_slots;
         c.lso = S.lane_spawn_off + (size_t) c.h->flow_set * (S.L + 1);
-        {
+        if (!bulk) {
             const int n8 = (n_in * 8 + 15) & ~15, n4 = (n_in * 4 + 15) & ~15, n2 = (n_in * 2 + 15) & ~15, n1 = (n_in + 15) & ~15;
             if (!GMEM && Y.async_stage) {
                 copy16_async(smem + Y.o_pos, img + Y.o_pos, n8, tid, NT);
@@ -1540,7 +1626,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 copy16(smem + Y.o_pj, img + Y.o_pj, n1, tid, NT);
             }
         }
-        {   // per-tick counters start from zero (the list surgery of every tick leaves them that way)
+        if (!bulk) {   // per-tick counters start from zero (the list surgery of every tick leaves them that way)
             int4 *z = (int4 *) (smem + Y.o_leave);
             const int nz = (Y.o_fresh - Y.o_leave + ((S.L + 15) & ~15)) / 16;      // leave, ent, fresh are adjacent
             for (int k = tid; k < nz; k += NT) z[k] = make_int4(0, 0, 0, 0);
@@ -1553,7 +1639,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             const int at = b0 + c.wq[s];
             ((int4 *) c.sp_rec)[s] = at < b1 ? __ldg(S.spawn_rec + at) : make_int4(-1, INT_MAX, 0, 0);
         }
-        if (!GMEM && Y.async_stage) copy16_async_wait();      // this thread's requests; the barrier publishes everybody's
+        if (!GMEM && Y.async_stage == 1) copy16_async_wait();      // this thread's requests; the barrier publishes everybody's
         __syncthreads();
         // drivable | next drivable: the route table is read once per vehicle per launch, not once per tick
         {
@@ -1590,14 +1676,40 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             const u32 bits = __ballot_sync(0xffffffffu, on);
             if ((tid & 31) == 0 && k < S.K) c.avail[k >> 5] = bits;
         }
-        __syncthreads();
+        bool frozen = __syncthreads_or(c.h->err != 0) != 0;
         pt_mark(c, PT_PROLOGUE);
-        for (int t = 0; t < a.n_ticks; ++t) engine_tick<NT, ONE_T>(S, Y, c);
+        for (int t = 0; t < a.n_ticks; ++t) frozen = engine_tick<NT, ONE_T>(S, Y, c, frozen);
         if (a.do_retrieve) retrieve<NT>(S, Y, c, a, b, smem);
         pt_mark(c, PT_RETRIEVE);
 
         // ---- write the image back ----
-        if (!a.decide_only && (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0)) {
+        if (bulk && !a.decide_only && a.n_ticks > 0) {
+            // the columns leave as bulk copies too: every thread orders its own shared-memory writes ahead of the copy
+            // engine's reads, one thread issues; it waits until the engine has READ the working set before anything reuses it
+            fence_proxy_async();
+            __syncthreads();
+            const int n = c.h->n_slots;
+            if (tid == 0) {
+                const unsigned n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
+                bulk_s2g(img, smem, (unsigned) Y.o_meta_end);
+                bulk_s2g(img + Y.o_pos, c.pos, n8);      // whichever buffer holds the current state
+                bulk_s2g(img + Y.o_spd, c.spd, n8);
+                bulk_s2g(img + Y.o_blk, c.blk, n2);
+                bulk_s2g(img + Y.o_rpos, smem + Y.o_rpos, n4);
+                bulk_s2g(img + Y.o_vid, smem + Y.o_vid, n4);
+                bulk_s2g(img + Y.o_lead, smem + Y.o_lead, n2);
+                bulk_s2g(img + Y.o_foll, smem + Y.o_foll, n2);
+                bulk_s2g(img + Y.o_pj, smem + Y.o_pj, n1);
+                bulk_commit();
+            }
+            u32 *drv_pairs = (u32 *) (img + Y.o_drv);     // two u16 drivables per 32-bit store
+            for (int i = tid; i < (n + 1) / 2; i += NT) {
+                u32 lo = c.dn[2 * i] & 0xFFFFu;
+                u32 hi = 2 * i + 1 < n ? (c.dn[2 * i + 1] & 0xFFFFu) : 0u;
+                drv_pairs[i] = lo | (hi << 16);
+            }
+            if (tid == 0) bulk_wait_read();
+        } else if (!a.decide_only && (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0)) {
             __syncthreads();      // retrieve's scratch lives in the next-state buffers; nothing below reads them
             copy16(img, smem, Y.o_meta_end, tid, NT);
             const int n = c.h->n_slots;
@@ -1622,6 +1734,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         __syncthreads();
         pt_mark(c, PT_STAGE_OUT);
     }
+    if (bulk && tid == 0) bulk_wait_all();      // the last image's stores are complete before the block retires
 }
 
 // ----------------------------------------------------------------------------
@@ -2091,6 +2204,10 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
             }
         }
         if ((rc = upload(E, pkl.data(), pkl.size(), &S.pk_lane))) return rc;
+        std::vector<int> insig(s->n_in_total > 0 ? s->n_in_total : 1, 0);
+        for (int sg = 0; sg < A; ++sg)
+            for (int e = s->sig_in_off[sg]; e < s->sig_in_off[sg + 1]; ++e) insig[e] = sg;
+        if ((rc = upload(E, insig.data(), insig.size(), &S.in_sig))) return rc;
         S.pk_mode = small_ints ? 1 : 0;
         int o = align16((small_ints ? 4 : 12) * s->n_in_total);
         S.pk_o_phase = o; o = align16(o + A);
@@ -2213,8 +2330,8 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     if (Vcap > 32767) { return fail(TSC_EINVAL, "vehicle_capacity above 32767 (blocker slots are 16-bit signed)"); }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    int async_stage = 1, prefetch_next = 1;
-    if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) async_stage = atoi(env) != 0;
+    int async_stage = 2, prefetch_next = 1;      // 2: bulk asynchronous copies (TMA) + mbarrier, 1: cp.async, 0: plain vector copies
+    if (const char *env = getenv("TSC_B200_ASYNC_STAGE")) { int v = atoi(env); if (v >= 0 && v <= 2) async_stage = v; }
     if (const char *env = getenv("TSC_B200_PREFETCH")) prefetch_next = atoi(env) != 0;
     // Pick the variant from how many working sets fit an SM's shared memory (the register budget follows from the
     // launch bounds): the first of (256 threads x 4 blocks per SM, 64 registers), (192 x 4, 80), (256 x 3, 80), (384 x 2, 80),
@@ -2243,7 +2360,7 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
         if (nt == 160 && !one_t) continue;
         build_layout(E->Y, S, Vcap, nt / 32);
         if ((size_t) E->Y.smem_bytes > prop.sharedMemPerBlockOptin) continue;
-        if ((int) (per_sm_bytes / (size_t) (E->Y.smem_bytes + 1024)) < minb) continue;
+        if ((int) (per_sm_bytes / (size_t) (E->Y.smem_bytes + 1024 + 64)) < minb) continue;      // + per-block reserve and the kernel's static shared memory
         E->nt = nt; E->minb = minb; chosen = true;
     }
     if (!chosen) { E->gmem = true; E->nt = 1024; E->minb = 1; build_layout(E->Y, S, Vcap, 32); }

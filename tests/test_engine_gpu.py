@@ -96,7 +96,8 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({"TSC_B200_THREADS": "256"}, 1560, (256, 0, 2)),       # two 256-thread blocks per SM (128 registers)
     ({"TSC_B200_ONE_TEMPLATE": "0"}, 600, (256, 0, 2)),     # per-vehicle template look-up although the scenario has one template
     ({"TSC_B200_PREFETCH": "0"}, 600, (256, 0, 4)),
-    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (256, 0, 4)),      # plain vector copies instead of cp.async for staging
+    ({"TSC_B200_ASYNC_STAGE": "0"}, 600, (256, 0, 4)),      # plain vector copies instead of bulk asynchronous copies for staging
+    ({"TSC_B200_ASYNC_STAGE": "1"}, 600, (256, 0, 4)),      # cp.async (16 bytes per request per thread)
     ({}, 2000, (512, 0, 1)),                                # one 512-thread block per SM
     ({"TSC_B200_THREADS": "1024"}, 2000, (1024, 0, 1)),     # the same with 32 warps at 64 registers
     ({"TSC_B200_GMEM": "1"}, 600, (1024, 1, 1)),            # working set in a global-memory workspace

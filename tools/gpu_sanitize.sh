@@ -20,6 +20,8 @@ run t384x2            "X=1" --capacity 1560
 run t256x2            "TSC_B200_THREADS=256" --capacity 1560
 run t512              "X=1" --capacity 2000
 run gmem1024          "TSC_B200_GMEM=1" --capacity 600
+run stage_cp_async    "TSC_B200_ASYNC_STAGE=1" --capacity 600
+run stage_plain       "TSC_B200_ASYNC_STAGE=0" --capacity 600
 run ctl_greedy        "X=1" --capacity 600 --controller greedy
 run ctl_max_pressure  "X=1" --capacity 600 --controller max_pressure --obs position_matrix
 run ctl_sotl          "X=1" --capacity 600 --controller sotl
