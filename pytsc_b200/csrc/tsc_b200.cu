@@ -133,6 +133,7 @@ struct Layout {
     int wl_cap;            // entries of a warp's private head-vehicle list
     int async_stage;       // staging of the image columns (TSC_B200_ASYNC_STAGE): 2 bulk asynchronous copies + mbarrier, 1 cp.async, 0 plain
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
+    int warp_surgery;      // 1: up to 32 movers do both halves of the list surgery inside the first warp (TSC_B200_WARP_SURGERY)
     // persistent part: identical byte offsets in the HBM image and in the working set
     int o_cnt, o_head, o_tail, o_wq, o_sraw, o_scur, o_schg, o_stop, o_meta_end;
     int o_pos, o_spd, o_rpos, o_vid, o_lead, o_foll, o_drv, o_pj, o_blk;
@@ -878,7 +879,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     }
     // up to 32 movers (the usual case: half a dozen) are all lanes of the first warp: a warp-level barrier orders the
     // two halves of the surgery and the other warps go straight to the end of the tick
-    if (n_mv <= 32) { if (tid < 32) __syncwarp(); } else __syncthreads();
+    if (Y.warp_surgery && n_mv <= 32) { if (tid < 32) __syncwarp(); } else __syncthreads();
     pt_mark(c, PT_LEAVE);
     for (int m = tid; m < n_mv; m += NT) {
         const int i = c.mv_slot[m];
@@ -2365,6 +2366,8 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     }
     if (!chosen) { E->gmem = true; E->nt = 1024; E->minb = 1; build_layout(E->Y, S, Vcap, 32); }
     E->Y.async_stage = async_stage; E->Y.prefetch_next = prefetch_next;
+    E->Y.warp_surgery = 1;
+    if (const char *env = getenv("TSC_B200_WARP_SURGERY")) E->Y.warp_surgery = atoi(env) != 0;
     E->kern = kernel_for(E->nt, E->minb, false, one_t, E->gmem);
     E->kern_ctl = kernel_for(E->nt, E->minb, true, one_t, E->gmem);
     const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;

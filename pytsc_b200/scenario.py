@@ -18,7 +18,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import bundle
-from .roadnet import RoadNet, VEHICLE_KEYS, expand_flows
+from .roadnet import RoadNet, VEHICLE_DEFAULTS, VEHICLE_KEYS, expand_flows
 
 ABI_VERSION = 3
 T_STRIDE = 12
@@ -189,6 +189,8 @@ def compile_scenario(config, parser, flows=None, flow_file=None, flow_sets=None)
     # every flow file is what a fresh cityflow.Engine(seed) would make of it: the generator restarts per set
     sp = merge_flow_sets([expand_flows(rn, f, float(sim["interval"]), int(sim["seed"]), horizon) for f in flow_sets])
     F = len(flow_sets)
+    if not sp["templates"]:      # no vehicle at all: CityFlow's default vehicle stands in (the tables must be well formed)
+        sp["templates"] = [tuple(float(VEHICLE_DEFAULTS[k]) for k in VEHICLE_KEYS)]
     L, K = len(rn.lanes), len(rn.lanelinks)
     a, s = {}, {}
     f64, i32 = np.float64, np.int32

@@ -117,3 +117,103 @@ def test_replicas_are_independent(cuda_lib):
         assert compare_snapshots(e.snapshot(0), eng.snapshot(b)) is None
         e.close()
     eng.check(); eng.close()
+
+
+def _oracle_for(tmp_path, net, flows, seed=0):
+    import json
+    from oracle.engine import Engine as OracleEngine
+    (tmp_path / "roadnet.json").write_text(json.dumps(net))
+    (tmp_path / "flow.json").write_text(json.dumps(flows))
+    cfg = dict(dir=str(tmp_path) + "/", roadnetFile="roadnet.json", flowFile="flow.json", interval=1.0, rlTrafficLight=True,
+               laneChange=False, seed=seed, saveReplay=False)
+    (tmp_path / "cfg.json").write_text(json.dumps(cfg))
+    return OracleEngine(str(tmp_path / "cfg.json"))
+
+
+def _lockstep_custom_flows(tmp_path, flows, ticks, capacity=900, expect_templates=None):
+    import torch
+    from pytsc_b200 import bundle
+    from pytsc_b200.binding import Engine
+    from pytsc_b200.scenario import compile_scenario
+    from helpers import oracle_engine, signal_inter_indices
+    cfg, parser, _ = build_scenario("hangzhou_4_4", **KW)
+    cs = compile_scenario(cfg, parser, flows=flows)
+    if expect_templates is not None:
+        assert cs.n_templates == expect_templates
+    orc = _oracle_for(tmp_path, parser.net, flows, seed=cfg.simulator["seed"])
+    eng = Engine(cs, 2, 0, vehicle_capacity=capacity)
+    inter = signal_inter_indices(parser)
+    seen = 0
+    for t in range(ticks):
+        if t % 5 == 0:
+            r = ((t // 30) % 8 + 1) if (t % 30) < 25 else 0
+            eng.set_phase(torch.full((2, eng.A), r, dtype=torch.int32, device="cuda"))
+            for a in range(eng.A):
+                orc.set_tl_phase_idx(inter[a], r)
+        orc.next_step()
+        eng.step(1)
+        if t % 7 == 0 or t == ticks - 1:
+            so = orc.snapshot()
+            seen = max(seen, len(so["uid"]))
+            msg = compare_snapshots(so, eng.snapshot(1))
+            assert msg is None, f"tick {t}: {msg}"
+    eng.check()
+    c = eng.counters()
+    assert c["n_running"][0] == orc.get_vehicle_count() and c["n_finished"][0] == orc.get_finished_vehicle_count()
+    info = eng.kernel_info()
+    eng.close()
+    return seen, info
+
+
+def test_several_vehicle_templates(cuda_lib, tmp_path):
+    """Flow files may give every flow its own vehicle parameters: three templates (lengths, accelerations, speeds, gaps,
+    headways) interleaved -- the per-vehicle template look-up path of the kernel, in lock-step with the oracle."""
+    from pytsc_b200 import bundle
+    cfg, parser, _ = build_scenario("hangzhou_4_4", **KW)
+    flows = bundle.load_flow(cfg.create_and_save_cityflow_cfg())
+    variants = [dict(length=4.0, minGap=2.0, maxSpeed=9.5, maxPosAcc=1.5, usualPosAcc=1.5, headwayTime=1.8),
+                dict(length=6.5, minGap=3.0, maxSpeed=12.5, maxNegAcc=5.0, usualNegAcc=3.5, headwayTime=1.2)]
+    for k, f in enumerate(flows):
+        if k % 3:
+            f["vehicle"] = dict(f["vehicle"], **variants[k % 3 - 1])
+    seen, info = _lockstep_custom_flows(tmp_path, flows, 450, expect_templates=3)
+    assert seen > 150 and info["threads"] in (256, 512)
+
+
+def test_empty_flow_file(cuda_lib, tmp_path):
+    """No vehicles at all: every launch, retrieve and the registered host path still work; all measurements are zero."""
+    import torch
+    from pytsc_b200.binding import Engine
+    from pytsc_b200.scenario import compile_scenario
+    cfg, parser, _ = build_scenario("syn_1x1", **KW)
+    cs = compile_scenario(cfg, parser, flows=[])
+    assert cs.n_vehicles == 0
+    eng = Engine(cs, 3, 0, vehicle_capacity=64)
+    bufs = eng.alloc_outputs()
+    eng.init_program(0)
+    for _ in range(20):
+        eng.env_step(None, bufs, n_ticks=5, controller=1, controller_arg=25)
+    torch.cuda.synchronize()
+    eng.check()
+    assert int(bufs["lane_count"].sum()) == 0 and float(bufs["sim"][:, 0].sum()) == 0.0 and float(bufs["sim"][:, 1].sum()) == 0.0
+    assert (bufs["reward_global"].cpu().numpy() <= 0).all()
+    assert eng.snapshot(2)["uid"].size == 0
+    eng.close()
+
+
+def test_continuous_flows(cuda_lib, tmp_path):
+    """CityFlow flow entries may emit a vehicle every `interval` seconds between startTime and endTime (the shipped files
+    only use single-vehicle entries): Flow::nextStep's counting (SURVEY A.3), fractional intervals included."""
+    from pytsc_b200 import bundle
+    cfg, parser, _ = build_scenario("hangzhou_4_4", **KW)
+    base = bundle.load_flow(cfg.create_and_save_cityflow_cfg())
+    routes = []
+    for f in base:
+        if f["route"] not in routes:
+            routes.append(f["route"])
+        if len(routes) == 40:
+            break
+    flows = [dict(vehicle=base[0]["vehicle"], route=r, interval=[3.0, 4.5, 7.0, 2.5][k % 4], startTime=5 * (k % 6), endTime=(-1 if k % 5 == 0 else 300 + 10 * k))
+             for k, r in enumerate(routes)]
+    seen, _ = _lockstep_custom_flows(tmp_path, flows, 420)
+    assert seen > 200

@@ -71,7 +71,8 @@ def test_bench_host_policy_is_the_fixed_time_rule():
     import numpy as np
     import bench
     from helpers import build_scenario
-    cfg, parser, cs = build_scenario(bench.SCENARIO, **bench.SCENARIO_KW)
+    w = bench.CONFIGS["hangzhou"]
+    cfg, parser, cs = build_scenario(w["scenario"], **w["kw"])
     A, B, G, dt = cs.n_signals, 7, bench.GREEN_TIME, 5
     green = np.ascontiguousarray(cs.sig_phase_green).reshape(A, -1).astype(bool)
     nph = np.asarray(cs.sig_n_phases, np.int64)
