@@ -64,6 +64,15 @@ def needs_build():
     return not os.path.exists(LIB) or built_hash() != source_hash()
 
 
+def build_variant(out, flags):
+    """A side build of the same source with extra -D flags (phase timing, A/B experiments) for TSC_B200_LIB."""
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(flags) + ["-I", INCLUDE, "-o", out, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

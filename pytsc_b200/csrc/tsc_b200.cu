@@ -206,16 +206,33 @@ struct Ctx {
     // kinematics ping-pong: every tick reads pos / spd / blk and writes npos / nspd / nblk, then they swap
     short *blk, *nblk;
     double *pos, *spd, *npos, *nspd;
+    int par;              // which half of the ping-pong holds the current state (0: the one that mirrors the image)
     int tick;
+#ifdef TSC_PHASE_TIMING
     unsigned long long *pt;   // debug phase timing (NULL = off)
     long long pt_last;
+#endif
 };
 
 // phase ids of the debug timing
 enum { PT_STAGE_IN = 0, PT_PROLOGUE, PT_SPAWN, PT_PHASE1A, PT_PHASE1, PT_PHASE1C, PT_PHASE2, PT_LEAVE, PT_ENTER, PT_COMPACT, PT_RETRIEVE,
        PT_STAGE_OUT, PT_NH, PT_NA, PT_NX, PT_NENT, PT_N };
+// (compiled in only with -DTSC_PHASE_TIMING, tools/phase_timing.py's build: in the shipped kernel the two words would
+// live on the stack and be reloaded beside every barrier)
 __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
+#ifdef TSC_PHASE_TIMING
     if (c.pt && threadIdx.x == 0) { long long t = clock64(); atomicAdd(c.pt + k, (unsigned long long) (t - c.pt_last)); c.pt_last = t; }
+#endif
+}
+
+// The kinematics ping-pong: which buffers are "current" and which "next" follows from the parity alone, so a tick ends
+// by flipping one integer (swapping six pointers that live on the stack cost a dependent local load + store each).
+__device__ __forceinline__ void set_pingpong(const Layout &Y, Ctx &c) {
+    unsigned char *const smem = (unsigned char *) c.h;
+    const bool p = c.par != 0;
+    c.pos = (double *) (smem + (p ? Y.o_npos : Y.o_pos)); c.npos = (double *) (smem + (p ? Y.o_pos : Y.o_npos));
+    c.spd = (double *) (smem + (p ? Y.o_nspd : Y.o_spd)); c.nspd = (double *) (smem + (p ? Y.o_spd : Y.o_nspd));
+    c.blk = (short *) (smem + (p ? Y.o_nblk : Y.o_blk)); c.nblk = (short *) (smem + (p ? Y.o_blk : Y.o_nblk));
 }
 
 // Append to a per-tick work list from whichever lanes of the warp are here together: one atomic per warp
@@ -594,6 +611,11 @@ __device__ __forceinline__ void head_look_ahead(const DevScn &S, const Ctx &c, i
     *leader_out = leader; *gap_out = gap;
 }
 
+#ifdef TSC_AB_PLAIN_ERR      // timing experiment only: a plain barrier, then everybody reads the flag (threads could disagree)
+#define TICK_SYNC_ERR(x) (__syncthreads(), (x))
+#else
+#define TICK_SYNC_ERR(x) (__syncthreads_or(x) != 0)
+#endif
 // `frozen`: the replica carries a sticky error (the same answer in every thread: it comes out of a barrier).  Returns
 // that answer as of the end of the tick.
 template <int NT, bool ONE_T>
@@ -839,8 +861,10 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
         }
     }
     // (the barrier also tells every thread, uniformly, whether any decision raised a sticky error)
-    const bool bail = __syncthreads_or(c.h->err != 0) != 0;
+    const bool bail = TICK_SYNC_ERR(c.h->err != 0);
+#ifdef TSC_PHASE_TIMING
     if (c.pt && tid == 0) atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x);
+#endif
     pt_mark(c, PT_PHASE2);
 
     // ---- updateLocation.  Slots are stable, so there is nothing to re-pack: every vehicle's next state is
@@ -931,14 +955,15 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
         }
     }
     if (tid == 0) {
+#ifdef TSC_PHASE_TIMING
         if (c.pt) atomicAdd(c.pt + PT_NENT, (unsigned long long) n_mv);
+#endif
         c.h->n_slots = n_slots; c.h->tick = tick + 1;
     }
     // the next state becomes the current one
-    { double *t = c.pos; c.pos = c.npos; c.npos = t; }
-    { double *t = c.spd; c.spd = c.nspd; c.nspd = t; }
-    { short *t = c.blk; c.blk = c.nblk; c.nblk = t; }
-    const bool err_now = __syncthreads_or(c.h->err != 0) != 0;      // (the list surgery may have found a FIFO violation)
+    c.par ^= 1;
+    set_pingpong(Y, c);
+    const bool err_now = TICK_SYNC_ERR(c.h->err != 0);      // (the list surgery may have found a FIFO violation)
     pt_mark(c, PT_ENTER);
     return err_now;
 }
@@ -1558,8 +1583,10 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
         for (int k = tid; k < S.T * TD_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
     } else c.tmpl = S.tmpl;
+#ifdef TSC_PHASE_TIMING
     c.pt = a.phase_cycles;
     c.pt_last = clock64();
+#endif
     // async_stage 2 (default): the image travels as bulk asynchronous copies (TMA, 1-D) issued by one thread, one per column
     __shared__ __align__(8) unsigned long long stage_bar;
     const bool bulk = !GMEM && Y.async_stage == 2;
@@ -1572,8 +1599,8 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     for (int b = a.b0 + blockIdx.x; b < a.B; b += gridDim.x) {
         unsigned char *img = images + (size_t) b * Y.img_bytes;
         // the kinematics ping-pong between two buffers every tick: start from the ones that mirror the image
-        c.pos = (double *) (smem + Y.o_pos); c.spd = (double *) (smem + Y.o_spd); c.blk = (short *) (smem + Y.o_blk);
-        c.npos = (double *) (smem + Y.o_npos); c.nspd = (double *) (smem + Y.o_nspd); c.nblk = (short *) (smem + Y.o_nblk);
+        c.par = 0;
+        set_pingpong(Y, c);
         c.ellt = (int *) (img + Y.o_ellt);      // cold column: worked on in place
         // ---- stage the replica image into the working set ----
         if (bulk) {
@@ -3002,6 +3029,9 @@ int64_t tsc_launch_count(tsc_handle E) { return E ? E->launches : 0; }
 
 int tsc_debug_timing(tsc_handle E, int32_t enable, uint64_t *cycles_out, int32_t n) {
     if (!E) return fail(TSC_EINVAL, "null handle");
+#ifndef TSC_PHASE_TIMING
+    if (enable) return fail(TSC_EINVAL, "this build has no phase timing (compile with -DTSC_PHASE_TIMING: tools/phase_timing.py does)");
+#endif
     CUDA_TRY(cudaSetDevice(E->device));
     CUDA_TRY(cudaDeviceSynchronize());
     if (cycles_out && E->d_phase_cycles) {

@@ -1,17 +1,20 @@
 #!/bin/bash
-# parity tests, then bench (no CPU baseline) under a list of env settings: tools/gpu_ab.sh "VAR=1" "VAR=2 OTHER=3" ...
-mkdir -p gpurun_out
-if [ -z "$SKIP_TESTS" ]; then timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log; fi
-i=0
-for cfg in "$@"; do
-  i=$((i+1))
-  env $cfg timeout 300 python bench.py --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/ab$i.json 2> gpurun_out/ab$i.err
-  python - <<PY
-import json
+# A/B in one box visit: "name|env" runs of the short bench, twice each, interleaved; parity subset first
+mkdir -p gpurun_out; : > gpurun_out/ab.txt
+timeout 900 python -m pytest tests/test_engine_gpu.py tests/test_episode_gpu.py tests/test_edge_gpu.py -m gpu -x -q > gpurun_out/pytest_engine.log 2>&1; tail -4 gpurun_out/pytest_engine.log
+run() {
+  name=$1; envs=$2; shift 2
+  ( env $envs timeout 300 python bench.py --steps 60 --warmup 8 --no-cpu-baseline "$@" 2> gpurun_out/ab_$name.err ) | python -c "
+import json,sys
 try:
-    d=json.load(open("gpurun_out/ab$i.json"))
-    print("[$cfg]", "ms %.4f"%d["ms_per_step"], "e2e ms %.3f"%d["e2e"]["ms_per_step"], "policy ms %.3f"%d["e2e"].get("host_policy_ms_per_step",-1), "frac %.4f"%d["roofline"]["frac"], d["config"]["kernel"])
+    d=json.loads(sys.stdin.read()); k=d['config']['kernel']
+    print('$name: dev ms %.4f  e2e ms %.4f  match %s  nt %d x %d regs %d smem %d' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['matches_device_leg'], k['threads'], k['blocks_per_sm'], k['regs'], k['smem_bytes']))
 except Exception as e:
-    print("[$cfg] failed", e); print(open("gpurun_out/ab$i.err").read()[-1500:])
-PY
+    print('$name failed', e)
+" | tee -a gpurun_out/ab.txt
+}
+for rep in 1 2; do
+for lib in ${AB_LIBS:-r2h head par2 par2_plain}; do
+run $lib "TSC_B200_LIB=$PWD/tools/ab/lib_$lib.so"
+done
 done

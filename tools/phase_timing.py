@@ -4,6 +4,14 @@ usage: python tools/phase_timing.py [vehicle_capacity] [replicas]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from pytsc_b200 import _build
+TIMING_LIB = os.path.join(ROOT, "tools", "ab", "lib_timing.so")      # built here (CPU container) so that it travels to the GPU box
+if not os.path.exists(TIMING_LIB) or os.path.getmtime(TIMING_LIB) < os.path.getmtime(_build.SRC):
+    os.makedirs(os.path.dirname(TIMING_LIB), exist_ok=True)
+    _build.build_variant(TIMING_LIB, ["-DTSC_PHASE_TIMING"])
+os.environ["TSC_B200_LIB"] = TIMING_LIB
+if "--build-only" in sys.argv:
+    sys.exit(0)
 import torch
 import bench
 from pytsc_b200.backend.config import Config
