@@ -527,46 +527,102 @@ def run_gpu_arm(args):
 
     # ---- end-to-end leg: the public host API ------------------------------------------------------------------
     # host policy -> actions (page-locked host memory) -> step_host -> observation rows, rewards, masks, global
-    # reward in HOST numpy arrays, every step, synchronous
-    host_out = env.register_host_buffers()
+    # reward in HOST numpy arrays, every step.  Double-buffered sampling: the rank's B replicas are two environments
+    # of B / 2, stepped alternately through step_host_begin / step_host_wait, so that the policy and the row finishing
+    # of one half overlap the launch of the other (every half's actions still follow its own previous observations).
+    n_half = 1 if (args.e2e_halves < 2 or B < 2) else 2
+    sizes = [B] if n_half == 1 else [B // 2, B - B // 2]
+    auto_threads = max(1, min(8, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    threads = int(os.environ.get("TSC_B200_HOST_THREADS", "0")) or auto_threads
+    threads_per_half = max(1, threads // n_half)
+    halves = []
+    for hb in sizes:
+        if n_half == 1:
+            h_env, h_wrap = env, wrapper
+        elif w["api"] == "BatchedEPyMARLTrafficSignalNetwork":
+            h_wrap = BatchedEPyMARLTrafficSignalNetwork(map_name=w["scenario"], simulator_backend="gpu", n_replicas=hb, device=local, **kw)
+            h_env = h_wrap.tsc_env
+        else:
+            h_wrap, h_env = None, BatchedTrafficSignalNetwork(w["scenario"], n_replicas=hb, device=local, **kw)
+        h_pol = HostFixedTimePolicy(cs.sig_phase_green, cs.sig_n_phases, hb, A, GREEN_TIME, n_ticks)
+        h_act = torch.zeros((hb, A), dtype=torch.int32, pin_memory=True)
+        h = {"env": h_env, "wrap": h_wrap, "eng": h_env.engine, "policy": h_pol, "act": h_act, "act_np": h_act.numpy(), "B": hb,
+             "step": 0, "out": h_env.register_host_buffers(threads=threads_per_half)}
+        if n_half > 1:      # its own untimed fast-forward into the loaded regime
+            h["eng"].reset(); h["eng"].init_program(0); h_pol.reset()
+            for _ in range(ff):
+                h["eng"].env_step(None, None, n_ticks=n_ticks, controller=1, controller_arg=GREEN_TIME)
+                h_pol.act(h["act_np"])
+            torch.cuda.synchronize()
+            h["eng"].check()
+            h["loaded"] = (h["eng"].save_state(device=True), h_pol.snapshot())
+        else:
+            h["loaded"] = (loaded_state, loaded_policy)
+        halves.append(h)
     policy_s = [0.0]
 
-    def e2e_step():
-        if state["step"] == sim_len_steps:
-            restart(False)
-        t_p = time.perf_counter()
-        policy.act(act_np)
-        policy_s[0] += time.perf_counter() - t_p
-        if wrapper is not None:
-            env.step_host(act_np, controller="phase_index")
-            _ = host_out["reward_global"] / A          # epymarl.py:106-108: common reward = global / n_agents
+    def half_restart(h, from_loaded):
+        if from_loaded:
+            h["eng"].load_state(h["loaded"][0]); h["policy"].restore(h["loaded"][1]); h["step"] = ff
         else:
-            env.step_host(act_np, controller="phase_index")
-        state["step"] += 1
+            h["eng"].reset(); h["eng"].init_program(0); h["policy"].reset(); h["step"] = 0
 
-    restart(True)
+    def half_begin(h):
+        if h["step"] == sim_len_steps:
+            half_restart(h, False)
+        t_p = time.perf_counter()
+        h["policy"].act(h["act_np"])
+        policy_s[0] += time.perf_counter() - t_p
+        h["env"].step_host_begin(h["act_np"], controller="phase_index")
+
+    def half_wait(h):
+        h["env"].step_host_wait()
+        if h["wrap"] is not None:
+            _ = h["out"]["reward_global"] / A          # epymarl.py:106-108: common reward = global / n_agents
+        h["step"] += 1
+
+    def e2e_run(n):      # n env-steps of every half, software-pipelined across the halves
+        if n <= 0:
+            return
+        half_begin(halves[0])
+        for k in range(n):
+            for j in range(1, n_half):
+                half_begin(halves[j])
+            half_wait(halves[0])
+            if k + 1 < n:
+                half_begin(halves[0])
+            for j in range(1, n_half):
+                half_wait(halves[j])
+
+    for h in halves:
+        half_restart(h, True)
     torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        e2e_step()
+    e2e_run(args.warmup)
     sync_all()
-    l0 = eng.launch_count()
+    l0 = sum(h["eng"].launch_count() for h in halves)
     policy_s[0] = 0.0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     sync_all()
     e2e_s = time.perf_counter() - t0
-    e2e_launches = eng.launch_count() - l0
-    eng.check()
-    h2d = act_np.nbytes
-    d2h = eng.host_packet_bytes()
-    host_bytes_finished = sum(v.nbytes for v in host_out.values())
-    e2e_reward = float(host_out["reward_global"].mean())
+    e2e_launches = sum(h["eng"].launch_count() for h in halves) - l0
+    for h in halves:
+        h["eng"].check()
+    h2d = sum(h["act_np"].nbytes for h in halves)
+    d2h = sum(h["eng"].host_packet_bytes() for h in halves)
+    host_bytes_finished = sum(v.nbytes for h in halves for v in h["out"].values())
+    e2e_reward = float(np.concatenate([h["out"]["reward_global"] for h in halves]).mean())
     # the host arrays must hold what the device leg computed for the same state and actions (both legs ran the same
     # number of steps from the same state under the same rule)
-    e2e_matches_device = bool(np.array_equal(host_out["obs"], bufs["obs"].cpu().numpy())
-                              and np.array_equal(host_out["reward"], bufs["reward"].cpu().numpy())
-                              and np.array_equal(host_out["mask"], bufs["mask"].cpu().numpy()))
+    dev_rows = {k: bufs[k].cpu().numpy() for k in ("obs", "reward", "mask")}
+    e2e_matches_device, lo = True, 0
+    for h in halves:
+        for k in ("obs", "reward", "mask"):
+            e2e_matches_device = e2e_matches_device and bool(np.array_equal(h["out"][k], dev_rows[k][lo:lo + h["B"]]))
+        lo += h["B"]
+    for h in halves:
+        if h["env"] is not env:
+            h["env"].close()
 
     # ---- max over ranks; episode metrics all-reduced once (the only collective) ----------
     t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device="cuda")
@@ -624,8 +680,9 @@ def run_gpu_arm(args):
                 "ms_per_step": 1e3 * e2e_s / args.steps, "mean_global_reward_last_step": e2e_reward,
                 "host_policy_ms_per_step": 1e3 * policy_s[0] / args.steps,
                 "host_result_bytes_per_step": host_bytes_finished, "host_threads": host_threads,
+                "environments": f"{n_half} x {sizes[0]} replicas, {threads_per_half} host workers each" + (", stepped alternately (double-buffered sampling)" if n_half > 1 else ""),
                 "matches_device_leg": e2e_matches_device,
-                "note": "host fixed-time policy (numpy, inside the timed region) -> actions H2D from page-locked memory -> one launch; "
+                "note": "host fixed-time policy (numpy, inside the timed region) -> actions H2D from page-locked memory -> one launch per environment; "
                         "each replica block stores a compact packet (per-lane queue / occupancy / speed as the row shows them, phase, "
                         "rewards, action bits) into page-locked host memory and raises a flag; host threads finish the fp32 "
                         "observation rows, rewards and masks in the caller's numpy arrays while the launch runs (d2h = packet bytes; "
@@ -652,6 +709,8 @@ def main():
     ap.add_argument("--fast-forward", type=int, default=360,
                     help="untimed env-steps before warm-up (both arms): 360 = tick 1800, the loaded regime")
     ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = the config's)")
+    ap.add_argument("--e2e-halves", type=int, default=2,
+                    help="e2e leg: 2 = double-buffered sampling over two environments of B/2 replicas (default), 1 = one synchronous step_host")
     ap.add_argument("--vehicle-capacity", type=int, default=0,
                     help="running vehicles per replica the image is sized for (0 = the config's)")
     ap.add_argument("--cpu-steps", type=int, default=60, help="env-steps per process of the cpu_baseline sample")

@@ -302,6 +302,20 @@ int  tsc_host_register(tsc_handle h, float *obs_host, float *reward_host, uint8_
 int  tsc_host_unregister(tsc_handle h);
 int  tsc_env_step_registered(tsc_handle h, const int32_t *actions_host, int32_t controller,
                              int32_t controller_arg, int32_t n_ticks);
+
+/* The same step in two halves, for callers that keep several handles (or their own work) in flight -- e.g. two
+ * handles of B/2 replicas each, stepped alternately so that the host policy and row finishing of one half overlap
+ * the launch of the other (the double-buffered sampling loop of bench.py's e2e leg).  _begin queues the action
+ * copy and the launch and wakes the worker threads, then returns; _wait finishes the caller's share of the rows,
+ * waits for the workers and the stream, and reports errors.  A page-locked actions_host must stay untouched
+ * until _wait returns.  At most one step per handle in flight.  tsc_env_step_registered = _begin + _wait. */
+int  tsc_env_step_registered_begin(tsc_handle h, const int32_t *actions_host, int32_t controller,
+                                   int32_t controller_arg, int32_t n_ticks);
+int  tsc_env_step_registered_wait(tsc_handle h);
+
+/* Worker threads of the registered path for handles registered AFTER this call (0 = the automatic choice,
+ * min(8, cores / LOCAL_WORLD_SIZE), or TSC_B200_HOST_THREADS); returns the count that will be used. */
+int  tsc_host_threads(tsc_handle h, int32_t n);
 int64_t tsc_host_packet_bytes(tsc_handle h);
 
 /* Copy the running vehicles of replica b to host arrays of capacity `cap`
@@ -343,12 +357,12 @@ int  tsc_debug_timing(tsc_handle h, int32_t enable, uint64_t *cycles_out, int32_
 /* Name, bytes of dynamic shared memory, threads per block and grid of the step kernel. */
 int  tsc_kernel_info(tsc_handle h, int32_t *smem_bytes, int32_t *threads, int32_t *grid, int32_t *regs);
 
-/* Which variant of the step kernel the handle runs: staged = 1 when the per-tick re-pack stages the
- * identity columns in registers (large replicas that only fit shared memory that way);
- * global_workspace = 1 when the replica's working set does not fit shared memory at all and lives in a
- * global-memory (L2-resident) workspace, 2 when only the cold enterLaneLinkTime column does (hybrid:
- * four replica blocks per SM); blocks_per_sm = launch-bounds variant. */
-int  tsc_kernel_variant(tsc_handle h, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm);
+/* Which variant of the step kernel the handle runs: fixed_capacity = 1 when the kernel was compiled for exactly
+ * this handle's vehicle capacity (the bench workloads' capacities: the per-vehicle columns of the working set sit at
+ * compile-time offsets; TSC_B200_FIXED_CAPACITY=0 forces the generic build); global_workspace = 1 when the
+ * replica's working set does not fit shared memory and lives in a global-memory (L2-resident) workspace;
+ * blocks_per_sm = launch-bounds variant. */
+int  tsc_kernel_variant(tsc_handle h, int32_t *fixed_capacity, int32_t *global_workspace, int32_t *blocks_per_sm);
 
 #ifdef __cplusplus
 }

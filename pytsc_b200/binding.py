@@ -24,7 +24,8 @@ SYMBOLS = ("tsc_abi_version", "tsc_last_error", "tsc_create", "tsc_destroy", "ts
            "tsc_snapshot", "tsc_load_snapshot", "tsc_check", "tsc_counters", "tsc_launch_count", "tsc_kernel_info",
            "tsc_debug_timing", "tsc_controller_act", "tsc_kernel_variant", "tsc_reset_replicas", "tsc_state_bytes",
            "tsc_save_state", "tsc_load_state", "tsc_reset_flows", "tsc_reset_replicas_flows", "tsc_host_register",
-           "tsc_host_unregister", "tsc_env_step_registered", "tsc_host_packet_bytes", "tsc_max_spanning_tree")
+           "tsc_host_unregister", "tsc_env_step_registered", "tsc_host_packet_bytes", "tsc_max_spanning_tree",
+           "tsc_env_step_registered_begin", "tsc_env_step_registered_wait", "tsc_host_threads")
 
 # tsc_env_step / tsc_controller_act controller codes (include/tsc_b200.h)
 CONTROLLERS = {"external": 0, "fixed_time": 1, "phase_index": 2, "greedy": 3, "max_pressure": 4, "sotl": 5, "random": 6}
@@ -72,6 +73,9 @@ def load_library(path=None):
     L.tsc_host_register.argtypes = [vp, vp, vp, vp, vp]
     L.tsc_host_unregister.argtypes = [vp]
     L.tsc_env_step_registered.argtypes = [vp, vp, i32, i32, i32]
+    L.tsc_env_step_registered_begin.argtypes = [vp, vp, i32, i32, i32]
+    L.tsc_env_step_registered_wait.argtypes = [vp]
+    L.tsc_host_threads.argtypes = [vp, i32]
     L.tsc_host_packet_bytes.argtypes = [vp]
     L.tsc_host_packet_bytes.restype = C.c_int64
     L.tsc_max_spanning_tree.argtypes = [vp, vp, vp, vp]
@@ -257,10 +261,14 @@ class Engine:
         self._check(self.lib.tsc_env_step_host(self.h, _np_ptr(actions), controller, controller_arg, n_ticks,
                                                _np_ptr(obs), _np_ptr(reward), _np_ptr(mask), _np_ptr(reward_global)))
 
-    def host_register(self, obs=None, reward=None, mask=None, reward_global=None):
+    def host_register(self, obs=None, reward=None, mask=None, reward_global=None, threads=0):
         """Register the caller's HOST result arrays (numpy, C-contiguous) for ``env_step_registered``: one launch
-        per step, compact per-replica packets over PCIe, rows finished by host threads (``tsc_host_register``).
+        per step, compact per-replica packets over PCIe, rows finished by host threads (``tsc_host_register``;
+        ``threads`` = 0 lets the library choose).
         The arrays must stay alive and must not be written by the caller until ``host_unregister``."""
+        n = self.lib.tsc_host_threads(self.h, int(threads))      # (returns the worker count that will be used)
+        if n < 0:
+            self._check(n)
         d = self.dims
         for arr, shape, dt in ((obs, (d["B"], d["A"], d["obs_dim"]), np.float32), (reward, (d["B"], d["A"]), np.float32),
                                (mask, (d["B"], d["A"], d["n_actions"]), np.uint8), (reward_global, (d["B"],), np.float32)):
@@ -278,6 +286,19 @@ class Engine:
         if actions is not None:
             assert actions.dtype == np.int32 and actions.shape == (self.B, self.A) and actions.flags["C_CONTIGUOUS"]
         self._check(self.lib.tsc_env_step_registered(self.h, _np_ptr(actions), controller, controller_arg, n_ticks))
+
+    def env_step_registered_begin(self, actions=None, n_ticks=5, controller=0, controller_arg=0):
+        """First half of ``env_step_registered``: queue the action copy and the launch, wake the host workers, return.
+        ``actions`` must stay untouched until ``env_step_registered_wait``."""
+        if actions is not None:
+            assert actions.dtype == np.int32 and actions.shape == (self.B, self.A) and actions.flags["C_CONTIGUOUS"]
+        self._inflight_actions = actions
+        self._check(self.lib.tsc_env_step_registered_begin(self.h, _np_ptr(actions), controller, controller_arg, n_ticks))
+
+    def env_step_registered_wait(self):
+        """Second half: on return the registered arrays hold the step's results."""
+        self._check(self.lib.tsc_env_step_registered_wait(self.h))
+        self._inflight_actions = None
 
     def max_spanning_tree(self, density_map):
         """``MetricsParser.mst`` for every replica: float64 [B, A, A] device tensor in (as the ``density_map`` output), the
@@ -344,5 +365,5 @@ class Engine:
         self._check(self.lib.tsc_kernel_info(self.h, *[C.byref(x) for x in v]))
         w = [C.c_int32() for _ in range(3)]
         self._check(self.lib.tsc_kernel_variant(self.h, *[C.byref(x) for x in w]))
-        return dict(zip(("smem_bytes", "threads", "grid", "regs", "staged", "global_workspace", "blocks_per_sm"),
+        return dict(zip(("smem_bytes", "threads", "grid", "regs", "fixed_capacity", "global_workspace", "blocks_per_sm"),
                         [x.value for x in v + w]))

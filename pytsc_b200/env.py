@@ -173,30 +173,42 @@ class BatchedTrafficSignalNetwork:
         return self.out["reward_global"], self.episode_over, self.get_env_info()
 
     # ---- the same step through HOST arrays (what a CPU-side trainer / the reference's callers hold) ---------
-    def register_host_buffers(self):
+    def register_host_buffers(self, threads=0):
         """Allocate and register the host result arrays of ``step_host``: ``obs`` float32 [B, A, obs_dim],
         ``reward`` [B, A], ``mask`` uint8 [B, A, n_actions], ``reward_global`` [B] (numpy).  Lane-feature
-        observations only."""
+        observations only.  ``threads``: host workers that finish the rows (0 = automatic)."""
         d = self.engine.dims
         self._host = {"obs": np.empty((d["B"], d["A"], d["obs_dim"]), np.float32),
                       "reward": np.empty((d["B"], d["A"]), np.float32),
                       "mask": np.empty((d["B"], d["A"], d["n_actions"]), np.uint8),
                       "reward_global": np.empty((d["B"],), np.float32)}
-        self.engine.host_register(**self._host)
+        self.engine.host_register(threads=threads, **self._host)
         return self._host
 
     def step_host(self, actions=None, controller=None, green_time=25, seed=0, theta=3, mu=4, phi_min=5):
         """``step`` with numpy int32 [B, A] actions in and the registered numpy arrays out (synchronous): one
         launch, < 1 KB per replica over PCIe, rows finished by host threads while the launch runs."""
+        self.step_host_begin(actions, controller, green_time, seed, theta, mu, phi_min)
+        return self.step_host_wait()
+
+    def step_host_begin(self, actions=None, controller=None, green_time=25, seed=0, theta=3, mu=4, phi_min=5):
+        """First half of ``step_host``: returns as soon as the launch is queued.  With two environments of B / 2
+        replicas stepped alternately (``a.step_host_begin(..); b.step_host_wait(); policy(b); b.step_host_begin(..);
+        a.step_host_wait(); ...``) the host policy and the row finishing of one half overlap the launch of the other
+        (double-buffered sampling).  ``actions`` must stay untouched until ``step_host_wait``."""
         if self._host is None:
             self.register_host_buffers()
         if controller is None or controller == "external":
-            self.engine.env_step_registered(actions, n_ticks=self.delta_time, controller=0)
+            self.engine.env_step_registered_begin(actions, n_ticks=self.delta_time, controller=0)
         elif controller == "phase_index":
-            self.engine.env_step_registered(actions, n_ticks=self.delta_time, controller=CONTROLLERS["phase_index"])
+            self.engine.env_step_registered_begin(actions, n_ticks=self.delta_time, controller=CONTROLLERS["phase_index"])
         else:
             arg = {"fixed_time": green_time, "sotl": sotl_arg(theta, mu, phi_min)}.get(controller, seed)
-            self.engine.env_step_registered(None, n_ticks=self.delta_time, controller=CONTROLLERS[controller], controller_arg=arg)
+            self.engine.env_step_registered_begin(None, n_ticks=self.delta_time, controller=CONTROLLERS[controller], controller_arg=arg)
+
+    def step_host_wait(self):
+        """Second half of ``step_host``: the registered numpy arrays hold the step's results on return."""
+        self.engine.env_step_registered_wait()
         self._tick += self.delta_time
         return self._host["reward_global"], self.episode_over, self._host
 

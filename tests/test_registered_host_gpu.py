@@ -111,6 +111,52 @@ def test_env_step_host_api(cuda_lib):
     a.close(); b.close()
 
 
+def test_double_buffered_halves_equal_one_batch(cuda_lib):
+    """``step_host_begin`` / ``step_host_wait``: two environments of B / 2 replicas stepped alternately (both launches in
+    flight while the host prepares the next actions) hold, half by half, the rows of one synchronous batch of B;
+    pairing errors are reported."""
+    import torch
+    from pytsc_b200 import BatchedTrafficSignalNetwork
+    from pytsc_b200.binding import TscError
+    kw = dict(signal=dict(observation_space="lane_features", reward_function="max_pressure",
+                          action_space="phase_selection", round_robin=False), gpu=dict(vehicle_capacity=640))
+    B = 300
+    whole = BatchedTrafficSignalNetwork("hangzhou_4_4", n_replicas=B, **kw)
+    halves = [BatchedTrafficSignalNetwork("hangzhou_4_4", n_replicas=B // 2, **kw) for _ in range(2)]
+    outs = [h.register_host_buffers(threads=2) for h in halves]
+    with pytest.raises(TscError):
+        halves[0].step_host_wait()                       # nothing in flight
+    rng = np.random.RandomState(5)
+    acts = [np.zeros((B // 2, whole.n_agents), np.int32) for _ in range(2)]
+
+    def draw(k):                                          # every replica its own valid actions, from its own previous mask
+        m = outs[k]["mask"] if draw.started else np.ones_like(outs[k]["mask"])
+        first_allowed = m.argmax(-1)
+        last_allowed = m.shape[-1] - 1 - m[..., ::-1].argmax(-1)
+        acts[k][...] = np.where(rng.rand(*first_allowed.shape) < 0.5, first_allowed, last_allowed)
+    draw.started = False
+    draw(0); halves[0].step_host_begin(acts[0])
+    for t in range(60):
+        draw(1); halves[1].step_host_begin(acts[1])
+        if t == 0:
+            with pytest.raises(TscError):
+                halves[1].step_host_begin(acts[1])        # one step per handle in flight
+        sent = [acts[0].copy(), acts[1].copy()]
+        halves[0].step_host_wait()
+        halves[1].step_host_wait()
+        draw.started = True
+        whole.step(torch.from_numpy(np.concatenate(sent)).cuda())
+        ref = {"obs": whole.get_observations().cpu().numpy(), "reward": whole.get_rewards().cpu().numpy(),
+               "mask": whole.get_action_mask().cpu().numpy(), "reward_global": whole.get_reward().cpu().numpy()}
+        for k in range(2):
+            for name, arr in ref.items():
+                assert np.array_equal(arr[k * (B // 2):(k + 1) * (B // 2)], outs[k][name]), (t, k, name)
+        draw(0); halves[0].step_host_begin(acts[0])
+    halves[0].step_host_wait()
+    for e in [whole] + halves:
+        e.check(); e.close()
+
+
 def test_bad_phase_is_reported(cuda_lib):
     """tsc_set_phase with a light phase the signal does not have sets a sticky flag (TSC_EINVAL), readable
     without a sync through the ``err`` output; tsc_init_program validates on the host."""
