@@ -108,9 +108,9 @@ struct RepHeader {   // 64 bytes, first thing in every replica image
     long long cum_tt;     // sum over finished vehicles of (finish tick - creation tick)
     long long fin_enter;  // sum of creation ticks of finished vehicles
     u32 err;              // sticky error bits
-    int n_ent;            // scratch: vehicles changing drivable (or finishing) this tick
-    int n_x;              // scratch: vehicles deferred to the cross phase this tick
-    int n_h, n_a;         // scratch: head vehicles / vehicles in an intersection zone this tick
+    int n_ent;            // scratch: vehicles changing drivable (or finishing) this tick  } even ticks; odd ticks count in
+    int n_x;              // scratch: vehicles deferred to the cross phase this tick       } n_h / n_a (tick_counters)
+    int n_h, n_a;         // scratch: the same two counters of odd ticks
     int n_new;            // scratch: n_slots after this tick's spawns
     int flow_set;         // which of the scenario's flow sets this replica runs (set at reset)
     int pad;
@@ -125,6 +125,7 @@ static_assert(sizeof(RepHeader) == 64, "RepHeader must be 64 bytes");
 #define NONE16 0xFFFFu        // "no vehicle" in the per-drivable lists
 #define PJ_MOVER 0x80u        // pj[] bit: the vehicle leaves its drivable this tick (set by its decision, cleared by the list surgery)
 #define HOLE_MAX 32           // finished vehicles leave holes; the slots are compacted once this many have piled up
+#define HOLE_MIN_ROUND 6      // ... or this many, when squeezing them out saves a round of the per-vehicle passes
 
 struct Layout {
     int Vcap;              // vehicle slots (running vehicles + holes)
@@ -482,6 +483,12 @@ __device__ bool can_pass(const DevScn &S, const Ctx &c, int me, const double *T,
     return yield == -1;
 }
 
+// The two per-tick list counters alternate between two pairs of header words by tick parity: a tick's first phase zeroes
+// the pair of the NEXT tick (idle for the whole of this one), so no reset ever shares a phase with a reader or a writer.
+// (the header's tick is advanced inside the list surgery: only the decisions may read the parity from there)
+__device__ __forceinline__ int *mover_counter(const Ctx &c, int tick) { return (tick & 1) ? &c.h->n_h : &c.h->n_ent; }
+__device__ __forceinline__ int *cross_counter(const Ctx &c, int tick) { return (tick & 1) ? &c.h->n_a : &c.h->n_x; }
+
 // Commit one vehicle's decision into the tick's next-state buffers: clamp the speed, advance along the
 // route, and register the move if it leaves its drivable (A.4).
 __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y, Ctx &c, int i, const double *T, int d, int rp,
@@ -507,7 +514,12 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
         c.pj[i] |= PJ_MOVER;
         atomicAdd((unsigned *) (c.leave + (d & ~3)), 1u << (8 * (d & 3)));
         if (!end) atomicAdd((unsigned *) (c.ent + (dd & ~3)), 1u << (8 * (dd & 3)));
-        const int k = atomicAdd(&c.h->n_ent, 1);
+#ifdef TSC_MOVER_PREFETCH
+        // what the list surgery will read for this mover, on its way into L1 while the other decisions go on
+        if (end) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.veh_tick + c.vid[i]));
+        else asm volatile("prefetch.global.L1 [%0];" ::"l"(S.route_seq + q + 1));
+#endif
+        const int k = atomicAdd(mover_counter(c, c.h->tick), 1);
         if (k < Y.ent_cap) {
             c.mv_slot[k] = (u16) i; c.mv_to[k] = end ? (u16) NONE16 : (u16) dd; c.mv_q[k] = q; c.mv_pj[k] = hops > 1 ? 1 : 0;
         } else atomicOr(&c.h->err, ERR_ENT_OVERFLOW);
@@ -671,7 +683,14 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     }
     {   // holes left by finished vehicles are squeezed out now and then (uniform decision: every thread reads the same header)
         const int ns = c.h->n_slots, holes = ns - c.h->n_running;
-        if (holes >= HOLE_MAX || (holes > 0 && ns + S.n_spawn_lanes > Y.Vcap)) {
+        // ... and as soon as a few of them cost every warp-owned pass over the slots an extra round (a round of NT slots
+        // takes as long with one vehicle in it as with NT)
+#ifndef TSC_NO_ROUND_COMPACTION
+        const bool extra_round = holes >= HOLE_MIN_ROUND && (ns + NT - 1) / NT > (ns - holes + NT - 1) / NT;
+#else
+        const bool extra_round = false;
+#endif
+        if (holes >= HOLE_MAX || extra_round || (holes > 0 && ns + S.n_spawn_lanes > Y.Vcap)) {
             compact_slots<NT>(S, Y, c);
             pt_mark(c, PT_COMPACT);
         }
@@ -684,6 +703,15 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     //      before the vehicle is in place; the cache is refilled with ONE 16-byte load whose latency the rest
     //      of the work hides.  The first warp serves the spawn lanes 32 at a time: a new vehicle's slot is
     //      n_slots + its rank among the lanes that spawn (ballot), so slot numbers do not depend on timing. ----
+    // fused (-DTSC_FUSED_SPAWN; measured slower, 0.703 vs 0.690 ms, so off): when handleWaiting touches nothing the decisions
+    // of the other vehicles read (spawn_pure, see below), the first warp also decides for the vehicles it has just let in, and
+    // no block-wide barrier separates this phase from the decisions
+#ifdef TSC_FUSED_SPAWN
+    const bool fused = S.spawn_pure != 0;
+#else
+    const bool fused = false;
+#endif
+    int n_new_w0 = n_old;      // (first warp) slots in use after this tick's spawns
     if (tid < 32) {
         int base = n_old, spawned = 0;
         for (int s0 = 0; s0 < S.n_spawn_lanes; s0 += 32) {
@@ -732,8 +760,10 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
         for (int o = 16; o > 0; o >>= 1) spawned += __shfl_xor_sync(0xffffffffu, spawned, o);
         if (tid == 0) {
             c.h->n_new = min(base, Y.Vcap); c.h->n_running += spawned;
-            c.h->n_ent = 0; c.h->n_x = 0;      // this tick's list counters (nobody touches them before the barrier below)
+            if (tick & 1) { c.h->n_ent = 0; c.h->n_x = 0; } else { c.h->n_h = 0; c.h->n_a = 0; }      // the NEXT tick's list counters
         }
+        n_new_w0 = min(base, Y.Vcap);
+        __syncwarp();
     }
     // ---- head vehicles (no vehicle ahead on their drivable) of the vehicles that were here before this tick, gathered
     //      warp-locally: look-ahead leader + gap (A.7).  Each WARP owns the slots of its 32-slot chunks.  When no spawn
@@ -762,10 +792,11 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
             head_look_ahead<ONE_T>(S, c, i, &leader, &gap);
             c.nblk[i] = (short) leader; c.npos[i] = gap;
         }
+        __syncwarp();      // the chunks' owners read these in the decisions
     }
-    __syncthreads();
+    if (!fused) __syncthreads();
     pt_mark(c, PT_SPAWN);
-    const int n_slots = c.h->n_new;
+    int *const xctr = cross_counter(c, tick);
 
     // ---- getAction.  Every decision reads only the state the tick started from (positions, lists, blockers) and
     //      writes the vehicle's own entries of the next-state buffers, so the whole of it runs without a block-wide
@@ -775,11 +806,16 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     {
         const int lane = tid & 31, w = tid >> 5, NW = NT / 32;
         const unsigned lt = (1u << lane) - 1u;
-        const int n_chunks = (n_slots + 31) >> 5;
+        // fused: every warp its chunks of the vehicles that were here before the tick, then the first warp the new ones;
+        // otherwise (after the barrier) the chunks cover the new ones as well
+        const int n_lim = fused ? n_old : c.h->n_new;
+        const int n_chunks = (n_lim + 31) >> 5;
+        const int own = w < n_chunks ? (n_chunks - w + NW - 1) / NW : 0;
+        const int extra = (fused && w == 0) ? (n_new_w0 - n_old + 31) >> 5 : 0;
         // (a vehicle that left a waiting buffer onto an empty lane this tick is a head too: its look-ahead runs here)
-        for (int ch = w; ch < n_chunks; ch += NW) {
-            const int i = (ch << 5) + lane;
-            const bool valid = i < n_slots && c.vid[i] >= 0;
+        for (int k = 0; k < own + extra; ++k) {
+            const int i = k < own ? ((w + k * NW) << 5) + lane : n_old + ((k - own) << 5) + lane;
+            const bool valid = k < own ? (i < n_lim && c.vid[i] >= 0) : (i < n_new_w0);
             const double *T = c.tmpl;
             u32 dnv = 0;
             int d = 0;
@@ -833,7 +869,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
             const unsigned mx = __ballot_sync(0xffffffffu, needx);
             if (mx) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&c.h->n_x, __popc(mx));
+                if (lane == 0) base = atomicAdd(xctr, __popc(mx));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (needx) { c.clist[base + __popc(mx & lt)] = (u16) i; c.nspd[i] = ns; c.npos[i] = vi; }
             }
@@ -845,6 +881,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     }
     __syncthreads();
     pt_mark(c, PT_PHASE1);
+    const int n_slots = c.h->n_new;
 
     // ---- getAction, cross phase: Cross::canPass for every cross ahead of every listed vehicle.  canPass has no side
     //      effects, so all crosses are evaluated at once and the first refusal in link order is the sequential scan of
@@ -852,7 +889,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     //      per vehicle, one lane per cross, all listed vehicles at once; G = the widest group that still gives every
     //      listed vehicle its own group in one round ----
     {
-        const int n_x = c.h->n_x;
+        const int n_x = *xctr;
         const int G = n_x * 16 <= NT ? 16 : (n_x * 8 <= NT ? 8 : (n_x * 4 <= NT ? 4 : 2));
         const int lane = tid & 31, sl = lane & (G - 1);
         const unsigned gm = ((1u << G) - 1u) << (lane & ~(G - 1));
@@ -902,7 +939,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     // (the barrier also tells every thread, uniformly, whether any decision raised a sticky error)
     const bool bail = TICK_SYNC_ERR(c.h->err != 0);
 #ifdef TSC_PHASE_TIMING
-    if (c.pt && tid == 0) atomicAdd(c.pt + PT_NX, (unsigned long long) c.h->n_x);
+    if (c.pt && tid == 0) atomicAdd(c.pt + PT_NX, (unsigned long long) *xctr);
 #endif
     pt_mark(c, PT_PHASE2);
 
@@ -911,7 +948,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
     //      Leaving: movers are a prefix of their drivable's list (FIFO); the mover at its head walks the prefix
     //      and hands the head over.  Entering (after a barrier): entrants go behind the vehicles that stay,
     //      ordered by new distance (descending, ties by creation id); one thread per entered drivable. ----
-    const int n_mv = c.h->n_ent;      // (stable until the next tick's first phase resets it)
+    const int n_mv = *mover_counter(c, tick);      // (stable: the next tick counts in the other pair)
     if (bail) {   // mover list overflow / no slot left: keep the old state; the sticky flag reports it
         __syncthreads();
         if (tid == 0) { c.h->tick = tick + 1; c.h->n_slots = n_slots; }      // (vehicles that did enter before the slots ran out stay listed)

@@ -1,18 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out; : > gpurun_out/ab.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
-run() {
-  name=$1; envs=$2; shift 2
-  ( env $envs timeout 300 python bench.py --steps 60 --warmup 8 --no-cpu-baseline "$@" 2> gpurun_out/ab_$name.err ) | python -c "
-import json,sys
-try:
-    d=json.loads(sys.stdin.read()); k=d['config']['kernel']
-    print('$name: dev ms %.4f  e2e ms %.4f  match %s  nt %d x %d regs %d smem %d' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['matches_device_leg'], k['threads'], k['blocks_per_sm'], k['regs'], k['smem_bytes']))
-except Exception as e:
-    print('$name failed', e)
-" | tee -a gpurun_out/ab.txt
-}
-for rep in 1 2; do
-run vc "X=1"
-run novc "TSC_B200_FIXED_CAPACITY=0"
-done
+mkdir -p gpurun_out
+TSC_B200_LIB=$PWD/tools/ab/lib_nfrc.so timeout 600 python -m pytest tests/test_engine_gpu.py tests/test_episode_gpu.py tests/test_edge_gpu.py -m gpu -x -q > gpurun_out/pytest_engine.log 2>&1; tail -5 gpurun_out/pytest_engine.log
+AB_LIBS="${AB_LIBS:-sb nf nfrc rc}" bash tools/gpu_ab_core.sh

@@ -11,19 +11,22 @@ run() {   # name, env assignments, args...
     echo "$tool $name rc=$rc :: $(grep -E 'sanitize_case ok' $log | head -1 | cut -c1-160) :: $(grep -E 'RACECHECK SUMMARY|ERROR SUMMARY' $log | tail -1)" >> $out/summary.txt
   done
 }
-run t256x4            "X=1" --capacity 600
+if [ -n "$SANITIZE_ALL" ]; then
 run t192x4            "TSC_B200_THREADS=192" --capacity 600
 run t192x5            "TSC_B200_THREADS=192 TSC_B200_MIN_BLOCKS=5" --capacity 560
 run t160x5            "TSC_B200_THREADS=160" --capacity 560
-run t256x3            "X=1" --capacity 1200
-run t384x2            "X=1" --capacity 1560
 run t256x2            "TSC_B200_THREADS=256" --capacity 1560
-run t512              "X=1" --capacity 2000
-run gmem1024          "TSC_B200_GMEM=1" --capacity 600
 run stage_cp_async    "TSC_B200_ASYNC_STAGE=1" --capacity 600
 run stage_plain       "TSC_B200_ASYNC_STAGE=0" --capacity 600
 run ctl_greedy        "X=1" --capacity 600 --controller greedy
-run ctl_max_pressure  "X=1" --capacity 600 --controller max_pressure --obs position_matrix
 run ctl_sotl          "X=1" --capacity 600 --controller sotl
-run registered_host   "X=1" --capacity 600 --registered
+fi
+run t256x4_fixed672   "X=1" --capacity 640
+run t256x4_generic    "X=1" --capacity 600
+run t256x3_fixed1184  "X=1" --capacity 1150
+run t384x2_fixed1568  "X=1" --capacity 1530
+run t512              "X=1" --capacity 2000
+run gmem1024          "TSC_B200_GMEM=1" --capacity 600
+run ctl_max_pressure  "X=1" --capacity 600 --controller max_pressure --obs position_matrix
+run registered_host   "X=1" --capacity 640 --registered
 cat $out/summary.txt
