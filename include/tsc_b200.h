@@ -359,8 +359,10 @@ int  tsc_kernel_info(tsc_handle h, int32_t *smem_bytes, int32_t *threads, int32_
 
 /* Which variant of the step kernel the handle runs: fixed_capacity = 1 when the kernel was compiled for exactly
  * this handle's vehicle capacity (the bench workloads' capacities: the per-vehicle columns of the working set sit at
- * compile-time offsets; TSC_B200_FIXED_CAPACITY=0 forces the generic build); global_workspace = 1 when the
- * replica's working set does not fit shared memory and lives in a global-memory (L2-resident) workspace;
+ * compile-time offsets; TSC_B200_FIXED_CAPACITY=0 forces the generic build); global_workspace != 0 when the
+ * replica's working set does not fit shared memory: 2 = its per-vehicle columns live in a global-memory
+ * (L2-resident) workspace, the per-drivable arrays, scratch lists and header in shared memory; 1 = all of it
+ * in the workspace (TSC_B200_GMEM_META_SHARED=0, or more drivables than shared memory holds);
  * blocks_per_sm = launch-bounds variant. */
 int  tsc_kernel_variant(tsc_handle h, int32_t *fixed_capacity, int32_t *global_workspace, int32_t *blocks_per_sm);
 

@@ -135,6 +135,7 @@ struct Layout {
     int async_stage;       // staging of the image columns (TSC_B200_ASYNC_STAGE): 2 bulk asynchronous copies + mbarrier, 1 cp.async, 0 plain
     int prefetch_next;     // 1: L2 prefetch of the block's next replica image during the step
     int warp_surgery;      // 1: up to 32 movers do both halves of the list surgery inside the first warp (TSC_B200_WARP_SURGERY)
+    int meta_shared;       // global-memory variant: everything from o_cnt on (per-drivable arrays, scratch, header) in shared memory
     // Per-vehicle columns first: their offsets depend on the capacity and the block size alone (v_offsets), so a kernel
     // built for one capacity has them as compile-time constants.  The hot columns have identical byte offsets in the HBM
     // image and in the working set.
@@ -215,6 +216,7 @@ __device__ __forceinline__ int trunc_int_x86(double x) {
 
 struct Ctx {
     RepHeader *h;
+    unsigned char *vb;    // base of the per-vehicle columns (shared memory, or the block's global-memory workspace)
     // per drivable: vehicle count and the ends of its list (front = head, back = tail)
     u16 *cnt, *head, *tail, *wq;
     u8 *leave, *ent;      // per drivable: vehicles leaving / entering this tick (bytes, counted four to an atomic word)
@@ -260,7 +262,7 @@ __device__ __forceinline__ void pt_mark(Ctx &c, int k) {
 // The kinematics ping-pong: which buffers are "current" and which "next" follows from the parity alone, so a tick ends
 // by flipping one integer (swapping six pointers that live on the stack cost a dependent local load + store each).
 __device__ __forceinline__ void set_pingpong(const Layout &Y, Ctx &c) {
-    unsigned char *const smem = (unsigned char *) c.h;
+    unsigned char *const smem = c.vb;
     const bool p = c.par != 0;
     c.pos = (double *) (smem + (p ? Y.o_npos : Y.o_pos)); c.npos = (double *) (smem + (p ? Y.o_pos : Y.o_npos));
     c.spd = (double *) (smem + (p ? Y.o_nspd : Y.o_spd)); c.nspd = (double *) (smem + (p ? Y.o_spd : Y.o_nspd));
@@ -1650,24 +1652,29 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
     const Layout &Y = Yl;
     extern __shared__ __align__(16) unsigned char smem_block[];
     unsigned char *const smem = GMEM ? a.workspace + (size_t) blockIdx.x * (size_t) ((Y.smem_bytes + 255) & ~255) : smem_block;
+    // GMEM with meta_shared (the usual case: the per-vehicle columns of a very large replica do not fit shared memory, its
+    // per-drivable / per-signal arrays, scratch lists and header do): everything from o_cnt on lives in shared memory
+    const bool hyb = GMEM && Y.meta_shared;
+    unsigned char *const msm = hyb ? smem_block - Y.o_cnt : smem;
     const int tid = threadIdx.x;
     Ctx c;
-    c.h = (RepHeader *) smem;
-    c.cnt = (u16 *) (smem + Y.o_cnt); c.head = (u16 *) (smem + Y.o_head); c.tail = (u16 *) (smem + Y.o_tail);
-    c.wq = (u16 *) (smem + Y.o_wq);
-    c.sraw = smem + Y.o_sraw; c.scur = smem + Y.o_scur; c.schg = smem + Y.o_schg; c.stop = (int *) (smem + Y.o_stop);
+    c.vb = smem;
+    c.h = hyb ? (RepHeader *) (smem_block + (Y.smem_bytes - Y.o_cnt)) : (RepHeader *) smem;
+    c.cnt = (u16 *) (msm + Y.o_cnt); c.head = (u16 *) (msm + Y.o_head); c.tail = (u16 *) (msm + Y.o_tail);
+    c.wq = (u16 *) (msm + Y.o_wq);
+    c.sraw = msm + Y.o_sraw; c.scur = msm + Y.o_scur; c.schg = msm + Y.o_schg; c.stop = (int *) (msm + Y.o_stop);
     c.rpos = (int *) (smem + Y.o_rpos); c.vid = (int *) (smem + Y.o_vid);
     c.lead = (u16 *) (smem + Y.o_lead); c.foll = (u16 *) (smem + Y.o_foll); c.pj = smem + Y.o_pj;
     c.dn = (u32 *) (smem + Y.o_dn); c.xlist = (u16 *) (smem + Y.o_xlist);
     c.clist = (u16 *) (smem + Y.o_drv);     // the image's u16 drivable column is expanded into dn[]; its room is reused
-    c.leave = smem + Y.o_leave; c.ent = smem + Y.o_ent; c.fresh = smem + Y.o_fresh;
-    c.mv_slot = (u16 *) (smem + Y.o_mvslot); c.mv_to = (u16 *) (smem + Y.o_mvto); c.mv_q = (int *) (smem + Y.o_mvq); c.mv_pj = smem + Y.o_mvpj;
-    c.scan = (int *) (smem + Y.o_scan);
-    c.avail = (u32 *) (smem + Y.o_avail);
-    c.sp_rec = (int *) (smem + Y.o_spawn); c.sp_lane = c.sp_rec + 4 * S.n_spawn_lanes; c.sp_base = c.sp_lane + S.n_spawn_lanes;
+    c.leave = msm + Y.o_leave; c.ent = msm + Y.o_ent; c.fresh = msm + Y.o_fresh;
+    c.mv_slot = (u16 *) (msm + Y.o_mvslot); c.mv_to = (u16 *) (msm + Y.o_mvto); c.mv_q = (int *) (msm + Y.o_mvq); c.mv_pj = msm + Y.o_mvpj;
+    c.scan = (int *) (msm + Y.o_scan);
+    c.avail = (u32 *) (msm + Y.o_avail);
+    c.sp_rec = (int *) (msm + Y.o_spawn); c.sp_lane = c.sp_rec + 4 * S.n_spawn_lanes; c.sp_base = c.sp_lane + S.n_spawn_lanes;
     for (int s = tid; s < S.n_spawn_lanes; s += NT) c.sp_lane[s] = __ldg(S.spawn_lane + s);
     if (ONE_T || S.T <= SMEM_TEMPLATES) {
-        double *ts = (double *) (smem + Y.o_tmpl);
+        double *ts = (double *) (msm + Y.o_tmpl);
         for (int k = tid; k < S.T * TD_STRIDE; k += NT) ts[k] = __ldg(S.tmpl + k);
         c.tmpl = ts;
     } else c.tmpl = S.tmpl;
@@ -1697,8 +1704,8 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 const unsigned n8 = (n0 * 8 + 15) & ~15, n4 = (n0 * 4 + 15) & ~15, n2 = (n0 * 2 + 15) & ~15, n1 = (n0 + 15) & ~15;
                 fence_proxy_async();      // whatever the block read or wrote here before, ahead of the copy engine's writes
                 mbar_expect_tx(&stage_bar, (unsigned) sizeof(RepHeader) + (unsigned) Y.meta_bytes + 2 * n8 + 2 * n4 + 3 * n2 + n1);
-                bulk_g2s(smem, img, (unsigned) sizeof(RepHeader), &stage_bar);
-                bulk_g2s(smem + Y.o_cnt, img + Y.o_imeta, (unsigned) Y.meta_bytes, &stage_bar);
+                bulk_g2s(c.h, img, (unsigned) sizeof(RepHeader), &stage_bar);
+                bulk_g2s(msm + Y.o_cnt, img + Y.o_imeta, (unsigned) Y.meta_bytes, &stage_bar);
                 bulk_g2s(smem + Y.o_pos, img + Y.o_pos, n8, &stage_bar);
                 bulk_g2s(smem + Y.o_spd, img + Y.o_spd, n8, &stage_bar);
                 bulk_g2s(smem + Y.o_rpos, img + Y.o_rpos, n4, &stage_bar);
@@ -1709,15 +1716,15 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
                 bulk_g2s(smem + Y.o_pj, img + Y.o_pj, n1, &stage_bar);
             }
             {   // meanwhile: per-tick counters start from zero (the list surgery of every tick leaves them that way)
-                int4 *z = (int4 *) (smem + Y.o_leave);
+                int4 *z = (int4 *) (msm + Y.o_leave);
                 const int nz = (Y.o_fresh - Y.o_leave + ((S.L + 15) & ~15)) / 16;      // leave, ent, fresh are adjacent
                 for (int k = tid; k < nz; k += NT) z[k] = make_int4(0, 0, 0, 0);
             }
             mbar_wait(&stage_bar, stage_parity);
             stage_parity ^= 1u;
         } else {
-            copy16(smem, img, (int) sizeof(RepHeader), tid, NT);
-            copy16(smem + Y.o_cnt, img + Y.o_imeta, Y.meta_bytes, tid, NT);
+            copy16(c.h, img, (int) sizeof(RepHeader), tid, NT);
+            copy16(msm + Y.o_cnt, img + Y.o_imeta, Y.meta_bytes, tid, NT);
             __syncthreads();
         }
         const int n_in = c.h->n_slots;
@@ -1745,7 +1752,7 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             }
         }
         if (!bulk) {   // per-tick counters start from zero (the list surgery of every tick leaves them that way)
-            int4 *z = (int4 *) (smem + Y.o_leave);
+            int4 *z = (int4 *) (msm + Y.o_leave);
             const int nz = (Y.o_fresh - Y.o_leave + ((S.L + 15) & ~15)) / 16;      // leave, ent, fresh are adjacent
             for (int k = tid; k < nz; k += NT) z[k] = make_int4(0, 0, 0, 0);
         }
@@ -1809,8 +1816,8 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             const int n = c.h->n_slots;
             if (tid == 0) {
                 const unsigned n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
-                bulk_s2g(img, smem, (unsigned) sizeof(RepHeader));
-                bulk_s2g(img + Y.o_imeta, smem + Y.o_cnt, (unsigned) Y.meta_bytes);
+                bulk_s2g(img, c.h, (unsigned) sizeof(RepHeader));
+                bulk_s2g(img + Y.o_imeta, msm + Y.o_cnt, (unsigned) Y.meta_bytes);
                 bulk_s2g(img + Y.o_pos, c.pos, n8);      // whichever buffer holds the current state
                 bulk_s2g(img + Y.o_spd, c.spd, n8);
                 bulk_s2g(img + Y.o_blk, c.blk, n2);
@@ -1830,8 +1837,8 @@ __global__ void __launch_bounds__(NT, MINB) tsc_step_kernel(const DevScn S, cons
             if (tid == 0) bulk_wait_read();
         } else if (!a.decide_only && (a.n_ticks > 0 || a.apply_actions || a.set_raw_phase || a.init_program >= 0)) {
             __syncthreads();      // retrieve's scratch lives in the next-state buffers; nothing below reads them
-            copy16(img, smem, (int) sizeof(RepHeader), tid, NT);
-            copy16(img + Y.o_imeta, smem + Y.o_cnt, Y.meta_bytes, tid, NT);
+            copy16(img, c.h, (int) sizeof(RepHeader), tid, NT);
+            copy16(img + Y.o_imeta, msm + Y.o_cnt, Y.meta_bytes, tid, NT);
             const int n = c.h->n_slots;
             const int n8 = (n * 8 + 15) & ~15, n4 = (n * 4 + 15) & ~15, n2 = (n * 2 + 15) & ~15, n1 = (n + 15) & ~15;
             if (a.n_ticks > 0) {
@@ -1945,6 +1952,7 @@ static step_kernel_t kernel_for(int nt, int minb, bool ctl, bool one_t, bool gme
         return ctl ? tsc_step_kernel<256, 3, true, false, true, VC_JINAN> : tsc_step_kernel<256, 3, false, false, true, VC_JINAN>;
     if (!gmem && one_t && nt == 384 && vc == VC_MANHATTAN)
         return ctl ? tsc_step_kernel<384, 2, true, false, true, VC_MANHATTAN> : tsc_step_kernel<384, 2, false, false, true, VC_MANHATTAN>;
+    if (gmem && one_t) return ctl ? tsc_step_kernel<1024, 1, true, true, true> : tsc_step_kernel<1024, 1, false, true, true>;
     if (gmem) return tsc_step_kernel<1024, 1, true, true, false>;
     if (!one_t) return nt >= 512 ? tsc_step_kernel<512, 1, true, false, false> : tsc_step_kernel<256, 2, true, false, false>;
     if (nt == 1024) return tsc_step_kernel<1024, 1, true, false, true>;      // 32 warps at 64 registers
@@ -2508,7 +2516,17 @@ static int create_body(tsc_engine *E, const tsc_scenario_t *s, int32_t n_replica
     E->kern = kernel_for(E->nt, E->minb, false, one_t, E->gmem, vc);
     E->kern_ctl = kernel_for(E->nt, E->minb, true, one_t, E->gmem, vc);
     E->fixed_capacity = E->kern != kernel_for(E->nt, E->minb, false, one_t, E->gmem, 0);
-    const int dyn_smem = E->gmem ? 0 : E->Y.smem_bytes;
+    E->Y.meta_shared = 0;
+    if (E->gmem) {
+        // the per-drivable / per-signal arrays, the scratch lists and the header of a replica whose vehicle columns do not fit
+        // shared memory usually do (16 x 16 grid: 12 480 drivables, ~ 150 KB): randomly read 2-byte entries and the tick's
+        // atomic counters are better off there than in L2 (TSC_B200_GMEM_META_SHARED=0: everything in the workspace)
+        const size_t need = (size_t) (E->Y.smem_bytes - E->Y.o_cnt) + sizeof(RepHeader);
+        bool want = need + 1024 + 64 <= prop.sharedMemPerBlockOptin;
+        if (const char *env = getenv("TSC_B200_GMEM_META_SHARED")) want = want && atoi(env) != 0;
+        E->Y.meta_shared = want ? 1 : 0;
+    }
+    const int dyn_smem = E->gmem ? (E->Y.meta_shared ? E->Y.smem_bytes - E->Y.o_cnt + (int) sizeof(RepHeader) : 0) : E->Y.smem_bytes;
     E->dyn_smem = dyn_smem;
     for (int k = 0; k < 2; ++k) {
         step_kernel_t kern = k ? E->kern_ctl : E->kern;
@@ -3196,7 +3214,7 @@ int tsc_kernel_info(tsc_handle E, int32_t *smem_bytes, int32_t *threads, int32_t
 int tsc_kernel_variant(tsc_handle E, int32_t *staged, int32_t *global_workspace, int32_t *blocks_per_sm) {
     if (!E) return fail(TSC_EINVAL, "null handle");
     if (staged) *staged = E->fixed_capacity ? 1 : 0;
-    if (global_workspace) *global_workspace = E->gmem ? 1 : 0;
+    if (global_workspace) *global_workspace = E->gmem ? (E->Y.meta_shared ? 2 : 1) : 0;
     if (blocks_per_sm) *blocks_per_sm = E->minb;
     return 0;
 }

@@ -100,7 +100,8 @@ def test_multi_tick_launch_equals_single_ticks(cuda_lib):
     ({"TSC_B200_ASYNC_STAGE": "1"}, 600, (256, 0, 4)),      # cp.async (16 bytes per request per thread)
     ({}, 2000, (512, 0, 1)),                                # one 512-thread block per SM
     ({"TSC_B200_THREADS": "1024"}, 2000, (1024, 0, 1)),     # the same with 32 warps at 64 registers
-    ({"TSC_B200_GMEM": "1"}, 600, (1024, 1, 1)),            # working set in a global-memory workspace
+    ({"TSC_B200_GMEM": "1"}, 600, (1024, 2, 1)),            # vehicle columns in a global-memory workspace, the rest in shared memory
+    ({"TSC_B200_GMEM": "1", "TSC_B200_GMEM_META_SHARED": "0"}, 600, (1024, 1, 1)),      # the whole working set in the workspace
 ])
 def test_kernel_variants_agree_with_oracle(cuda_lib, env, capacity, variant, monkeypatch):
     """The code paths an environment switch (or an unusual scenario) selects at tsc_create produce the

@@ -22,4 +22,5 @@ except Exception as e:
     print("$cfgn failed", e); print(open("gpurun_out/bench_$cfgn.err").read()[-1500:])
 PY
 done
+timeout 300 python tools/phase_timing.py 640 > gpurun_out/phase_timing.txt 2>&1; cat gpurun_out/phase_timing.txt
 ls -la gpurun_out | head -40
