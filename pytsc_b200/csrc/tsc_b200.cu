@@ -909,11 +909,25 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
             const int t1 = __ldg(&S.llinfo[ll].type);
             double vi = c.npos[i], ns = c.nspd[i];
             int blocker = -1;
+#ifdef TSC_CROSS_PIPELINE
+            // software-pipelined: the next round's entry is requested before this round's is evaluated
+            int4 e0 = make_int4(0, 0, 0, 0), e1 = e0, e2 = e0;
+            if (head.z + sl < head.w) { const int4 *src = (const int4 *) &S.cross[head.z + sl]; e0 = __ldg(src); e1 = __ldg(src + 1); e2 = __ldg(src + 2); }
+#endif
             for (int base = head.z; base < head.w; base += G) {
                 const int xi = base + sl;
                 bool refuse = false;
                 int foe = -1;
                 double dOn = 0.0;
+#ifdef TSC_CROSS_PIPELINE
+                CrossEntry X;
+                { int4 *dst = (int4 *) &X; dst[0] = e0; dst[1] = e1; dst[2] = e2; }
+                if (xi + G < head.w) { const int4 *src = (const int4 *) &S.cross[xi + G]; e0 = __ldg(src); e1 = __ldg(src + 1); e2 = __ldg(src + 2); }
+                if (xi < head.w) {
+                    dOn = X.dist;
+                    if (!(dOn < dts)) refuse = !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe);
+                }
+#else
                 if (xi < head.w) {
                     // (a per-tick "could this link announce a vehicle at all" bit per lane-link, tested before the entry is
                     // loaded, was measured: the cross phase got 1.2 k cycles per tick shorter, computing the bits cost 2.5 k)
@@ -924,6 +938,7 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
                     dOn = X.dist;
                     if (!(dOn < dts)) refuse = !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe);
                 }
+#endif
                 const unsigned m = __ballot_sync(gm, refuse) & gm;
                 if (m) {
                     const int src_lane = __ffs(m) - 1;
