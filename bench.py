@@ -342,6 +342,39 @@ def bind_to_gpu_numa_node(index):
         return f"unchanged ({type(e).__name__})", None
 
 
+def bind_to_rank_cpu_slice(local_rank, local_world):
+    """Several ranks on one host without a NUMA hint: give every rank its own contiguous share of the allowed CPUs, whole
+    physical cores where sysfs shows the hyper-thread siblings, so that one rank's policy thread and row-finishing workers
+    do not share cores with another rank's.  Returns a description (None: nothing done)."""
+    try:
+        if os.environ.get("BENCH_NO_AFFINITY") or local_world < 2:
+            return None
+        allowed = sorted(os.sched_getaffinity(0))
+        cores, seen = [], set()
+        for cpu in allowed:
+            if cpu in seen:
+                continue
+            sib = {cpu}
+            try:
+                txt = open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list").read().strip()
+                for part in txt.split(","):
+                    lo, _, hi = part.partition("-")
+                    sib.update(range(int(lo), int(hi or lo) + 1))
+            except Exception:
+                pass
+            sib &= set(allowed)
+            seen |= sib
+            cores.append(sorted(sib))
+        per = len(cores) // local_world
+        if per < 1:
+            return None
+        mine = [c for core in cores[local_rank * per:(local_rank + 1) * per] for c in core]
+        os.sched_setaffinity(0, mine)
+        return f"rank slice: {len(mine)} of {len(allowed)} cpus ({per} cores)"
+    except Exception as e:
+        return f"unchanged ({type(e).__name__})"
+
+
 class HostFixedTimePolicy:
     """FixedTimeController.get_action (controllers/controllers.py:39-54) for all B x A signals on the host, with its own
     copy of the programs' state: the e2e leg's stand-in for a user's policy.
@@ -427,6 +460,10 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device (the gpu backend has no CPU fallback)")
     torch.cuda.set_device(local)
     affinity, prev_affinity = bind_to_gpu_numa_node(local)
+    if prev_affinity is None:
+        sliced = bind_to_rank_cpu_slice(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+        if sliced:
+            affinity = sliced
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
@@ -532,8 +569,11 @@ def run_gpu_arm(args):
     # of one half overlap the launch of the other (every half's actions still follow its own previous observations).
     n_half = 1 if (args.e2e_halves < 2 or B < 2) else 2
     sizes = [B] if n_half == 1 else [B // 2, B - B // 2]
-    auto_threads = max(1, min(8, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    threads = int(os.environ.get("TSC_B200_HOST_THREADS", "0")) or auto_threads
+    # row-finishing workers: this process's CPUs (its rank slice, if it has one) minus one for the policy thread
+    my_cpus = len(os.sched_getaffinity(0))
+    if "rank slice" not in str(affinity):
+        my_cpus //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    threads = int(os.environ.get("TSC_B200_HOST_THREADS", "0")) or max(1, min(8, my_cpus - 1))
     threads_per_half = max(1, threads // n_half)
     halves = []
     for hb in sizes:

@@ -306,8 +306,8 @@ int  tsc_env_step_registered(tsc_handle h, const int32_t *actions_host, int32_t 
 /* The same step in two halves, for callers that keep several handles (or their own work) in flight -- e.g. two
  * handles of B/2 replicas each, stepped alternately so that the host policy and row finishing of one half overlap
  * the launch of the other (the double-buffered sampling loop of bench.py's e2e leg).  _begin queues the action
- * copy and the launch and wakes the worker threads, then returns; _wait finishes the caller's share of the rows,
- * waits for the workers and the stream, and reports errors.  A page-locked actions_host must stay untouched
+ * copy and the launch and wakes the worker threads, then returns; _wait waits for the workers (they
+ * finish all the rows) and the stream, and reports errors.  A page-locked actions_host must stay untouched
  * until _wait returns.  At most one step per handle in flight.  tsc_env_step_registered = _begin + _wait. */
 int  tsc_env_step_registered_begin(tsc_handle h, const int32_t *actions_host, int32_t controller,
                                    int32_t controller_arg, int32_t n_ticks);

@@ -909,36 +909,22 @@ __device__ bool engine_tick(const DevScn &S, const Layout &Y, Ctx &c, bool froze
             const int t1 = __ldg(&S.llinfo[ll].type);
             double vi = c.npos[i], ns = c.nspd[i];
             int blocker = -1;
-#ifdef TSC_CROSS_PIPELINE
-            // software-pipelined: the next round's entry is requested before this round's is evaluated
-            int4 e0 = make_int4(0, 0, 0, 0), e1 = e0, e2 = e0;
-            if (head.z + sl < head.w) { const int4 *src = (const int4 *) &S.cross[head.z + sl]; e0 = __ldg(src); e1 = __ldg(src + 1); e2 = __ldg(src + 2); }
-#endif
             for (int base = head.z; base < head.w; base += G) {
                 const int xi = base + sl;
                 bool refuse = false;
                 int foe = -1;
                 double dOn = 0.0;
-#ifdef TSC_CROSS_PIPELINE
-                CrossEntry X;
-                { int4 *dst = (int4 *) &X; dst[0] = e0; dst[1] = e1; dst[2] = e2; }
-                if (xi + G < head.w) { const int4 *src = (const int4 *) &S.cross[xi + G]; e0 = __ldg(src); e1 = __ldg(src + 1); e2 = __ldg(src + 2); }
-                if (xi < head.w) {
-                    dOn = X.dist;
-                    if (!(dOn < dts)) refuse = !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe);
-                }
-#else
                 if (xi < head.w) {
                     // (a per-tick "could this link announce a vehicle at all" bit per lane-link, tested before the entry is
                     // loaded, was measured: the cross phase got 1.2 k cycles per tick shorter, computing the bits cost 2.5 k)
                     CrossEntry X;
                     const int4 *src = (const int4 *) &S.cross[xi];
                     int4 *dst = (int4 *) &X;
-                    dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);      // (L1::no_allocate loads measured slower: 0.762 vs 0.742 ms)
+                    dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);      // (measured slower: L1::no_allocate loads, 0.762 vs 0.742 ms;
+                    // requesting the next round's entry before this one is evaluated, 0.706 vs 0.685)
                     dOn = X.dist;
                     if (!(dOn < dts)) refuse = !can_pass<ONE_T>(S, c, i, T, t1, X, dts, &foe);
                 }
-#endif
                 const unsigned m = __ballot_sync(gm, refuse) & gm;
                 if (m) {
                     const int src_lane = __ffs(m) - 1;
@@ -2069,11 +2055,15 @@ static void host_finish_replica(HostPath *H, int b) {
         const int n = S.n_in_total;
         if (S.pk_mode) {
             const u32 *nw = (const u32 *) np, *ow = (const u32 *) op;
-            for (int i = 0; i < n; ++i) {
-                const u32 v = nw[i];
-                if (v != ow[i] && dst[i] >= 0) {
-                    float *d = ob + dst[i];
-                    d[0] = (float) (v & 255u); d[1] = (float) ((v >> 8) & 255u); d[2] = (float) ((v >> 16) & 255u);
+            for (int i0 = 0; i0 < n; i0 += 4) {      // most lanes keep their values from one step to the next: four at a time
+                const int i1 = i0 + 4 < n ? i0 + 4 : n;
+                if (i1 - i0 == 4 && memcmp(nw + i0, ow + i0, 16) == 0) continue;
+                for (int i = i0; i < i1; ++i) {
+                    const u32 v = nw[i];
+                    if (v != ow[i] && dst[i] >= 0) {
+                        float *d = ob + dst[i];
+                        d[0] = (float) (v & 255u); d[1] = (float) ((v >> 8) & 255u); d[2] = (float) ((v >> 16) & 255u);
+                    }
                 }
             }
         } else {
@@ -2095,11 +2085,13 @@ static void host_finish_replica(HostPath *H, int b) {
     if (H->reward) memcpy(H->reward + (size_t) b * A, np + S.pk_o_reward, (size_t) A * 4);
     if (H->rg) H->rg[b] = *(const float *) (np + S.pk_o_rg);
     if (H->mask) {
-        const u32 *bits = (const u32 *) (np + S.pk_o_mask);
+        const u32 *bits = (const u32 *) (np + S.pk_o_mask), *obits = (const u32 *) (op + S.pk_o_mask);
         const int na = S.n_actions;
         u8 *m = H->mask + (size_t) b * A * na;
+        const bool first = H->seq <= 2;      // (the two packet buffers start zeroed, the caller's mask array does not)
         for (int sg = 0; sg < A; ++sg, m += na) {
             const u32 x = bits[sg];
+            if (!first && x == obits[sg]) continue;
             int p = 0;
             for (; p + 8 <= na; p += 8) memcpy(m + p, &H->mask_lut[(x >> p) & 255u], 8);
             for (; p < na; ++p) m[p] = (u8) ((x >> p) & 1u);
@@ -2995,7 +2987,8 @@ int tsc_host_register(tsc_handle E, float *obs_host, float *reward_host, uint8_t
     H->nthreads = E->host_threads_req > 0 ? E->host_threads_req : host_thread_count();
     const int ngroups = (E->B + HOST_GROUP - 1) / HOST_GROUP;
     if (H->nthreads > ngroups) H->nthreads = ngroups;
-    for (int w = 1; w < H->nthreads; ++w) H->threads.emplace_back(host_worker_main, H, w);
+    // the workers finish ALL rows; the caller only launches and waits (between _begin and _wait it is busy with its policy)
+    for (int w = 0; w < H->nthreads; ++w) H->threads.emplace_back(host_worker_main, H, w);
     return 0;
 }
 
@@ -3046,11 +3039,11 @@ int tsc_env_step_registered_wait(tsc_handle E) {
     CUDA_TRY(cudaSetDevice(E->device));
     cudaStream_t sc = E->host_compute;
     H->pending = false;
-    host_work(H, 0, H->seq);      // the caller is worker 0
     unsigned spins = 0;
-    while (H->done.load(std::memory_order_acquire) < H->nthreads - 1) {
+    while (H->done.load(std::memory_order_acquire) < H->nthreads) {
         __builtin_ia32_pause();
-        if ((++spins & 0x3FFF) == 0 && !H->failed.load() && cudaStreamQuery(sc) != cudaErrorNotReady) {
+        if ((++spins & 0x3F) == 0) sched_yield();      // (the workers may share this thread's core)
+        if ((spins & 0x3FFF) == 0 && !H->failed.load() && cudaStreamQuery(sc) != cudaErrorNotReady) {
             // the launch is over (or failed): flags that are still missing will never come
             bool missing = false;
             for (int b = 0; b < E->B && !missing; ++b) missing = __atomic_load_n(&H->flags[b], __ATOMIC_ACQUIRE) != H->seq;

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nproc; nvidia-smi -L | head -8
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/scale_ref_$N.json 2> gpurun_out/scale_ref_$N.err; tail -c 400 gpurun_out/scale_ref_$N.json
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 200 --warmup 20 > gpurun_out/scale_long_$N.json 2> gpurun_out/scale_long_$N.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps ${LONG_STEPS:-200} --warmup 20 > gpurun_out/scale_long_$N.json 2> gpurun_out/scale_long_$N.err
 python - <<PY
 import json
 for f in ("scale_$N", "scale_long_$N"):
