@@ -346,7 +346,7 @@ class Engine:
         self._check(self.lib.tsc_counters(self.h, *[_np_ptr(out[k]) for k in ("tick", "n_running", "n_finished", "n_slots")]))
         return out
 
-    PHASES = ("stage_in", "prologue", "spawn", "phase1a", "phase1b", "phase1c", "phase2", "leave", "enter", "compact",
+    PHASES = ("stage_in", "prologue", "spawn", "retrieve_lanes", "decisions", "retrieve_signals", "cross", "leave", "enter", "compact",
               "retrieve", "stage_out", "n_heads", "n_zone", "n_cross", "n_movers")
 
     def debug_timing(self, enable=True):

@@ -1320,6 +1320,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         if (O.lane_meas64) { O.lane_meas64[2 * o] = occ; O.lane_meas64[2 * o + 1] = ms; }
     }
     __syncthreads();
+    pt_mark(c, PT_PHASE1A);      // (debug timing: retrieve, lane sums)
     if (pkst) {      // per incoming lane, in observation-row order, the three values the row shows (observations.py:313-321)
         for (int i = tid; i < S.n_in_total; i += NT) {
             const u32 e = __ldg(S.pk_lane + i);
@@ -1417,6 +1418,7 @@ __device__ void retrieve(const DevScn &S, const Layout &Y, Ctx &c, const StepArg
         }
     }
     __syncthreads();
+    pt_mark(c, PT_PHASE1C);      // (debug timing: retrieve, per-signal block)
 
     // --- position-matrix observation rows (observations.py:140-160; :72-88 drops window entries <= 0, so a lane's block has
     //     variable length and later lanes shift left): a thread per incoming lane.  Each counts the entries of the lanes

@@ -2,6 +2,7 @@
 # One full GPU-box visit: whole GPU suite, compute-sanitizer over the kernel variants, bench (both arms), ncu launch list and one
 # full capture of the step kernel at the loaded state, the other BASELINE configs.
 mkdir -p gpurun_out
+timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
 timeout 1500 bash tools/gpu_sanitize.sh > gpurun_out/sanitize.log 2>&1; cat gpurun_out/sanitizer/summary.txt | cut -c1-60,200-330
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1200 gpurun_out/bench.json; tail -3 gpurun_out/bench.err

@@ -22,11 +22,14 @@ run ctl_greedy        "X=1" --capacity 600 --controller greedy
 run ctl_sotl          "X=1" --capacity 600 --controller sotl
 fi
 run t256x4_fixed672   "X=1" --capacity 640
+run gmem1024_hybrid   "TSC_B200_GMEM=1" --capacity 600
+run gmem1024_global   "TSC_B200_GMEM=1 TSC_B200_GMEM_META_SHARED=0" --capacity 600
+run registered_host   "X=1" --capacity 640 --registered
+if [ -z "$SANITIZE_SHORT" ]; then
 run t256x4_generic    "X=1" --capacity 600
 run t256x3_fixed1184  "X=1" --capacity 1150
 run t384x2_fixed1568  "X=1" --capacity 1530
 run t512              "X=1" --capacity 2000
-run gmem1024          "TSC_B200_GMEM=1" --capacity 600
 run ctl_max_pressure  "X=1" --capacity 600 --controller max_pressure --obs position_matrix
-run registered_host   "X=1" --capacity 640 --registered
+fi
 cat $out/summary.txt

@@ -43,7 +43,7 @@ tot = sum(cyc.values())
 info = eng.kernel_info()
 print(f"cap {cap} B {B} kernel {info}  {1e3 * wall / N:.3f} ms/step (with timing on)  running {int(bufs['sim'][0,0])}")
 per = B * N
-TICK = ("spawn", "phase1a", "phase1b", "phase1c", "phase2", "count_scan", "newslot", "scatter")
+TICK = ("spawn", "decisions", "cross", "leave", "enter")
 for k, v in cyc.items():
     print(f"  {k:11s} {100 * v / tot:5.1f}%  {v / per:9.0f} cycles / replica-step" + (f"  ({v / per / 5:7.0f} / tick)" if k in TICK else ""))
 print(f"  total       {tot / per:9.0f} cycles / replica-step")
