@@ -368,6 +368,9 @@ def bind_to_rank_cpu_slice(local_rank, local_world):
         per = len(cores) // local_world
         if per < 1:
             return None
+        cap = int(os.environ.get("BENCH_CORES_PER_RANK", "0"))      # (experiments: a denser host than this one)
+        if cap > 0:
+            per = min(per, cap)
         mine = [c for core in cores[local_rank * per:(local_rank + 1) * per] for c in core]
         os.sched_setaffinity(0, mine)
         return f"rank slice: {len(mine)} of {len(allowed)} cpus ({per} cores)"
@@ -569,11 +572,12 @@ def run_gpu_arm(args):
     # of one half overlap the launch of the other (every half's actions still follow its own previous observations).
     n_half = 1 if (args.e2e_halves < 2 or B < 2) else 2
     sizes = [B] if n_half == 1 else [B // 2, B - B // 2]
-    # row-finishing workers: this process's CPUs (its rank slice, if it has one) minus one for the policy thread
+    # row-finishing workers: one per CPU of this process (its rank slice, if it has one), split between the halves; they sleep
+    # between steps and hand groups of replicas out dynamically, so the policy thread joins in whenever it waits
     my_cpus = len(os.sched_getaffinity(0))
     if "rank slice" not in str(affinity):
         my_cpus //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    threads = int(os.environ.get("TSC_B200_HOST_THREADS", "0")) or max(1, min(8, my_cpus - 1))
+    threads = int(os.environ.get("TSC_B200_HOST_THREADS", "0")) or max(1, min(8, my_cpus))
     threads_per_half = max(1, threads // n_half)
     halves = []
     for hb in sizes:

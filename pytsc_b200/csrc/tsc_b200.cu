@@ -25,6 +25,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <sys/prctl.h>
+#include <time.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -2038,7 +2040,11 @@ struct HostPath {
     u32 job_seq = 0;          // guarded by mu: the step the workers should process
     bool quit = false;
     bool pending = false;     // a step begun and not yet waited for
-    std::atomic<int> done{0};
+    // work sharing: groups of HOST_GROUP replicas are claimed one at a time by whoever has time (the workers, and the caller
+    // while it waits); both words carry the step's sequence number in their upper half, so a straggler of the previous step
+    // can neither claim nor count anything of this one
+    std::atomic<uint64_t> claim{0};           // (seq << 32) | next group to hand out
+    std::atomic<uint64_t> groups_done{0};     // (seq << 32) | groups finished
     std::atomic<int> failed{0};
     uint64_t mask_lut[256];   // byte k of entry x = bit k of x
 };
@@ -2057,16 +2063,33 @@ static void host_finish_replica(HostPath *H, int b) {
         const int n = S.n_in_total;
         if (S.pk_mode) {
             const u32 *nw = (const u32 *) np, *ow = (const u32 *) op;
-            for (int i0 = 0; i0 < n; i0 += 4) {      // most lanes keep their values from one step to the next: four at a time
+            // pass 1: which lanes changed (most keep their values from one step to the next: four at a time); the row
+            // lines they live in are requested for writing all at once -- the arrays are far larger than the caches, and one
+            // miss after the other was most of this function's time.  pass 2: the writes.
+            int changed[512];
+            int nc = 0;
+            for (int i0 = 0; i0 < n; i0 += 4) {
                 const int i1 = i0 + 4 < n ? i0 + 4 : n;
                 if (i1 - i0 == 4 && memcmp(nw + i0, ow + i0, 16) == 0) continue;
                 for (int i = i0; i < i1; ++i) {
-                    const u32 v = nw[i];
-                    if (v != ow[i] && dst[i] >= 0) {
-                        float *d = ob + dst[i];
-                        d[0] = (float) (v & 255u); d[1] = (float) ((v >> 8) & 255u); d[2] = (float) ((v >> 16) & 255u);
+                    if (nw[i] != ow[i] && dst[i] >= 0) {
+                        if (nc == 512) {      // (more than 512 changed lanes in one replica: flush)
+                            for (int k = 0; k < nc; ++k) {
+                                const u32 v = nw[changed[k]];
+                                float *d = ob + dst[changed[k]];
+                                d[0] = (float) (v & 255u); d[1] = (float) ((v >> 8) & 255u); d[2] = (float) ((v >> 16) & 255u);
+                            }
+                            nc = 0;
+                        }
+                        __builtin_prefetch(ob + dst[i], 1);
+                        changed[nc++] = i;
                     }
                 }
+            }
+            for (int k = 0; k < nc; ++k) {
+                const u32 v = nw[changed[k]];
+                float *d = ob + dst[changed[k]];
+                d[0] = (float) (v & 255u); d[1] = (float) ((v >> 8) & 255u); d[2] = (float) ((v >> 16) & 255u);
             }
         } else {
             const u32 *nw = (const u32 *) np, *ow = (const u32 *) op;      // compared as bit patterns
@@ -2101,27 +2124,39 @@ static void host_finish_replica(HostPath *H, int b) {
     }
 }
 
-static void host_work(HostPath *H, int w, u32 seq) {
-    const int B = H->E->B, ngroups = (B + HOST_GROUP - 1) / HOST_GROUP;
+static void host_work(HostPath *H, u32 seq) {
+    const int B = H->E->B;
+    const u32 ngroups = (u32) ((B + HOST_GROUP - 1) / HOST_GROUP);
     const auto t0 = std::chrono::steady_clock::now();
-    for (int g = w; g < ngroups; g += H->nthreads) {
+    for (;;) {
+        uint64_t v = H->claim.load(std::memory_order_acquire);
+        for (;;) {
+            if ((u32) (v >> 32) != seq || (u32) v >= ngroups) return;      // another step's turn, or nothing left to hand out
+            if (H->claim.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel)) break;
+        }
+        const int g = (int) (u32) v;
         const int b1 = std::min(B, (g + 1) * HOST_GROUP);
         for (int b = g * HOST_GROUP; b < b1; ++b) {
             unsigned spins = 0;
             while (__atomic_load_n(&H->flags[b], __ATOMIC_ACQUIRE) != seq) {
-                __builtin_ia32_pause();
-                if ((++spins & 0x3FF) == 0) sched_yield();      // (two handles in flight, or ranks sharing cores: let the others run)
-                if ((spins & 0xFFFF) == 0) {
+                // a short spin covers the gaps inside a running launch; a launch that has not started yet (the other handle's is
+                // still running, or the stream is busy) is waited for asleep, so that the core goes to the policy thread or to the
+                // workers of the handle whose packets ARE arriving
+                if (++spins < 512) __builtin_ia32_pause();
+                else { struct timespec ts = {0, 15000}; nanosleep(&ts, nullptr); }
+                if ((spins & 0x3FF) == 0) {
                     if (H->failed.load(std::memory_order_relaxed)) return;
                     if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) { H->failed.store(2); return; }
                 }
             }
             host_finish_replica(H, b);
         }
+        H->groups_done.fetch_add(1, std::memory_order_release);
     }
 }
 
-static void host_worker_main(HostPath *H, int w) {
+static void host_worker_main(HostPath *H) {
+    prctl(PR_SET_TIMERSLACK, 2000UL, 0, 0, 0);      // the 15 us naps above are not to be rounded up to the default 50 us slack
     u32 seen = 0;
     for (;;) {
         u32 seq;
@@ -2131,8 +2166,7 @@ static void host_worker_main(HostPath *H, int w) {
             if (H->quit) return;
             seq = seen = H->job_seq;
         }
-        host_work(H, w, seq);
-        H->done.fetch_add(1, std::memory_order_release);
+        host_work(H, seq);
     }
 }
 
@@ -2989,8 +3023,10 @@ int tsc_host_register(tsc_handle E, float *obs_host, float *reward_host, uint8_t
     H->nthreads = E->host_threads_req > 0 ? E->host_threads_req : host_thread_count();
     const int ngroups = (E->B + HOST_GROUP - 1) / HOST_GROUP;
     if (H->nthreads > ngroups) H->nthreads = ngroups;
-    // the workers finish ALL rows; the caller only launches and waits (between _begin and _wait it is busy with its policy)
-    for (int w = 0; w < H->nthreads; ++w) H->threads.emplace_back(host_worker_main, H, w);
+    // the workers finish the rows; the caller launches, and lends a hand while it waits in _wait (its short naps there want
+    // the same fine timer slack as the workers')
+    prctl(PR_SET_TIMERSLACK, 2000UL, 0, 0, 0);
+    for (int w = 0; w < H->nthreads; ++w) H->threads.emplace_back(host_worker_main, H);
     return 0;
 }
 
@@ -3022,9 +3058,10 @@ int tsc_env_step_registered_begin(tsc_handle E, const int32_t *actions_host, int
     a.do_retrieve = 1;
     a.pk = H->pk_dev[H->cur]; a.pk_flags = H->flags_dev; a.pk_seq = H->seq;
     H->failed.store(0);
-    H->done.store(0);
     int rc = launch(E, a, sc);
     if (rc) return rc;
+    H->groups_done.store((uint64_t) H->seq << 32, std::memory_order_release);
+    H->claim.store((uint64_t) H->seq << 32, std::memory_order_release);
     {
         std::lock_guard<std::mutex> lk(H->mu);
         H->job_seq = H->seq;
@@ -3041,11 +3078,13 @@ int tsc_env_step_registered_wait(tsc_handle E) {
     CUDA_TRY(cudaSetDevice(E->device));
     cudaStream_t sc = E->host_compute;
     H->pending = false;
+    host_work(H, H->seq);      // whatever has not been handed out yet
+    const u32 ngroups = (u32) ((E->B + HOST_GROUP - 1) / HOST_GROUP);
     unsigned spins = 0;
-    while (H->done.load(std::memory_order_acquire) < H->nthreads) {
-        __builtin_ia32_pause();
-        if ((++spins & 0x3F) == 0) sched_yield();      // (the workers may share this thread's core)
-        if ((spins & 0x3FFF) == 0 && !H->failed.load() && cudaStreamQuery(sc) != cudaErrorNotReady) {
+    while ((u32) H->groups_done.load(std::memory_order_acquire) < ngroups && !H->failed.load(std::memory_order_relaxed)) {
+        if (++spins < 512) __builtin_ia32_pause();
+        else { struct timespec ts = {0, 5000}; nanosleep(&ts, nullptr); }      // (the workers may share this thread's core)
+        if ((spins & 0x3FF) == 0 && !H->failed.load() && cudaStreamQuery(sc) != cudaErrorNotReady) {
             // the launch is over (or failed): flags that are still missing will never come
             bool missing = false;
             for (int b = 0; b < E->B && !missing; ++b) missing = __atomic_load_n(&H->flags[b], __ATOMIC_ACQUIRE) != H->seq;
