@@ -348,8 +348,9 @@ int64_t tsc_launch_count(tsc_handle h);
 
 /* Debug: per-phase clock64() sums seen by thread 0 of every block since timing was (re)enabled.
  * Copies up to n counters into cycles_out (may be NULL), then enables (zeroing) or disables the
- * instrumentation; returns the number of counters (stage-in, prologue, spawn, getAction 1a / 1b / 1c / 2,
- * count+scan, new slots, scatter, retrieve, stage-out, then four list-length sums).  Syncs.  Only builds made with
+ * instrumentation; returns the number of counters (stage-in, prologue, handleWaiting + look-ahead, retrieve's
+ * lane sums, decisions, retrieve's per-signal block, cross phase, list surgery leave / enter, compaction, rest of
+ * retrieve, stage-out, then four list-length sums).  Syncs.  Only builds made with
  * -DTSC_PHASE_TIMING carry the instrumentation (tools/phase_timing.py makes one); the shipped library answers
  * TSC_EINVAL to enable = 1. */
 int  tsc_debug_timing(tsc_handle h, int32_t enable, uint64_t *cycles_out, int32_t n);
