@@ -421,8 +421,9 @@ class HostFixedTimePolicy:
 
     def act(self, out):
         np = self.np
-        np.take(self.action, self.state, out=out)
-        np.take(self.nxt_state, self.state, out=self.tmp)
+        # (mode="wrap": numpy buffers `out` under the default mode="raise"; the indices are table entries, always in range)
+        np.take(self.action, self.state, out=out, mode="wrap")
+        np.take(self.nxt_state, self.state, out=self.tmp, mode="wrap")
         self.state, self.tmp = self.tmp, self.state
 
 
