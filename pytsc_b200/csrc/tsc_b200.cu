@@ -518,11 +518,6 @@ __device__ __forceinline__ void finish_vehicle(const DevScn &S, const Layout &Y,
         c.pj[i] |= PJ_MOVER;
         atomicAdd((unsigned *) (c.leave + (d & ~3)), 1u << (8 * (d & 3)));
         if (!end) atomicAdd((unsigned *) (c.ent + (dd & ~3)), 1u << (8 * (dd & 3)));
-#ifdef TSC_MOVER_PREFETCH
-        // what the list surgery will read for this mover, on its way into L1 while the other decisions go on
-        if (end) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.veh_tick + c.vid[i]));
-        else asm volatile("prefetch.global.L1 [%0];" ::"l"(S.route_seq + q + 1));
-#endif
         const int k = atomicAdd(mover_counter(c, c.h->tick), 1);
         if (k < Y.ent_cap) {
             c.mv_slot[k] = (u16) i; c.mv_to[k] = end ? (u16) NONE16 : (u16) dd; c.mv_q[k] = q; c.mv_pj[k] = hops > 1 ? 1 : 0;
@@ -666,11 +661,7 @@ __device__ __forceinline__ void head_look_ahead(const DevScn &S, const Ctx &c, i
     *leader_out = leader; *gap_out = gap;
 }
 
-#ifdef TSC_AB_PLAIN_ERR      // timing experiment only: a plain barrier, then everybody reads the flag (threads could disagree)
-#define TICK_SYNC_ERR(x) (__syncthreads(), (x))
-#else
 #define TICK_SYNC_ERR(x) (__syncthreads_or(x) != 0)
-#endif
 // `frozen`: the replica carries a sticky error (the same answer in every thread: it comes out of a barrier).  Returns
 // that answer as of the end of the tick.
 template <int NT, bool ONE_T>
